@@ -1,0 +1,410 @@
+// Implicit-GEMM convolution / linear layer on Blackwell tensor cores (tcgen05 + TMEM + TMA), bf16 -> fp32.
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * W[cout, tap, cin]
+//   M tile = 128 output pixels arranged as a TH x TW spatial patch of ONE image (TH*TW == 128)
+//   N tile = BLOCK_N output channels, K block = 64 input channels of one filter tap.
+// The A operand of every (tap, cin-chunk) K block is ONE 4-D TMA box {64 ch, TW, TH, 1} of the
+// channels-last activation view, shifted by the tap; TMA zero-fills out-of-bounds coordinates, which
+// is exactly the convolution's zero padding, so no im2col buffer and no predication exist anywhere.
+// The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle = the canonical
+// K-major UMMA operand layout.  Warp roles (persistent CTA, one per SM):
+//   warp 0: TMA producer   warp 1: TMEM alloc + tcgen05.mma issuer   warps 2-5: epilogue
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// Replaces the cuDNN/cuBLAS calls detectron2 makes for ResNet/FPN/RPN/box-head layers
+// (reached from aldi/trainer.py:87, aldi/distill.py:157,162, aldi/pseudolabeler.py:21).
+#include "common.cuh"
+#include "sm100.cuh"
+#include "tmap.h"
+#include "../../include/aldi_b200.h"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // bf16 elements = 128 B = swizzle span
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kNumThreads = 192;
+
+struct ConvArgs {
+  int n, ho, wo;
+  int tiles_h, tiles_w, th, tw, tw_shift;
+  int num_n_tiles, num_tiles;
+  int kchunks, taps_w, num_kb;
+  int pad_h, pad_w;
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int res_mode;
+  long long res_sw, res_sh, res_sn;
+  const __nv_bfloat16* mask;
+  long long mask_sw, mask_sh, mask_sn;
+  void* out;
+  int out_f32;
+  int cout_store;
+  long long out_sw, out_sh, out_sn;
+  int relu, accumulate;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % a.num_n_tiles;
+        int m_tile = tile / a.num_n_tiles;
+        const int twi = m_tile % a.tiles_w;
+        m_tile /= a.tiles_w;
+        const int thi = m_tile % a.tiles_h;
+        const int img = m_tile / a.tiles_h;
+        const int h0 = thi * a.th, w0 = twi * a.tw;
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+          const int r = tap / a.taps_w, s = tap - r * a.taps_w;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, w0 + s - a.pad_w, h0 + r - a.pad_h, img);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % a.num_n_tiles;
+      int m_tile = tile / a.num_n_tiles;
+      const int twi = m_tile % a.tiles_w;
+      m_tile /= a.tiles_w;
+      const int thi = m_tile % a.tiles_h;
+      const int img = m_tile / a.tiles_h;
+      const int h = thi * a.th + (row >> a.tw_shift);
+      const int w = twi * a.tw + (row & (a.tw - 1));
+      const bool valid = (h < a.ho) && (w < a.wo);
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const long long out_off = (long long)img * a.out_sn + (long long)h * a.out_sh + (long long)w * a.out_sw;
+      long long res_off = 0, mask_off = 0;
+      if (a.res_mode == 1)
+        res_off = (long long)img * a.res_sn + (long long)h * a.res_sh + (long long)w * a.res_sw;
+      else if (a.res_mode == 2)
+        res_off = (long long)img * a.res_sn + (long long)(h >> 1) * a.res_sh + (long long)(w >> 1) * a.res_sw;
+      if (a.mask) mask_off = (long long)img * a.mask_sn + (long long)h * a.mask_sh + (long long)w * a.mask_sw;
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), raw);
+        tmem_ld_wait();
+        const int cbase = n_tile * BLOCK_N + c0;
+        if (valid && cbase < a.cout_store) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (a.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= __ldg(a.scale + cbase + j);
+          }
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cbase + j);
+          }
+          if (a.res_mode) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + res_off + cbase);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              unpack_bf16x8(__ldg(rp + g), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (a.mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + mask_off + cbase);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              unpack_bf16x8(__ldg(mp + g), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] = (f[j] > 0.f) ? v[g * 8 + j] : 0.f;
+            }
+          }
+          if (a.out_f32) {
+            float* op = reinterpret_cast<float*>(a.out) + out_off + cbase;
+            if (cbase + 32 <= a.cout_store && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                if (a.accumulate) {
+                  float4 old = reinterpret_cast<float4*>(op)[g];
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                reinterpret_cast<float4*>(op)[g] = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < a.cout_store) op[j] = a.accumulate ? op[j] + v[j] : v[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + out_off + cbase;
+            if (cbase + 32 <= a.cout_store) {
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (a.accumulate) {
+                  float f[8];
+                  unpack_bf16x8(o4[g], f);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+                }
+                o4[g] = pack_bf16x8(v + g * 8);
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < a.cout_store) {
+                  float o = v[j];
+                  if (a.accumulate) o += __bfloat162float(op[j]);
+                  op[j] = __float2bfloat16_rn(o);
+                }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) {
+      aldi_set_error("aldi_conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return ALDI_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  int grid = a.num_tiles < aldi_num_sms() ? a.num_tiles : aldi_num_sms();
+  conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_conv_tc");
+  return ALDI_OK;
+}
+
+// spatial patch (TH x TW = 128) that wastes the fewest pixels for an (ho, wo) output
+void pick_patch(int ho, int wo, int* th, int* tw) {
+  long best = -1;
+  for (int t = 128; t >= 8; t >>= 1) {
+    int hh = 128 / t;
+    long cover = (long)((wo + t - 1) / t) * t * (long)((ho + hh - 1) / hh) * hh;
+    if (best < 0 || cover < best) {
+      best = cover;
+      *tw = t;
+      *th = hh;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(p && p->x && p->w && p->out, "aldi_conv_tc: null pointer");
+  ALDI_CHECK_ARG(p->x_c > 0 && p->x_c % 64 == 0, "aldi_conv_tc: x_c=%d must be a positive multiple of 64", p->x_c);
+  ALDI_CHECK_ARG(p->cout_p > 0 && p->cout_p % 64 == 0, "aldi_conv_tc: cout_p=%d must be a multiple of 64", p->cout_p);
+  ALDI_CHECK_ARG(p->cout_store > 0 && p->cout_store <= p->cout_p, "aldi_conv_tc: bad cout_store");
+  ALDI_CHECK_ARG(p->n > 0 && p->ho > 0 && p->wo > 0, "aldi_conv_tc: empty output");
+  ALDI_CHECK_ARG(p->taps_h > 0 && p->taps_w > 0 && p->taps_h * p->taps_w <= 64, "aldi_conv_tc: bad taps");
+  ALDI_CHECK_ARG(p->stride <= 1, "aldi_conv_tc: stride %d unsupported, pass a strided view of x", p->stride);
+  ALDI_CHECK_ARG((p->x_sw % 8) == 0 && (p->x_sh % 8) == 0 && (p->x_sn % 8) == 0,
+                 "aldi_conv_tc: activation strides must be multiples of 8 elements (16 B)");
+  ALDI_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
+                 "aldi_conv_tc: x/w must be 16-byte aligned");
+  if (p->out_dtype == ALDI_DTYPE_BF16) {
+    ALDI_CHECK_ARG((p->out_sw % 8) == 0 && (p->out_sh % 8) == 0 && (p->out_sn % 8) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p->out) & 15) == 0,
+                   "aldi_conv_tc: bf16 output must be 16-byte aligned with strides multiple of 8");
+  }
+  if (p->res_mode) {
+    ALDI_CHECK_ARG(p->residual && (p->res_sw % 8) == 0 && (p->res_sh % 8) == 0 && (p->res_sn % 8) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p->residual) & 15) == 0,
+                   "aldi_conv_tc: residual must be 16-byte aligned with strides multiple of 8");
+  }
+  if (p->mask) {
+    ALDI_CHECK_ARG((p->mask_sw % 8) == 0 && (p->mask_sh % 8) == 0 && (p->mask_sn % 8) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p->mask) & 15) == 0,
+                   "aldi_conv_tc: mask must be 16-byte aligned with strides multiple of 8");
+  }
+
+  int block_n = (p->cout_p % 256 == 0) ? 256 : (p->cout_p % 128 == 0) ? 128 : 64;
+  int th, tw;
+  pick_patch(p->ho, p->wo, &th, &tw);
+
+  ConvArgs a;
+  a.n = p->n; a.ho = p->ho; a.wo = p->wo;
+  a.th = th; a.tw = tw;
+  a.tw_shift = 0;
+  while ((1 << a.tw_shift) < tw) ++a.tw_shift;
+  a.tiles_h = aldi_div_up(p->ho, th);
+  a.tiles_w = aldi_div_up(p->wo, tw);
+  a.num_n_tiles = p->cout_p / block_n;
+  a.num_tiles = p->n * a.tiles_h * a.tiles_w * a.num_n_tiles;
+  a.kchunks = p->x_c / 64;
+  a.taps_w = p->taps_w;
+  a.num_kb = p->taps_h * p->taps_w * a.kchunks;
+  a.pad_h = p->pad_h; a.pad_w = p->pad_w;
+  a.scale = p->scale; a.bias = p->bias;
+  a.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
+  a.res_mode = p->res_mode;
+  a.res_sw = p->res_sw; a.res_sh = p->res_sh; a.res_sn = p->res_sn;
+  a.mask = reinterpret_cast<const __nv_bfloat16*>(p->mask);
+  a.mask_sw = p->mask_sw; a.mask_sh = p->mask_sh; a.mask_sn = p->mask_sn;
+  a.out = p->out;
+  a.out_f32 = (p->out_dtype == ALDI_DTYPE_F32);
+  a.cout_store = p->cout_store;
+  a.out_sw = p->out_sw; a.out_sh = p->out_sh; a.out_sn = p->out_sn;
+  a.relu = p->relu; a.accumulate = p->accumulate;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p->x_c, (uint64_t)p->x_w, (uint64_t)p->x_h, (uint64_t)p->x_n};
+    uint64_t strides[3] = {(uint64_t)p->x_sw * 2, (uint64_t)p->x_sh * 2, (uint64_t)p->x_sn * 2};
+    uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+    int rc = aldi_make_tmap_bf16(&tmA, p->x, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t ktot = (uint64_t)p->taps_h * p->taps_w * p->x_c;
+    uint64_t dims[2] = {ktot, (uint64_t)p->cout_p};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)block_n};
+    int rc = aldi_make_tmap_bf16(&tmB, p->w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  switch (block_n) {
+    case 256: return launch_conv<256>(tmA, tmB, a, stream);
+    case 128: return launch_conv<128>(tmA, tmB, a, stream);
+    default: return launch_conv<64>(tmA, tmB, a, stream);
+  }
+}

@@ -1,0 +1,167 @@
+// Flat-buffer parameter kernels: EMA teacher update, SGD-momentum step, weight packing for the conv paths.
+// All are pure HBM-bandwidth kernels: 128-bit accesses, grid sized to a multiple of the SM count.
+#include "common.cuh"
+#include "../../include/aldi_b200.h"
+
+namespace {
+
+// ---- EMA: aldi/ema.py:43-46  new_t = student * (1 - alpha) + teacher * alpha ------------------------
+// torch evaluates this as three separate fp32 kernels (mul, mul, add), so no FMA contraction: use the
+// explicitly rounded intrinsics to stay bit-identical with the reference expression.
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ t, const float* __restrict__ s, size_t n4,
+                                                  size_t n, float a, float oma) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float4* t4 = reinterpret_cast<float4*>(t);
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+  for (size_t k = i; k < n4; k += stride) {
+    float4 tv = t4[k];
+    const float4 sv = __ldg(s4 + k);
+    tv.x = __fadd_rn(__fmul_rn(sv.x, oma), __fmul_rn(tv.x, a));
+    tv.y = __fadd_rn(__fmul_rn(sv.y, oma), __fmul_rn(tv.y, a));
+    tv.z = __fadd_rn(__fmul_rn(sv.z, oma), __fmul_rn(tv.z, a));
+    tv.w = __fadd_rn(__fmul_rn(sv.w, oma), __fmul_rn(tv.w, a));
+    t4[k] = tv;
+  }
+  for (size_t k = n4 * 4 + i; k < n; k += stride) t[k] = __fadd_rn(__fmul_rn(s[k], oma), __fmul_rn(t[k], a));
+}
+
+// ---- SGD momentum (torch.optim.SGD, dampening 0, nesterov off) ------------------------------------
+//   g = grad*grad_scale + wd*p ; m = mom*m + g ; p = p - lr*m ; optional fused EMA of the new p
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, float* __restrict__ m, const float* __restrict__ g, size_t n4, size_t n, float lr,
+           float wd, float mom, float gscale, float* __restrict__ teacher, float a, float oma) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* t4 = reinterpret_cast<float4*>(teacher);
+  auto upd = [&](float& pv, float& mv, float gv) {
+    gv = __fadd_rn(__fmul_rn(gv, gscale), __fmul_rn(wd, pv));
+    mv = __fadd_rn(__fmul_rn(mv, mom), gv);
+    pv = __fadd_rn(pv, __fmul_rn(-lr, mv));
+  };
+  for (size_t k = i; k < n4; k += stride) {
+    float4 pv = p4[k], mv = m4[k];
+    const float4 gv = __ldg(g4 + k);
+    upd(pv.x, mv.x, gv.x); upd(pv.y, mv.y, gv.y); upd(pv.z, mv.z, gv.z); upd(pv.w, mv.w, gv.w);
+    p4[k] = pv;
+    m4[k] = mv;
+    if (teacher) {
+      float4 tv = t4[k];
+      tv.x = __fadd_rn(__fmul_rn(pv.x, oma), __fmul_rn(tv.x, a));
+      tv.y = __fadd_rn(__fmul_rn(pv.y, oma), __fmul_rn(tv.y, a));
+      tv.z = __fadd_rn(__fmul_rn(pv.z, oma), __fmul_rn(tv.z, a));
+      tv.w = __fadd_rn(__fmul_rn(pv.w, oma), __fmul_rn(tv.w, a));
+      t4[k] = tv;
+    }
+  }
+  for (size_t k = n4 * 4 + i; k < n; k += stride) {
+    float pv = p[k], mv = m[k];
+    upd(pv, mv, g[k]);
+    p[k] = pv;
+    m[k] = mv;
+    if (teacher) teacher[k] = __fadd_rn(__fmul_rn(pv, oma), __fmul_rn(teacher[k], a));
+  }
+}
+
+// ---- weight packing -------------------------------------------------------------------------------
+// forward operand:  out[co][t][ci] (cout_p x taps x cin_p, zero padded)  = w[co][t][ci]
+template <typename T>
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ w, T* __restrict__ out, int cout,
+                                                       int taps, int cin, int cout_p, int cin_p) {
+  const size_t total = (size_t)cout_p * taps * cin_p;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_p);
+    size_t r = i / cin_p;
+    const int t = (int)(r % taps);
+    const int co = (int)(r / taps);
+    float v = 0.f;
+    if (co < cout && ci < cin) v = __ldg(w + ((size_t)co * taps + t) * cin + ci);
+    out[i] = from_f32<T>(v);
+  }
+}
+// data-gradient operand: out[ci][taps-1-t][co] (cin_p x taps x cout_p) = w[co][t][ci] * scale[co]
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ scale, T* __restrict__ out, int cout,
+                  int taps, int cin, int cout_p, int cin_p) {
+  const size_t total = (size_t)cin_p * taps * cout_p;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout_p);
+    size_t r = i / cout_p;
+    const int tf = (int)(r % taps);
+    const int ci = (int)(r / taps);
+    float v = 0.f;
+    if (co < cout && ci < cin) {
+      v = __ldg(w + ((size_t)co * taps + (taps - 1 - tf)) * cin + ci);
+      if (scale) v *= __ldg(scale + co);
+    }
+    out[i] = from_f32<T>(v);
+  }
+}
+
+int grid_for(size_t work_items, int threads) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  size_t cap = (size_t)aldi_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int aldi_ema_update(float* teacher, const float* student, size_t n, double alpha, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(teacher && student, "aldi_ema_update: null pointer");
+  if (n == 0) return ALDI_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(teacher) | reinterpret_cast<uintptr_t>(student)) & 15) == 0;
+  const size_t n4 = aligned ? n / 4 : 0;
+  ema_kernel<<<grid_for(n4 ? n4 : n, 256), 256, 0, stream>>>(teacher, student, n4, n, (float)alpha,
+                                                              (float)(1.0 - alpha));
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_ema_update");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_sgd_momentum_step(float* params, float* momentum_buf, const float* grads, size_t n, float lr,
+                                      float weight_decay, float momentum, float grad_scale, float* teacher,
+                                      double ema_alpha, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(params && momentum_buf && grads, "aldi_sgd_momentum_step: null pointer");
+  if (n == 0) return ALDI_OK;
+  uintptr_t al = reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(momentum_buf) |
+                 reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(teacher);
+  const size_t n4 = (al & 15) == 0 ? n / 4 : 0;
+  sgd_kernel<<<grid_for(n4 ? n4 : n, 256), 256, 0, stream>>>(params, momentum_buf, grads, n4, n, lr, weight_decay,
+                                                              momentum, grad_scale, teacher, (float)ema_alpha,
+                                                              (float)(1.0 - ema_alpha));
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_sgd_momentum_step");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_pack_weight(const float* w, const float* scale, void* out, int out_dtype, int dgrad, int cout,
+                                int taps, int cin, int cout_p, int cin_p, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(w && out, "aldi_pack_weight: null pointer");
+  ALDI_CHECK_ARG(cout > 0 && taps > 0 && cin > 0 && cout_p >= cout && cin_p >= cin, "aldi_pack_weight: bad dims");
+  const size_t total = (size_t)cout_p * taps * cin_p;
+  const int grid = grid_for(total, 256);
+  if (out_dtype == ALDI_DTYPE_BF16) {
+    if (dgrad)
+      pack_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, scale, (__nv_bfloat16*)out, cout, taps, cin,
+                                                                  cout_p, cin_p);
+    else
+      pack_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, (__nv_bfloat16*)out, cout, taps, cin, cout_p, cin_p);
+  } else {
+    if (dgrad)
+      pack_dgrad_kernel<float><<<grid, 256, 0, stream>>>(w, scale, (float*)out, cout, taps, cin, cout_p, cin_p);
+    else
+      pack_fwd_kernel<float><<<grid, 256, 0, stream>>>(w, (float*)out, cout, taps, cin, cout_p, cin_p);
+  }
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_pack_weight");
+  return ALDI_OK;
+}

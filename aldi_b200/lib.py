@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI library (include/aldi_b200.h).
+
+The library is the product's compute path; there is NO CPU or PyTorch fallback: if the shared object is
+missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaldi_b200.so")
+
+F32, BF16 = 0, 1
+
+c_void_p, c_int, c_ll, c_float, c_double, c_size_t = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_size_t)
+
+
+class ConvParams(ctypes.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("x_c", c_int), ("x_w", c_int), ("x_h", c_int), ("x_n", c_int),
+        ("x_sw", c_ll), ("x_sh", c_ll), ("x_sn", c_ll),
+        ("w", c_void_p), ("cout_p", c_int),
+        ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int), ("stride", c_int),
+        ("n", c_int), ("ho", c_int), ("wo", c_int),
+        ("scale", c_void_p), ("bias", c_void_p),
+        ("residual", c_void_p), ("res_mode", c_int), ("res_sw", c_ll), ("res_sh", c_ll), ("res_sn", c_ll),
+        ("mask", c_void_p), ("mask_sw", c_ll), ("mask_sh", c_ll), ("mask_sn", c_ll),
+        ("out", c_void_p), ("out_dtype", c_int), ("cout_store", c_int),
+        ("out_sw", c_ll), ("out_sh", c_ll), ("out_sn", c_ll),
+        ("relu", c_int), ("accumulate", c_int),
+    ]
+
+
+class WgradParams(ctypes.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("x_c", c_int), ("x_w", c_int), ("x_h", c_int), ("x_n", c_int),
+        ("x_sw", c_ll), ("x_sh", c_ll), ("x_sn", c_ll),
+        ("dy", c_void_p), ("dy_c", c_int), ("dy_sw", c_ll), ("dy_sh", c_ll), ("dy_sn", c_ll),
+        ("n", c_int), ("ho", c_int), ("wo", c_int),
+        ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int), ("stride", c_int),
+        ("scale", c_void_p), ("dw", c_void_p), ("cout_store", c_int), ("cin_store", c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/aldi_b200.h must appear here
+SIGNATURES = {
+    "aldi_last_error": (ctypes.c_char_p, []),
+    "aldi_abi_version": (c_int, []),
+    "aldi_launch_count": (ctypes.c_ulonglong, []),
+    "aldi_reset_launch_count": (None, []),
+    "aldi_ema_update": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p]),
+    "aldi_sgd_momentum_step": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
+                                       c_void_p, c_double, c_void_p]),
+    "aldi_pack_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "aldi_conv_tc": (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
+    "aldi_conv_f32": (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
+    "aldi_wgrad_tc": (c_int, [ctypes.POINTER(WgradParams), c_void_p]),
+    "aldi_wgrad_f32": (c_int, [ctypes.POINTER(WgradParams), c_void_p]),
+}
+
+
+class AldiError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libaldi_b200.so; raise loudly if it has not been built (python -m aldi_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AldiError(
+            "libaldi_b200.so not found at %s: build it with `python -m aldi_b200.build` "
+            "(there is no CPU/PyTorch fallback for the hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().aldi_last_error().decode("utf-8", "replace")
+        raise AldiError("%s failed (rc=%d): %s" % (what or "aldi call", rc, msg))
+
+
+def launch_count():
+    return int(load().aldi_launch_count())
+
+
+def reset_launch_count():
+    load().aldi_reset_launch_count()

@@ -1,0 +1,132 @@
+"""Thin Python wrappers: torch tensors (device memory + strides) -> C-ABI calls on the current CUDA stream.
+
+torch is used for memory and streams only; all arithmetic happens in libaldi_b200.so.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _l
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _l.F32
+    if t.dtype == torch.bfloat16:
+        return _l.BF16
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _cl4(t, what):
+    """(N, H, W, C) view with unit channel stride -> (n, h, w, c, sn, sh, sw)."""
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise ValueError("%s must be a 4-d channels-last view with unit channel stride, got shape %s stride %s"
+                         % (what, tuple(t.shape), tuple(t.stride())))
+    n, h, w, c = t.shape
+    return n, h, w, c, t.stride(0), t.stride(1), t.stride(2)
+
+
+# ---------------------------------------------------------------------------------------------------
+def ema_update(teacher_flat, student_flat, alpha):
+    """aldi/ema.py:32-57 on flat fp32 buffers."""
+    assert teacher_flat.dtype == torch.float32 and student_flat.dtype == torch.float32
+    assert teacher_flat.is_cuda and student_flat.is_cuda and teacher_flat.numel() == student_flat.numel()
+    assert teacher_flat.is_contiguous() and student_flat.is_contiguous()
+    L = _l.load()
+    _l.check(L.aldi_ema_update(_ptr(teacher_flat), _ptr(student_flat), teacher_flat.numel(), float(alpha), _stream()),
+             "aldi_ema_update")
+
+
+def sgd_momentum_step(params, momentum_buf, grads, lr, weight_decay, momentum, grad_scale=1.0, teacher=None,
+                      ema_alpha=0.0):
+    for t in (params, momentum_buf, grads):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    L = _l.load()
+    _l.check(L.aldi_sgd_momentum_step(_ptr(params), _ptr(momentum_buf), _ptr(grads), params.numel(), float(lr),
+                                      float(weight_decay), float(momentum), float(grad_scale), _ptr(teacher),
+                                      float(ema_alpha), _stream()), "aldi_sgd_momentum_step")
+
+
+def pack_weight(w, out, *, dgrad=False, scale=None, cout, taps, cin, cout_p, cin_p):
+    """fp32 master weight (cout, taps, cin) -> padded GEMM operand in `out` (bf16 or fp32)."""
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == cout * taps * cin
+    assert out.is_contiguous() and out.numel() == cout_p * taps * cin_p
+    L = _l.load()
+    _l.check(L.aldi_pack_weight(_ptr(w), _ptr(scale), _ptr(out), _dt(out), int(bool(dgrad)), cout, taps, cin, cout_p,
+                                cin_p, _stream()), "aldi_pack_weight")
+
+
+def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, bias=None, residual=None,
+         res_mode=0, mask=None, relu=False, accumulate=False, cout_store=None):
+    """Implicit-GEMM conv/linear (forward or data-gradient).  x, out, residual, mask are channels-last
+    (N,H,W,C) views; wp is the packed (cout_p, taps*C) operand.  bf16 inputs -> tcgen05 path, fp32 -> CUDA cores."""
+    n, xh, xw, xc, x_sn, x_sh, x_sw = _cl4(x, "x")
+    on, oh, ow, oc, o_sn, o_sh, o_sw = _cl4(out, "out")
+    assert on == n
+    cout_p = wp.shape[0]
+    assert wp.is_contiguous() and wp.numel() == cout_p * taps_h * taps_w * xc, (wp.shape, taps_h, taps_w, xc)
+    assert wp.dtype == x.dtype
+    p = _l.ConvParams()
+    p.x = x.data_ptr(); p.x_c = xc; p.x_w = xw; p.x_h = xh; p.x_n = n
+    p.x_sw = x_sw; p.x_sh = x_sh; p.x_sn = x_sn
+    p.w = wp.data_ptr(); p.cout_p = cout_p
+    p.taps_h = taps_h; p.taps_w = taps_w; p.pad_h = pad_h; p.pad_w = pad_w; p.stride = stride
+    p.n = n; p.ho = oh; p.wo = ow
+    p.scale = scale.data_ptr() if scale is not None else None
+    p.bias = bias.data_ptr() if bias is not None else None
+    if residual is not None:
+        assert res_mode in (1, 2) and residual.dtype == x.dtype
+        rn, rh, rw, rc, r_sn, r_sh, r_sw = _cl4(residual, "residual")
+        p.residual = residual.data_ptr(); p.res_mode = res_mode
+        p.res_sw = r_sw; p.res_sh = r_sh; p.res_sn = r_sn
+    else:
+        p.residual = None; p.res_mode = 0
+    if mask is not None:
+        assert mask.dtype == x.dtype
+        mn, mh, mw, mc, m_sn, m_sh, m_sw = _cl4(mask, "mask")
+        assert (mh, mw) == (oh, ow)
+        p.mask = mask.data_ptr(); p.mask_sw = m_sw; p.mask_sh = m_sh; p.mask_sn = m_sn
+    else:
+        p.mask = None
+    p.out = out.data_ptr(); p.out_dtype = _dt(out)
+    p.cout_store = int(cout_store if cout_store is not None else min(oc, cout_p))
+    assert p.cout_store <= oc
+    p.out_sw = o_sw; p.out_sh = o_sh; p.out_sn = o_sn
+    p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate))
+    L = _l.load()
+    if x.dtype == torch.bfloat16:
+        _l.check(L.aldi_conv_tc(ctypes.byref(p), _stream()), "aldi_conv_tc")
+    else:
+        _l.check(L.aldi_conv_f32(ctypes.byref(p), _stream()), "aldi_conv_f32")
+
+
+def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, cout_store=None,
+          cin_store=None):
+    """dw[co, tap, ci] += scale[co] * sum_pixels dy[pixel, co] * x[pixel shifted by tap, ci]  (fp32 atomics)."""
+    n, xh, xw, xc, x_sn, x_sh, x_sw = _cl4(x, "x")
+    dn, oh, ow, dc, d_sn, d_sh, d_sw = _cl4(dy, "dy")
+    assert dn == n and dy.dtype == x.dtype and dw.dtype == torch.float32 and dw.is_contiguous()
+    p = _l.WgradParams()
+    p.x = x.data_ptr(); p.x_c = xc; p.x_w = xw; p.x_h = xh; p.x_n = n
+    p.x_sw = x_sw; p.x_sh = x_sh; p.x_sn = x_sn
+    p.dy = dy.data_ptr(); p.dy_c = dc; p.dy_sw = d_sw; p.dy_sh = d_sh; p.dy_sn = d_sn
+    p.n = n; p.ho = oh; p.wo = ow
+    p.taps_h = taps_h; p.taps_w = taps_w; p.pad_h = pad_h; p.pad_w = pad_w; p.stride = stride
+    p.scale = scale.data_ptr() if scale is not None else None
+    p.dw = dw.data_ptr()
+    p.cout_store = int(cout_store if cout_store is not None else dc)
+    p.cin_store = int(cin_store if cin_store is not None else xc)
+    assert dw.numel() == p.cout_store * taps_h * taps_w * p.cin_store
+    L = _l.load()
+    if x.dtype == torch.bfloat16:
+        _l.check(L.aldi_wgrad_tc(ctypes.byref(p), _stream()), "aldi_wgrad_tc")
+    else:
+        _l.check(L.aldi_wgrad_f32(ctypes.byref(p), _stream()), "aldi_wgrad_f32")
