@@ -1,0 +1,122 @@
+"""Parameter table of the Faster R-CNN R50-FPN detector the ALDI++ step trains, with Detectron2 state_dict
+key names (so released checkpoints / `DetectionCheckpointerWithEMA` files map 1:1 — aldi/checkpoint.py:8-31,
+aldi/ema.py:19-50 iterate over exactly these keys), plus a deterministic synthetic initialiser used by the
+benchmark and the parity tests (there is no network for the COCO-pretrained `model_final_f10217.pkl`).
+"""
+from collections import OrderedDict
+
+import torch
+
+
+class ConvSpec:
+    """One conv / linear layer: Detectron2 key prefix and geometry."""
+
+    def __init__(self, key, cin, cout, k=1, stride=1, pad=0, bias=False, norm=False, trainable=True):
+        self.key, self.cin, self.cout, self.k, self.stride, self.pad = key, cin, cout, k, stride, pad
+        self.bias, self.norm, self.trainable = bias, norm, trainable
+
+
+RES_DEPTHS = (3, 4, 6, 3)
+
+
+def resnet_specs(freeze_at=2):
+    specs = OrderedDict()
+    bu = "backbone.bottom_up."
+    specs["stem"] = ConvSpec(bu + "stem.conv1", 3, 64, 7, 2, 3, norm=True, trainable=freeze_at < 1)
+    cin, cout, mid = 64, 256, 64
+    for si, nblk in enumerate(RES_DEPTHS):
+        stage = si + 2
+        tr = freeze_at < stage
+        for b in range(nblk):
+            stride = 2 if (b == 0 and si > 0) else 1
+            p = "%sres%d.%d." % (bu, stage, b)
+            name = "res%d.%d." % (stage, b)
+            if b == 0:
+                specs[name + "shortcut"] = ConvSpec(p + "shortcut", cin, cout, 1, stride, 0, norm=True, trainable=tr)
+            specs[name + "conv1"] = ConvSpec(p + "conv1", cin, mid, 1, stride, 0, norm=True, trainable=tr)
+            specs[name + "conv2"] = ConvSpec(p + "conv2", mid, mid, 3, 1, 1, norm=True, trainable=tr)
+            specs[name + "conv3"] = ConvSpec(p + "conv3", mid, cout, 1, 1, 0, norm=True, trainable=tr)
+            cin = cout
+        cout *= 2
+        mid *= 2
+    return specs
+
+
+def rcnn_specs(num_classes=8, freeze_at=2):
+    specs = resnet_specs(freeze_at)
+    for lvl, c in zip((2, 3, 4, 5), (256, 512, 1024, 2048)):
+        specs["fpn_lateral%d" % lvl] = ConvSpec("backbone.fpn_lateral%d" % lvl, c, 256, 1, 1, 0, bias=True)
+        specs["fpn_output%d" % lvl] = ConvSpec("backbone.fpn_output%d" % lvl, 256, 256, 3, 1, 1, bias=True)
+    rp = "proposal_generator.rpn_head."
+    specs["rpn_conv"] = ConvSpec(rp + "conv", 256, 256, 3, 1, 1, bias=True)
+    specs["rpn_obj"] = ConvSpec(rp + "objectness_logits", 256, 3, 1, 1, 0, bias=True)
+    specs["rpn_delta"] = ConvSpec(rp + "anchor_deltas", 256, 12, 1, 1, 0, bias=True)
+    specs["fc1"] = ConvSpec("roi_heads.box_head.fc1", 256 * 7 * 7, 1024, bias=True)
+    specs["fc2"] = ConvSpec("roi_heads.box_head.fc2", 1024, 1024, bias=True)
+    specs["cls_score"] = ConvSpec("roi_heads.box_predictor.cls_score", 1024, num_classes + 1, bias=True)
+    specs["bbox_pred"] = ConvSpec("roi_heads.box_predictor.bbox_pred", 1024, num_classes * 4, bias=True)
+    return specs
+
+
+LINEAR_LAYERS = ("fc1", "fc2", "cls_score", "bbox_pred")
+NORM_FIELDS = ("weight", "bias", "running_mean", "running_var")
+
+
+def d2_shape(name, s):
+    """Shape of `<key>.weight` in the Detectron2 state_dict."""
+    if name in LINEAR_LAYERS:
+        return (s.cout, s.cin)
+    return (s.cout, s.cin, s.k, s.k)
+
+
+def state_dict_entries(num_classes=8, freeze_at=2):
+    """[(d2_key, shape, layer_name, field)] in a fixed order; field in {weight,bias,norm.<f>}."""
+    out = []
+    for name, s in rcnn_specs(num_classes, freeze_at).items():
+        out.append((s.key + ".weight", d2_shape(name, s), name, "weight"))
+        if s.bias:
+            out.append((s.key + ".bias", (s.cout,), name, "bias"))
+        if s.norm:
+            for f in NORM_FIELDS:
+                out.append(("%s.norm.%s" % (s.key, f), (s.cout,), name, "norm." + f))
+    return out
+
+
+def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2):
+    """Deterministic CPU-generated weights with O(1) activations (stands in for a burn-in checkpoint).
+
+    Scales are chosen so that a bf16 trunk stays in range, RPN logits are well separated and the
+    box classifier is confident enough (>0.8) on some RoIs for the pseudo-label path to be non-empty.
+    """
+    sd = OrderedDict()
+    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at)):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        if field == "weight":
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            fan_out = shape[0] * (shape[2] * shape[3] if len(shape) == 4 else 1)
+            if name == "stem" or name.startswith("res"):
+                t = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
+            elif name.startswith("fpn") or name in ("fc1", "fc2"):
+                bound = (3.0 / fan_in) ** 0.5
+                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            elif name.startswith("rpn"):
+                t = torch.randn(shape, generator=g) * 0.03
+            elif name == "cls_score":
+                t = torch.randn(shape, generator=g) * 0.2
+            else:  # bbox_pred
+                t = torch.randn(shape, generator=g) * 0.02
+        elif field == "bias":
+            t = torch.randn(shape, generator=g) * 0.01
+        elif field == "norm.weight":
+            base = 0.05 if name == "stem" else 0.4 if name.endswith("conv3") else 0.8 if name.endswith("shortcut") else 1.0
+            t = base * (1.0 + 0.1 * torch.randn(shape, generator=g))
+        elif field == "norm.bias":
+            t = 0.05 * torch.randn(shape, generator=g)
+        elif field == "norm.running_mean":
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:  # running_var
+            t = 1.0 + 0.2 * torch.rand(shape, generator=g)
+        sd[key] = t.float()
+    return sd
