@@ -19,6 +19,10 @@ FLAGS = [
 ]
 
 
+# selection kernels must reproduce the reference's float expressions bit-for-bit: no FMA contraction
+EXACT_SOURCES = ("select.cu",)
+
+
 def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -41,7 +45,8 @@ def _compile(src):
     dig = _digest(path)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [NVCC] + FLAGS + ["-c", path, "-o", obj]
+    extra = ["-fmad=false"] if src in EXACT_SOURCES else []
+    cmd = [NVCC] + FLAGS + extra + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

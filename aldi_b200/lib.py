@@ -42,6 +42,29 @@ class WgradParams(ctypes.Structure):
     ]
 
 
+class RoiAlignParams(ctypes.Structure):
+    _fields_ = [
+        ("feat", c_void_p * 4), ("dfeat", c_void_p * 4), ("feat_h", c_int * 4), ("feat_w", c_int * 4),
+        ("scale", c_float * 4), ("num_levels", c_int), ("min_level", c_int), ("canonical_box_size", c_float),
+        ("canonical_level", c_int), ("channels", c_int), ("pooled", c_int), ("dtype", c_int),
+        ("rois", c_void_p), ("roi_batch", c_void_p), ("num_valid", c_void_p), ("num_rois", c_int),
+        ("out", c_void_p), ("dout", c_void_p),
+    ]
+
+
+class RpnLevels(ctypes.Structure):
+    _fields_ = [
+        ("num_levels", c_int), ("num_anchors", c_int),
+        ("h", c_int * 5), ("w", c_int * 5), ("stride", c_int * 5), ("loc_off", c_int * 5),
+        ("total_locs", c_int), ("ch_stride", c_int),
+        ("cell", (c_float * 4) * 3 * 5),
+        ("scale_clamp", c_float), ("min_box_size", c_float),
+    ]
+
+
+c_uint = ctypes.c_uint
+P = c_void_p  # device / host pointers
+
 # name -> (restype, argtypes); every symbol declared in include/aldi_b200.h must appear here
 SIGNATURES = {
     "aldi_last_error": (ctypes.c_char_p, []),
@@ -57,6 +80,34 @@ SIGNATURES = {
     "aldi_conv_f32": (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     "aldi_wgrad_tc": (c_int, [ctypes.POINTER(WgradParams), c_void_p]),
     "aldi_wgrad_f32": (c_int, [ctypes.POINTER(WgradParams), c_void_p]),
+    "aldi_preprocess": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "aldi_stem_im2col": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "aldi_maxpool3x3s2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_sum2x2_accum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_add_f32": (c_int, [P, c_int, P, c_size_t, P]),
+    "aldi_colsum": (c_int, [P, c_int, c_ll, c_ll, c_int, c_float, P, P]),
+    "aldi_frozenbn_fold": (c_int, [P, P, P, P, c_float, P, P, c_int, P]),
+    "aldi_roi_align_forward": (c_int, [ctypes.POINTER(RoiAlignParams), P]),
+    "aldi_roi_align_backward": (c_int, [ctypes.POINTER(RoiAlignParams), P]),
+    "aldi_rpn_topk_decode": (c_int, [P, ctypes.POINTER(RpnLevels), c_int, c_int, P, P, P, P, P, P, c_int, P, P]),
+    "aldi_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "aldi_nms_sorted": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_int, P, c_size_t, P, P, P, P, P, P]),
+    "aldi_rpn_label_anchors": (c_int, [ctypes.POINTER(RpnLevels), c_int, P, P, c_int, c_float, c_float, c_int, c_float,
+                                       c_uint, P, P, P, P, P, P]),
+    "aldi_roi_label_sample": (c_int, [P, P, c_int, c_int, P, P, P, c_int, c_float, c_int, c_int, c_float, c_uint, P,
+                                      c_int, P, P, P, P, P, P, P, P]),
+    "aldi_roi_inference_candidates": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, c_float, P, c_float, P, P, P, P,
+                                              P, c_int, P]),
+    "aldi_pseudo_label_threshold": (c_int, [P, P, P, P, c_int, c_int, c_float, P, P, P, P, c_int, P]),
+    "aldi_rpn_loss": (c_int, [P, ctypes.POINTER(RpnLevels), c_int, P, P, P, P, c_int, c_int, c_float, c_float, c_float,
+                              P, c_int, c_int, c_int, P, P]),
+    "aldi_roi_loss": (c_int, [P, c_int, c_int, c_int, P, P, P, P, c_int, P, c_float, c_float, c_float, P, c_int, c_int,
+                              P, P]),
+    "aldi_distill_rpn_loss": (c_int, [P, P, ctypes.POINTER(RpnLevels), c_int, P, P, c_float, c_float, c_float, c_float,
+                                      P, c_int, c_int, c_int, P, P]),
+    "aldi_distill_roi_loss": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_float, c_int, c_float, c_float,
+                                      c_float, P, c_int, c_int, c_int, P, P]),
+    "aldi_domain_bce_loss": (c_int, [P, c_int, c_int, c_float, c_float, c_float, P, c_int, c_int, P, P]),
 }
 
 

@@ -111,6 +111,110 @@ typedef struct {
 int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream);
 int aldi_wgrad_f32(const aldi_wgrad_params* p, void* stream);
 
+/* ---- glue kernels of the trunk (detectron2 GeneralizedRCNN.preprocess_image, BasicStem, FPN backward) ---- */
+int aldi_preprocess(const uint8_t* images /*(N,3,hin,win) uint8*/, const int* sizes /*(N,2) valid h,w*/, float* out
+                    /*(N,hp,wp,4) fp32*/, int n, int hin, int win, int hp, int wp, const float* h_mean,
+                    const float* h_std, void* stream);
+/* fused normalise + im2col of the stem's 7x7/2 conv: out bf16 (N,ho,wo,192), k=(r*7+s)*3+c, zero for k>=147 */
+int aldi_stem_im2col(const uint8_t* images, const int* sizes, void* out_bf16, int n, int hin, int win, int ho, int wo,
+                     const float* h_mean, const float* h_std, void* stream);
+int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, int h, int w, int c, void* stream);
+/* coarse[n,h,w,c] += sum of the 2x2 block of fine (backward of nearest-2x upsample + add in FPN top-down) */
+int aldi_sum2x2_accum(const void* fine, void* coarse, int dtype, int n, int h, int w, int c, void* stream);
+int aldi_add_f32(void* dst, int dtype, const float* src, size_t n, void* stream);
+/* out[c] += scale * sum_rows x[row*row_stride + c]  (bias gradients) */
+int aldi_colsum(const void* x, int dtype, long long rows, long long row_stride, int c, float scale, float* out,
+                void* stream);
+/* FrozenBatchNorm2d -> per-channel (scale, shift): scale = w*rsqrt(var+eps), shift = b - mean*scale */
+int aldi_frozenbn_fold(const float* weight, const float* bias, const float* mean, const float* var, float eps,
+                       float* scale, float* shift, int n, void* stream);
+
+/* ---- RoIAlign over FPN levels (detectron2 ROIPooler + torchvision roi_align, aligned=True, sampling_ratio=0) ---- */
+typedef struct {
+  const void* feat[4];      /* per level (N, feat_h, feat_w, channels) channels-last */
+  float* dfeat[4];          /* backward: fp32 gradient accumulators, same geometry (zeroed by caller) */
+  int feat_h[4], feat_w[4];
+  float scale[4];           /* 1/stride */
+  int num_levels, min_level;
+  float canonical_box_size; /* 224 */
+  int canonical_level;      /* 4 */
+  int channels, pooled, dtype;
+  const float* rois;        /* (M,4) xyxy, image pixels */
+  const int* roi_batch;     /* (M) image index */
+  const int* num_valid;     /* device scalar: rows >= *num_valid are padding (NULL: all valid) */
+  int num_rois;             /* M */
+  void* out;                /* forward: (M, pooled, pooled, channels) */
+  const void* dout;         /* backward */
+} aldi_roialign_params;
+int aldi_roi_align_forward(const aldi_roialign_params* p, void* stream);
+int aldi_roi_align_backward(const aldi_roialign_params* p, void* stream);
+
+/* ---- selection ops (bit-exact index sets; compiled without FMA contraction) ------------------ */
+typedef struct {
+  int num_levels, num_anchors;
+  int h[5], w[5], stride[5], loc_off[5]; /* loc_off: first location of the level in the concatenated map */
+  int total_locs, ch_stride;             /* rpn_out is (N, total_locs, ch_stride) fp32: A logits then A*4 deltas */
+  float cell[5][3][4];                   /* DefaultAnchorGenerator cell anchors */
+  float scale_clamp, min_box_size;
+} aldi_rpn_levels;
+/* detectron2 find_top_rpn_proposals front half: per (image, level) top-k logits (descending), decode
+ * (Box2BoxTransform weights 1), clip, finite/non-empty validity.  Candidates are level-major.        */
+int aldi_rpn_topk_decode(const float* rpn_out, const aldi_rpn_levels* levels, int n_images, int pre_topk,
+                         const int* img_sizes, float* cand_box, float* cand_score, int* cand_cat, int* cand_idx,
+                         unsigned char* cand_valid, int cand_stride, int* err_flag, void* stream);
+/* batched_nms (per-category greedy NMS, IoU > thresh suppresses) + keep[:post_topk]; output in score order */
+size_t aldi_nms_workspace_bytes(int n_images, int cand_stride);
+int aldi_nms_sorted(const float* cand_box, const float* cand_score, const int* cand_cat,
+                    const unsigned char* cand_valid, const int* cand_count, int n_images, int cand_stride,
+                    float iou_thresh, int post_topk, void* workspace, size_t workspace_bytes, float* out_box,
+                    float* out_score, int* out_cat, int* out_src, int* out_count, void* stream);
+/* RPN.label_and_sample_anchors: Matcher([lo,hi],[0,-1,1], low-quality) + subsample_labels; labels (N,R) int8 */
+int aldi_rpn_label_anchors(const aldi_rpn_levels* levels, int n_images, const float* gt_boxes, const int* gt_counts,
+                           int gmax, float iou_lo, float iou_hi, int num_samples, float pos_fraction,
+                           unsigned int seed, const unsigned int* salts, int* gt_best_ws, signed char* labels,
+                           int* matched, int* stats, void* stream);
+/* StandardROIHeads.label_and_sample_proposals: append GT, Matcher([thr],[0,1]), subsample; (N*num_samples) rows */
+int aldi_roi_label_sample(const float* prop_box, const int* prop_count, int prop_stride, int n_images,
+                          const float* gt_boxes, const int* gt_classes, const int* gt_counts, int gmax,
+                          float iou_thresh, int num_classes, int num_samples, float pos_fraction, unsigned int seed,
+                          const unsigned int* salts, int append_gt, float* out_box, int* out_batch, int* out_class,
+                          float* out_gtbox, int* out_src, int* out_count, int* stats, void* stream);
+/* FastRCNNOutputLayers.inference front half: softmax, per-class decode + clip, score filter */
+int aldi_roi_inference_candidates(const float* pred, int pred_stride, const float* prop_box, const int* prop_count,
+                                  int prop_stride, int n_images, int num_classes, const int* img_sizes,
+                                  float score_thresh, const float* h_weights4, float scale_clamp, float* cand_box,
+                                  float* cand_score, int* cand_cat, int* cand_src, int* cand_count, int cand_stride,
+                                  void* stream);
+/* aldi/pseudolabeler.py:51-67 process_bbox: keep detections with score > threshold (order preserved) */
+int aldi_pseudo_label_threshold(const float* det_box, const float* det_score, const int* det_class,
+                                const int* det_count, int det_stride, int n_images, float threshold, float* gt_box,
+                                int* gt_class, float* gt_score, int* gt_count, int gmax, void* stream);
+
+/* ---- fused losses (scalar values accumulated into loss_out[0..1], gradients written densely) ---- */
+/* detectron2 RPN.losses: loss_out[0] += loss_rpn_cls, loss_out[1] += loss_rpn_loc (both * gscale) */
+int aldi_rpn_loss(const float* rpn_out, const aldi_rpn_levels* levels, int n_images, const signed char* labels,
+                  const int* matched, const float* gt_boxes, const int* gt_counts, int gmax,
+                  int batch_size_per_image, float w_cls, float w_loc, float gscale, void* drpn, int dtype,
+                  int dstride, int accumulate, float* loss_out, void* stream);
+/* detectron2 FastRCNNOutputLayers.losses: loss_out[0] += loss_cls, loss_out[1] += loss_box_reg */
+int aldi_roi_loss(const float* pred, int pred_stride, int m, int num_classes, const int* gt_class,
+                  const float* roi_box, const float* gt_box, const int* counts, int n_images,
+                  const float* h_weights4, float w_cls, float w_box, float gscale, void* dpred, int dtype,
+                  int dstride, float* loss_out, void* stream);
+/* aldi/distill.py:193-229: loss_out[0] += loss_obj_bce, loss_out[1] += loss_rpn_l1 */
+int aldi_distill_rpn_loss(const float* student_rpn_out, const float* teacher_rpn_out, const aldi_rpn_levels* levels,
+                          int n_images, const signed char* labels, const int* stats, float obj_temperature,
+                          float w_obj, float w_reg, float gscale, void* drpn, int dtype, int dstride, int accumulate,
+                          float* loss_out, void* stream);
+/* aldi/distill.py:231-278: loss_out[0] += loss_cls_ce (CE or KL), loss_out[1] += loss_roih_l1 */
+int aldi_distill_roi_loss(const float* student_pred, const float* teacher_pred, int pred_stride, int m,
+                          int num_classes, const int* row_class, const int* counts, int n_images,
+                          float cls_temperature, int use_kl, float w_cls, float w_reg, float gscale, void* dpred,
+                          int dtype, int dstride, int accumulate, float* loss_out, void* stream);
+/* aldi/align.py:81-90: loss_out[0] += weight * mean BCE-with-logits(pred, domain_label) */
+int aldi_domain_bce_loss(const float* pred, int n, int stride, float domain_label, float weight, float gscale,
+                         void* dpred, int dtype, int dstride, float* loss_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
