@@ -1,0 +1,486 @@
+"""Faster R-CNN R50-FPN forward / backward on flat parameter buffers, every arithmetic op a C-ABI kernel call.
+
+This is the B200 replacement of what `model(batched_inputs)` / `model.inference(...)` execute inside
+Detectron2 for the reference (aldi/model.py:27-29 -> detectron2 GeneralizedRCNN):
+  * parameters live in ONE flat fp32 buffer per model (student / teacher) so the EMA update and the
+    optimizer step are single kernels (aldi/ema.py:32-50 loops over ~300 tensors instead);
+  * activations are channels-last in the compute dtype (bf16 -> tcgen05 kernels, fp32 -> parity kernels);
+  * FrozenBN / bias / ReLU / residual / FPN top-down add are conv epilogues; ReLU backward masks and
+    residual joins are data-gradient epilogues; stride-2 1x1 convs, p6 and the stride-2 scatter of their
+    gradients are strided views handed to TMA — no kernels;
+  * backward is written out explicitly (no autograd graph): the architecture is fixed.
+There is no PyTorch-op fallback: torch only allocates memory.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import arch, ops
+from . import lib as _l
+
+FUSED = OrderedDict([("rpn_head", ("rpn_obj", "rpn_delta")), ("predictor", ("cls_score", "bbox_pred"))])
+SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+class FlatLayout:
+    """Detectron2 state_dict keys <-> ranges of one flat fp32 buffer (trainable range first)."""
+
+    def __init__(self, num_classes=8, freeze_at=2):
+        self.num_classes = num_classes
+        self.specs = arch.rcnn_specs(num_classes, freeze_at)
+        member_of = {m: g for g, ms in FUSED.items() for m in ms}
+        train, frozen, buffers = [], [], []
+        done = set()
+        for name, s in self.specs.items():
+            if name in done:
+                continue
+            group = [name] if name not in member_of else list(FUSED[member_of[name]])
+            done.update(group)
+            dst = train if s.trainable else frozen
+            dst.append([(g, "weight") for g in group])
+            if s.bias:
+                dst.append([(g, "bias") for g in group])
+            if s.norm:
+                for f in arch.NORM_FIELDS:
+                    buffers.append([(name, "norm." + f)])
+        self.entries = OrderedDict()  # (layer, field) -> (offset, numel, d2_key, d2_shape)
+        off = 0
+        for region, groups in (("train", train), ("frozen", frozen), ("buffers", buffers)):
+            if region == "frozen":
+                self.num_trainable = off
+            for group in groups:
+                off = (off + 3) // 4 * 4  # 16-byte alignment of every (fused) tensor
+                for layer, field in group:
+                    s = self.specs[layer]
+                    shape = arch.d2_shape(layer, s) if field == "weight" else (s.cout,)
+                    n = 1
+                    for d in shape:
+                        n *= d
+                    self.entries[(layer, field)] = (off, n, "%s.%s" % (s.key, field), shape)
+                    off += n
+        self.numel = (off + 3) // 4 * 4
+        self.num_trainable = (self.num_trainable + 3) // 4 * 4
+
+    def to_internal(self, layer, field, t):
+        """Detectron2 tensor -> flat-buffer element order (convs OHWI, fc1 (h,w,c) input order)."""
+        if field != "weight":
+            return t.reshape(-1)
+        if layer == "fc1":
+            return t.reshape(t.shape[0], 256, 7, 7).permute(0, 2, 3, 1).reshape(-1)
+        if t.dim() == 4:
+            return t.permute(0, 2, 3, 1).reshape(-1)
+        return t.reshape(-1)
+
+    def from_internal(self, layer, field, flat, shape):
+        if field != "weight":
+            return flat.reshape(shape).clone()
+        if layer == "fc1":
+            return flat.reshape(shape[0], 7, 7, 256).permute(0, 3, 1, 2).reshape(shape).contiguous()
+        if len(shape) == 4:
+            return flat.reshape(shape[0], shape[2], shape[3], shape[1]).permute(0, 3, 1, 2).contiguous()
+        return flat.reshape(shape).clone()
+
+    def pack_state_dict(self, sd):
+        flat = torch.zeros(self.numel, dtype=torch.float32)
+        missing = []
+        for (layer, field), (off, n, key, shape) in self.entries.items():
+            if key not in sd:
+                missing.append(key)
+                continue
+            t = sd[key].detach().to("cpu", torch.float32)
+            assert tuple(t.shape) == tuple(shape), (key, tuple(t.shape), shape)
+            flat[off:off + n] = self.to_internal(layer, field, t)
+        if missing:
+            raise KeyError("missing keys in state_dict: %s" % missing[:5])
+        return flat
+
+    def unpack_state_dict(self, flat):
+        flat = flat.detach().to("cpu")
+        out = OrderedDict()
+        for (layer, field), (off, n, key, shape) in self.entries.items():
+            out[key] = self.from_internal(layer, field, flat[off:off + n], shape)
+        return out
+
+
+class LayerGeom:
+    """Geometry of one executed GEMM layer (after head fusion)."""
+
+    def __init__(self, name, cin, cout, k, pad, stride, members, norm, trainable):
+        self.name, self.cin, self.cout, self.k, self.pad, self.stride = name, cin, cout, k, pad, stride
+        self.members, self.norm, self.trainable = members, norm, trainable
+        self.cin_p, self.cout_p = _pad64(cin), _pad64(cout)
+
+
+class DetectorWeights:
+    """One model's parameters: flat fp32 master + GEMM operands + folded FrozenBN, refreshed by kernels."""
+
+    def __init__(self, layout, flat, dtype):
+        self.layout, self.flat, self.dtype = layout, flat, dtype
+        self.dev = flat.device
+        self.geom = OrderedDict()
+        sp = layout.specs
+        member_of = {m: g for g, ms in FUSED.items() for m in ms}
+        for name, s in sp.items():
+            if name in member_of:
+                g = member_of[name]
+                if g in self.geom:
+                    continue
+                ms = FUSED[g]
+                self.geom[g] = LayerGeom(g, s.cin, sum(sp[m].cout for m in ms), s.k, s.pad, s.stride, ms, False,
+                                         s.trainable)
+            else:
+                self.geom[name] = LayerGeom(name, s.cin, s.cout, s.k, s.pad, s.stride, (name,), s.norm, s.trainable)
+        # stem: bf16 path runs it as a GEMM over the fused normalise+im2col buffer (K = 147 -> 192)
+        self.stem_gemm = dtype == torch.bfloat16
+        self.fwd, self.dgrad, self.scale, self.shift = {}, {}, {}, {}
+        for name, g in self.geom.items():
+            taps = g.k * g.k
+            if name == "stem":
+                kdim = 192 if self.stem_gemm else taps * 4
+                self.fwd[name] = torch.zeros(g.cout_p, kdim, device=self.dev, dtype=dtype)
+            else:
+                self.fwd[name] = torch.zeros(g.cout_p, taps * g.cin_p, device=self.dev, dtype=dtype)
+            if g.norm:
+                self.scale[name] = torch.zeros(g.cout_p, device=self.dev)
+            self.shift[name] = torch.zeros(g.cout_p, device=self.dev)
+        self.no_dgrad = {"stem", "res3.0.conv1", "res3.0.shortcut", "fpn_lateral2"}
+
+    # ---- flat views -------------------------------------------------------------------------------
+    def view(self, layer, field, buf=None):
+        buf = self.flat if buf is None else buf
+        g = self.geom[layer]
+        off, _, _, _ = self.layout.entries[(g.members[0], field)]
+        n = sum(self.layout.entries[(m, field)][1] for m in g.members)
+        return buf[off:off + n]
+
+    def enable_dgrad(self):
+        for name, g in self.geom.items():
+            if g.trainable and name not in self.no_dgrad and name not in self.dgrad:
+                self.dgrad[name] = torch.zeros(g.cin_p, g.k * g.k * g.cout_p, device=self.dev, dtype=self.dtype)
+
+    def refresh(self):
+        """Re-derive operands from the master weights (after load / optimizer step / EMA update)."""
+        for name, g in self.geom.items():
+            taps = g.k * g.k
+            w = self.view(name, "weight")
+            if g.norm:
+                ops.call("aldi_frozenbn_fold", self.view(name, "norm.weight"), self.view(name, "norm.bias"),
+                         self.view(name, "norm.running_mean"), self.view(name, "norm.running_var"), 1e-5,
+                         self.scale[name], self.shift[name], g.cout)
+            else:
+                self.shift[name][:g.cout].copy_(self.view(name, "bias"))
+            if name == "stem":
+                if self.stem_gemm:
+                    ops.pack_weight(w, self.fwd[name], cout=g.cout, taps=1, cin=147, cout_p=g.cout_p, cin_p=192)
+                else:
+                    ops.pack_weight(w, self.fwd[name], cout=g.cout, taps=taps, cin=3, cout_p=g.cout_p, cin_p=4)
+            else:
+                ops.pack_weight(w, self.fwd[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
+            if name in self.dgrad:
+                ops.pack_weight(w, self.dgrad[name], dgrad=True, scale=self.scale.get(name), cout=g.cout, taps=taps,
+                                cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
+
+
+# ---------------------------------------------------------------------------------------------------
+PIXEL_MEAN = (103.530, 116.280, 123.675)
+PIXEL_STD = (1.0, 1.0, 1.0)
+ANCHOR_SIZES = ((32,), (64,), (128,), (256,), (512,))
+ANCHOR_RATIOS = (0.5, 1.0, 2.0)
+FPN_STRIDES = (4, 8, 16, 32, 64)
+
+
+def cell_anchors():
+    """detectron2 DefaultAnchorGenerator.generate_cell_anchors (float64 math, stored as fp32)."""
+    out = []
+    for sizes in ANCHOR_SIZES:
+        lvl = []
+        for size in sizes:
+            area = size ** 2.0
+            for ar in ANCHOR_RATIOS:
+                w = math.sqrt(area / ar)
+                h = ar * w
+                lvl.append(torch.tensor([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0]).tolist())
+        out.append(lvl)
+    return out
+
+
+class Detector:
+    """Stateless executor: runs the trunk / heads of ONE DetectorWeights on a batch and, for the student,
+    the explicit backward that accumulates into a flat gradient buffer."""
+
+    RPN_CH = 16    # fp32 head output row: 3 logits + 12 deltas (+1 pad)
+    PRED_CH = 64   # fp32 predictor row: K+1 logits + 4K deltas, padded
+
+    def __init__(self, num_classes=8):
+        self.K = num_classes
+        self.cells = cell_anchors()
+
+    # ---- generic layer ------------------------------------------------------------------------------
+    @staticmethod
+    def conv(W, name, x, *, relu=False, residual=None, res_mode=0, out=None, out_dtype=None, cout_store=None):
+        g = W.geom[name]
+        xv = x[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else x
+        n, h, w, _ = xv.shape
+        if out is None:
+            out = torch.empty(n, h, w, g.cout_p, device=x.device, dtype=out_dtype or x.dtype)
+        ops.conv(xv, W.fwd[name], out, taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad, scale=W.scale.get(name),
+                 bias=W.shift[name], residual=residual, res_mode=res_mode, relu=relu, cout_store=cout_store)
+        return out
+
+    # ---- trunk forward ---------------------------------------------------------------------------------
+    def backbone(self, W, images_u8, sizes, save):
+        """images_u8: (N,3,H,W) uint8 on device (already on the padded canvas); sizes: (N,2) int32 valid (h,w).
+        Returns (features dict p2..p6 + res2..res5, saved-activation dict or None)."""
+        n, _, hp, wp = images_u8.shape
+        assert hp % 32 == 0 and wp % 32 == 0
+        dev, dt = images_u8.device, W.dtype
+        mean, std = ops.host_floats(PIXEL_MEAN), ops.host_floats(PIXEL_STD)
+        g = W.geom["stem"]
+        ho, wo = hp // 2, wp // 2
+        stem_out = torch.empty(n, ho, wo, 64, device=dev, dtype=dt)
+        if W.stem_gemm:
+            col = torch.empty(n, ho, wo, 192, device=dev, dtype=dt)
+            ops.call("aldi_stem_im2col", images_u8, sizes, col, n, hp, wp, ho, wo, mean, std)
+            ops.conv(col, W.fwd["stem"], stem_out, scale=W.scale["stem"], bias=W.shift["stem"], relu=True)
+            del col
+        else:
+            x0 = torch.empty(n, hp, wp, 4, device=dev, dtype=torch.float32)
+            ops.call("aldi_preprocess", images_u8, sizes, x0, n, hp, wp, hp, wp, mean, std)
+            ops.conv(x0, W.fwd["stem"], stem_out, taps_h=7, taps_w=7, pad_h=3, pad_w=3, stride=2, scale=W.scale["stem"],
+                     bias=W.shift["stem"], relu=True)
+            del x0
+        x = torch.empty(n, ho // 2, wo // 2, 64, device=dev, dtype=dt)
+        ops.call("aldi_maxpool3x3s2", stem_out, x, _l.BF16 if dt == torch.bfloat16 else _l.F32, n, ho, wo, 64)
+        del stem_out
+        saved = {} if save else None
+        feats = {}
+        for si, nblk in enumerate(arch.RES_DEPTHS):
+            stage = si + 2
+            for b in range(nblk):
+                p = "res%d.%d." % (stage, b)
+                h1 = self.conv(W, p + "conv1", x, relu=True)
+                h2 = self.conv(W, p + "conv2", h1, relu=True)
+                sc = self.conv(W, p + "shortcut", x) if b == 0 else x
+                out = self.conv(W, p + "conv3", h2, relu=True, residual=sc, res_mode=1)
+                if save and W.geom[p + "conv1"].trainable:
+                    saved[p] = (x, h1, h2)
+                x = out
+            feats["res%d" % stage] = x
+        # FPN top-down: lateral 1x1 with the nearest-2x upsampled coarser map added in the epilogue
+        prev = None
+        for lvl in (5, 4, 3, 2):
+            r = feats["res%d" % lvl]
+            prev = self.conv(W, "fpn_lateral%d" % lvl, r, residual=prev, res_mode=2 if prev is not None else 0)
+            feats["p%d" % lvl] = self.conv(W, "fpn_output%d" % lvl, prev)
+            if save:
+                saved["prev%d" % lvl] = prev
+        feats["p6"] = feats["p5"][:, ::2, ::2, :]  # LastLevelMaxPool(kernel 1, stride 2) == strided view
+        return feats, saved
+
+    # ---- RPN ----------------------------------------------------------------------------------------
+    def levels(self, feats):
+        shapes = [tuple(feats["p%d" % l].shape[1:3]) for l in (2, 3, 4, 5, 6)]
+        return ops.make_rpn_levels(shapes, FPN_STRIDES, self.cells, self.RPN_CH, SCALE_CLAMP, 0.0)
+
+    def rpn_head(self, W, feats, lv, save):
+        n = feats["p2"].shape[0]
+        dev = feats["p2"].device
+        rpn_out = torch.zeros(n, lv.total_locs, self.RPN_CH, device=dev, dtype=torch.float32)
+        ts = []
+        for i, l in enumerate((2, 3, 4, 5, 6)):
+            p = feats["p%d" % l]
+            t = self.conv(W, "rpn_conv", p, relu=True)
+            h, w = p.shape[1], p.shape[2]
+            view = rpn_out.as_strided((n, h, w, self.RPN_CH),
+                                      (lv.total_locs * self.RPN_CH, w * self.RPN_CH, self.RPN_CH, 1),
+                                      lv.loc_off[i] * self.RPN_CH)
+            self.conv(W, "rpn_head", t, out=view, cout_store=15)
+            ts.append(t if save else None)
+        return rpn_out, ts
+
+    def proposals(self, rpn_out, lv, sizes, pre_topk, post_topk, nms_thresh=0.7, err_flag=None):
+        n = rpn_out.shape[0]
+        dev = rpn_out.device
+        stride = sum(min(lv.h[i] * lv.w[i] * lv.num_anchors, pre_topk) for i in range(lv.num_levels))
+        cb = torch.empty(n, stride, 4, device=dev)
+        cs = torch.empty(n, stride, device=dev)
+        cc = torch.empty(n, stride, dtype=torch.int32, device=dev)
+        ci = torch.empty(n, stride, dtype=torch.int32, device=dev)
+        cv = torch.empty(n, stride, dtype=torch.uint8, device=dev)
+        ops.call("aldi_rpn_topk_decode", rpn_out, _l.ctypes.byref(lv), n, pre_topk, sizes, cb, cs, cc, ci, cv, stride,
+                 err_flag)
+        out = self.nms(cb, cs, cc, cv, None, nms_thresh, post_topk)
+        out["cand"] = (cb, cs, cc, ci, cv)
+        return out
+
+    @staticmethod
+    def nms(cb, cs, cc, cv, counts, thresh, post_topk):
+        n, stride = cs.shape
+        dev = cs.device
+        L = _l.load()
+        wsb = int(L.aldi_nms_workspace_bytes(n, stride))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ob = torch.zeros(n, post_topk, 4, device=dev)
+        osc = torch.zeros(n, post_topk, device=dev)
+        oc = torch.zeros(n, post_topk, dtype=torch.int32, device=dev)
+        osrc = torch.zeros(n, post_topk, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        ops.call("aldi_nms_sorted", cb, cs, cc, cv, counts, n, stride, thresh, post_topk, ws, wsb, ob, osc, oc, osrc, cnt)
+        return {"boxes": ob, "scores": osc, "cats": oc, "src": osrc, "count": cnt}
+
+    # ---- box head -------------------------------------------------------------------------------------
+    def box_head(self, W, feats, rois, roi_batch, save):
+        m = rois.shape[0]
+        dev, dt = rois.device, W.dtype
+        plv = [feats["p%d" % l] for l in (2, 3, 4, 5)]
+        pooled = torch.empty(m, 7, 7, 256, device=dev, dtype=dt)
+        ops.roi_align(plv, rois, roi_batch, out=pooled, scales=[1.0 / s for s in FPN_STRIDES[:4]])
+        x = pooled.view(1, 1, m, 7 * 7 * 256)
+        f1 = self.conv(W, "fc1", x, relu=True)
+        f2 = self.conv(W, "fc2", f1, relu=True)
+        pred = torch.zeros(1, 1, m, self.PRED_CH, device=dev, dtype=torch.float32)
+        self.conv(W, "predictor", f2, out=pred, cout_store=5 * self.K + 1)
+        return pred.view(m, self.PRED_CH), ((x, f1, f2) if save else None)
+
+    def detections(self, pred, props, sizes, score_thresh, nms_thresh=0.5, topk=100):
+        """FastRCNNOutputLayers.inference on (N*P) predictions -> per-image detections (score order)."""
+        n, p = props["scores"].shape
+        dev = pred.device
+        cstride = min(p * self.K, 16384)
+        cb = torch.empty(n, cstride, 4, device=dev)
+        cs = torch.empty(n, cstride, device=dev)
+        cc = torch.empty(n, cstride, dtype=torch.int32, device=dev)
+        csrc = torch.empty(n, cstride, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        ops.call("aldi_roi_inference_candidates", pred, pred.shape[1], props["boxes"], props["count"], p, n, self.K, sizes,
+                 score_thresh, ops.host_floats((10.0, 10.0, 5.0, 5.0)), SCALE_CLAMP, cb, cs, cc, csrc, cnt, cstride)
+        return self.nms(cb, cs, cc, None, cnt, nms_thresh, topk)
+
+    # ---- backward -------------------------------------------------------------------------------------
+    def _wgrad(self, W, G, name, x, dy):
+        g = W.geom[name]
+        xv = x[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else x
+        ops.wgrad(xv, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
+                  scale=W.scale.get(name), cout_store=g.cout, cin_store=g.cin)
+        if not g.norm:
+            rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
+            assert dy.is_contiguous()
+            ops.call("aldi_colsum", dy, _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32, rows, dy.shape[3], g.cout,
+                     1.0, W.view(name, "bias", G))
+
+    def _dgrad(self, W, name, dy, out, *, mask=None, residual=None, accumulate=False):
+        g = W.geom[name]
+        outv = out[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else out
+        maskv = mask[:, ::2, ::2, :] if (mask is not None and g.stride == 2 and g.k == 1) else mask
+        ops.conv(dy, W.dgrad[name], outv, taps_h=g.k, taps_w=g.k, pad_h=g.k - 1 - g.pad, pad_w=g.k - 1 - g.pad,
+                 mask=maskv, residual=residual, res_mode=1 if residual is not None else 0, accumulate=accumulate,
+                 cout_store=g.cin)
+        return out
+
+    def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch):
+        """Accumulate d(loss)/d(params) into the flat gradient buffer G.
+        d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64)."""
+        dt = W.dtype
+        dtc = _l.BF16 if dt == torch.bfloat16 else _l.F32
+        dev = d_rpn.device
+        n = d_rpn.shape[0]
+        # ---- box head: predictor -> fc2 -> fc1 -> RoIAlign scatter
+        dP = {}
+        for l in (2, 3, 4, 5):
+            dP[l] = torch.zeros_like(feats["p%d" % l])
+        if dpred is not None:
+            x, f1, f2 = head_saved
+            m = dpred.shape[0]
+            dy = dpred.view(1, 1, m, dpred.shape[1])
+            self._wgrad(W, G, "predictor", f2, dy)
+            df2 = torch.empty_like(f2)
+            self._dgrad(W, "predictor", dy, df2, mask=f2)
+            self._wgrad(W, G, "fc2", f1, df2)
+            df1 = torch.empty_like(f1)
+            self._dgrad(W, "fc2", df2, df1, mask=f1)
+            self._wgrad(W, G, "fc1", x, df1)
+            dx = torch.empty_like(x)
+            self._dgrad(W, "fc1", df1, dx)
+            plv = [feats["p%d" % l] for l in (2, 3, 4, 5)]
+            dfeat = [torch.zeros(p.shape, device=dev, dtype=torch.float32) for p in plv]
+            ops.roi_align(plv, rois, roi_batch, dout=dx.view(m, 7, 7, 256), dfeats=dfeat,
+                          scales=[1.0 / s for s in FPN_STRIDES[:4]])
+            for l, d in zip((2, 3, 4, 5), dfeat):
+                ops.call("aldi_add_f32", dP[l], dtc, d, d.numel())
+            del dfeat, dx, df1, df2
+        # ---- RPN head (weights shared over the 5 levels)
+        if d_rpn is not None:
+            for i, l in enumerate((2, 3, 4, 5, 6)):
+                p = feats["p%d" % l]
+                h, w = p.shape[1], p.shape[2]
+                t = rpn_ts[i]
+                dy = d_rpn.as_strided((n, h, w, 64), (lv.total_locs * 64, w * 64, 64, 1), lv.loc_off[i] * 64)
+                self._wgrad_strided_bias(W, G, "rpn_head", t, dy)
+                dt_ = torch.empty_like(t)
+                self._dgrad(W, "rpn_head", dy, dt_, mask=t)
+                self._wgrad(W, G, "rpn_conv", p, dt_)
+                tgt = dP[l] if l < 6 else dP[5][:, ::2, ::2, :]
+                self._dgrad(W, "rpn_conv", dt_, tgt, accumulate=True)
+                del dt_
+        # ---- FPN: p_l = output_l(prev_l); prev_l = lateral_l(res_l) + up2(prev_{l+1})
+        dprev, dres = {}, {}
+        for l in (2, 3, 4, 5):
+            prev = saved["prev%d" % l]
+            self._wgrad(W, G, "fpn_output%d" % l, prev, dP[l])
+            dprev[l] = torch.empty_like(prev)
+            self._dgrad(W, "fpn_output%d" % l, dP[l], dprev[l])
+            if l > 2:
+                c = dprev[l]
+                ops.call("aldi_sum2x2_accum", dprev[l - 1], c, dtc, c.shape[0], c.shape[1], c.shape[2], c.shape[3])
+            dP[l] = None
+        for l in (2, 3, 4, 5):
+            r = feats["res%d" % l]
+            self._wgrad(W, G, "fpn_lateral%d" % l, r, dprev[l])
+            if l > 2:
+                dres[l] = torch.empty_like(r)
+                self._dgrad(W, "fpn_lateral%d" % l, dprev[l], dres[l], mask=r)
+            dprev[l] = None
+        # ---- ResNet res5 -> res3 (stem + res2 frozen: aldi configs keep D2's FREEZE_AT=2)
+        for stage in (5, 4, 3):
+            dout = dres[stage]
+            nblk = arch.RES_DEPTHS[stage - 2]
+            for b in reversed(range(nblk)):
+                p = "res%d.%d." % (stage, b)
+                x, h1, h2 = saved[p]
+                self._wgrad(W, G, p + "conv3", h2, dout)
+                dh2 = torch.empty_like(h2)
+                self._dgrad(W, p + "conv3", dout, dh2, mask=h2)
+                self._wgrad(W, G, p + "conv2", h1, dh2)
+                dh1 = torch.empty_like(h1)
+                self._dgrad(W, p + "conv2", dh2, dh1, mask=h1)
+                del dh2
+                self._wgrad(W, G, p + "conv1", x, dh1)
+                if b == 0:
+                    self._wgrad(W, G, p + "shortcut", x, dout)
+                    if stage > 3:
+                        # x is the previous stage's output: its gradient buffer already holds the FPN-lateral
+                        # term; the two stride-2 branches scatter-accumulate into the even positions
+                        dx = dres[stage - 1]
+                        self._dgrad(W, p + "conv1", dh1, dx, mask=x, accumulate=True)
+                        self._dgrad(W, p + "shortcut", dout, dx, mask=x, accumulate=True)
+                else:
+                    dx = torch.empty_like(x)
+                    self._dgrad(W, p + "conv1", dh1, dx, mask=x, residual=dout)
+                    dout = dx
+                del dh1
+            dres[stage] = None
+
+    def _wgrad_strided_bias(self, W, G, name, x, dy):
+        """wgrad + bias grad where dy is a strided level view of the concatenated RPN gradient map."""
+        g = W.geom[name]
+        ops.wgrad(x, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
+                  cout_store=g.cout, cin_store=g.cin)
+        n, h, w, c = dy.shape
+        dtc = _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32
+        for i in range(n):  # rows of one image's level slab are contiguous
+            ops.call("aldi_colsum", dy[i], dtc, h * w, c, g.cout, 1.0, W.view(name, "bias", G))

@@ -130,3 +130,72 @@ def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
         _l.check(L.aldi_wgrad_tc(ctypes.byref(p), _stream()), "aldi_wgrad_tc")
     else:
         _l.check(L.aldi_wgrad_f32(ctypes.byref(p), _stream()), "aldi_wgrad_f32")
+
+
+# ---------------------------------------------------------------------------------------------------
+# generic call helper for the remaining entry points (tensors -> device pointers, current stream appended)
+# ---------------------------------------------------------------------------------------------------
+def _arg(a):
+    if isinstance(a, torch.Tensor):
+        return ctypes.c_void_p(a.data_ptr())
+    return a
+
+
+def call(name, *args):
+    L = _l.load()
+    _l.check(getattr(L, name)(*[_arg(a) for a in args], _stream()), name)
+
+
+def host_floats(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def make_rpn_levels(shapes, strides, cell_anchors, ch_stride, scale_clamp, min_box_size=0.0):
+    """shapes: [(H,W)] per level; cell_anchors: per level list of A [x0,y0,x1,y1] (python floats / tensors)."""
+    lv = _l.RpnLevels()
+    lv.num_levels = len(shapes)
+    lv.num_anchors = len(cell_anchors[0])
+    off = 0
+    for i, ((h, w), s) in enumerate(zip(shapes, strides)):
+        lv.h[i], lv.w[i], lv.stride[i], lv.loc_off[i] = int(h), int(w), int(s), off
+        off += int(h) * int(w)
+        for a in range(lv.num_anchors):
+            for k in range(4):
+                lv.cell[i][a][k] = float(cell_anchors[i][a][k])
+    lv.total_locs = off
+    lv.ch_stride = ch_stride
+    lv.scale_clamp = scale_clamp
+    lv.min_box_size = min_box_size
+    return lv
+
+
+def roi_align(feats, rois, roi_batch, out=None, dout=None, dfeats=None, *, scales, pooled=7, min_level=2,
+              canonical_box_size=224.0, canonical_level=4, num_valid=None):
+    """feats: list of (N,H,W,C) contiguous channels-last maps.  Forward if dout is None else backward."""
+    p = _l.RoiAlignParams()
+    for i, f in enumerate(feats):
+        assert f.is_contiguous()
+        p.feat[i] = f.data_ptr()
+        p.feat_h[i], p.feat_w[i] = f.shape[1], f.shape[2]
+        p.scale[i] = float(scales[i])
+        if dfeats is not None:
+            assert dfeats[i].dtype == torch.float32 and dfeats[i].is_contiguous()
+            p.dfeat[i] = dfeats[i].data_ptr()
+    p.num_levels = len(feats)
+    p.min_level = min_level
+    p.canonical_box_size = canonical_box_size
+    p.canonical_level = canonical_level
+    p.channels = feats[0].shape[3]
+    p.pooled = pooled
+    p.dtype = _dt(feats[0])
+    p.rois = rois.data_ptr()
+    p.roi_batch = roi_batch.data_ptr()
+    p.num_valid = num_valid.data_ptr() if num_valid is not None else None
+    p.num_rois = rois.shape[0]
+    L = _l.load()
+    if dout is None:
+        p.out = out.data_ptr()
+        _l.check(L.aldi_roi_align_forward(ctypes.byref(p), _stream()), "aldi_roi_align_forward")
+    else:
+        p.dout = dout.data_ptr()
+        _l.check(L.aldi_roi_align_backward(ctypes.byref(p), _stream()), "aldi_roi_align_backward")

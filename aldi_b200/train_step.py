@@ -1,0 +1,397 @@
+"""The ALDI++ teacher–student training step on one B200 (one process per GPU).
+
+`B200TrainStep` is the object the reference's trainer seams are cut at: it owns the flat
+student / teacher / gradient / momentum buffers and exposes
+    ema_update(iter)            <- ALDITrainer.before_step          (aldi/trainer.py:242-246, aldi/ema.py:52-57)
+    run_model(data) -> losses   <- _ALDITrainer.run_model           (aldi/trainer.py:129-130, :28-117)
+    optimizer_step(lr)          <- SimpleTrainer/AMPTrainer.run_step (aldi/dropin.py:121,177-178)
+Semantics reproduced from the reference (SURVEY.md §8a traps): micro-batching and the 1/num_grad_accum
+scaling incl. uneven micro-batches (T6, T9), zero-weighted hard losses kept in the dict (T5), the RPN
+distillation index quirk (T1, in the kernel), a fresh anchor sampling on the teacher RPN with pseudo GT
+(T2), one sampling seed per distillation forward shared by student and teacher RoI heads (T3), EMA over
+every state_dict entry incl. FrozenBN buffers (T7).
+
+Schedule differences that do not change results: the teacher trunk + RPN head run ONCE per micro-batch
+(pass #1 eval-mode inference and pass #2 train-mode forward see identical FrozenBN features); gradients of all
+micro-batches accumulate into one flat buffer that is all-reduced once per step (the reference all-reduces
+per micro-batch backward; averaging is linear).
+"""
+import math
+import random
+
+import torch
+import torch.distributed as dist
+
+from . import lib as _l
+from . import ops, sampling
+from .detector import Detector, DetectorWeights, FlatLayout
+
+SRC_KEYS = ("loss_cls", "loss_box_reg", "loss_rpn_cls", "loss_rpn_loc")
+SOFT_KEYS = ("loss_obj_bce", "loss_rpn_l1", "loss_cls_ce", "loss_roih_l1")
+
+
+class StepConfig:
+    """The cfg values the hot path reads (names follow aldi/config.py and detectron2 defaults)."""
+
+    def __init__(self, **kw):
+        self.num_classes = 8
+        self.ims_per_gpu = 2                     # SOLVER.IMS_PER_GPU
+        self.ema_alpha = 0.9996                  # EMA.ALPHA
+        self.ema_start_iter = 0                  # EMA.START_ITER
+        self.pseudo_threshold = 0.8              # DOMAIN_ADAPT.TEACHER.THRESHOLD
+        self.do_hard_cls = self.do_hard_obj = self.do_hard_rpn_reg = self.do_hard_roi_reg = False
+        self.do_cls_dst = self.do_obj_dst = self.do_rpn_reg_dst = self.do_roih_reg_dst = True
+        self.cls_temperature = 1.0               # DOMAIN_ADAPT.DISTILL.CLS_TMP
+        self.obj_temperature = 1.0               # DOMAIN_ADAPT.DISTILL.OBJ_TMP
+        self.cls_loss_type = "CE"                # DOMAIN_ADAPT.CLS_LOSS_TYPE
+        self.base_lr = 0.06                      # SOLVER.BASE_LR
+        self.momentum = 0.9
+        self.weight_decay = 1e-4
+        self.rpn_pre_topk = (2000, 1000)         # (train, test) per level
+        self.rpn_post_topk = (1000, 1000)
+        self.rpn_nms_thresh = 0.7
+        self.rpn_batch = 256
+        self.rpn_pos_fraction = 0.5
+        self.rpn_iou = (0.3, 0.7)
+        self.roi_batch = 512
+        self.roi_pos_fraction = 0.25
+        self.roi_iou = 0.5
+        self.test_score_thresh = 0.05
+        self.test_nms_thresh = 0.5
+        self.test_topk = 100
+        self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": parity path
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError("unknown StepConfig field %s" % k)
+            setattr(self, k, v)
+
+    @property
+    def distill_enabled(self):                   # aldi/distill.py:140-142
+        return any([self.do_hard_cls, self.do_hard_obj, self.do_hard_rpn_reg, self.do_hard_roi_reg, self.do_cls_dst,
+                    self.do_obj_dst, self.do_rpn_reg_dst, self.do_roih_reg_dst])
+
+
+class Batch:
+    """A micro-batch staged on the device: uint8 canvas, valid sizes, padded GT."""
+
+    def __init__(self, data, device, with_gt):
+        n = len(data)
+        hs = [int(d["image"].shape[1]) for d in data]
+        ws = [int(d["image"].shape[2]) for d in data]
+        hp = (max(hs) + 31) // 32 * 32
+        wp = (max(ws) + 31) // 32 * 32
+        same = all(h == hp and w == wp for h, w in zip(hs, ws))
+        if same:
+            self.images = torch.stack([d["image"] for d in data]).to(device, non_blocking=True)
+        else:
+            canvas = torch.zeros(n, 3, hp, wp, dtype=torch.uint8)
+            for i, d in enumerate(data):
+                canvas[i, :, :hs[i], :ws[i]] = d["image"]
+            self.images = canvas.to(device, non_blocking=True)
+        self.h2d_bytes = self.images.numel()
+        self.n, self.hp, self.wp = n, hp, wp
+        self.sizes = torch.tensor([[h, w] for h, w in zip(hs, ws)], dtype=torch.int32).to(device, non_blocking=True)
+        self.gt = None
+        if with_gt:
+            self.gt = GroundTruth.from_host([d["boxes"] for d in data], [d["classes"] for d in data], device)
+
+
+class GroundTruth:
+    def __init__(self, boxes, classes, counts, gmax, scores=None):
+        self.boxes, self.classes, self.counts, self.gmax, self.scores = boxes, classes, counts, gmax, scores
+
+    @staticmethod
+    def from_host(boxes_list, classes_list, device):
+        n = len(boxes_list)
+        gmax = max(32, (max([len(b) for b in boxes_list] + [1]) + 31) // 32 * 32)
+        b = torch.zeros(n, gmax, 4)
+        c = torch.zeros(n, gmax, dtype=torch.int32)
+        cnt = torch.zeros(n, dtype=torch.int32)
+        for i, (bb, cc) in enumerate(zip(boxes_list, classes_list)):
+            k = len(bb)
+            if k:
+                b[i, :k] = bb.float()
+                c[i, :k] = cc.to(torch.int32)
+            cnt[i] = k
+        return GroundTruth(b.to(device, non_blocking=True), c.to(device, non_blocking=True),
+                           cnt.to(device, non_blocking=True), gmax)
+
+
+class B200TrainStep:
+    def __init__(self, cfg, state_dict, device="cuda:0", teacher_state_dict=None, process_group=None):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.dtype = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
+        self.dtc = _l.BF16 if cfg.dtype == "bf16" else _l.F32
+        _l.load()  # fail loudly if the CUDA library is missing
+        self.layout = FlatLayout(cfg.num_classes)
+        self.det = Detector(cfg.num_classes)
+        flat = self.layout.pack_state_dict(state_dict).to(self.device)
+        tflat = flat.clone() if teacher_state_dict is None else \
+            self.layout.pack_state_dict(teacher_state_dict).to(self.device)
+        self.student = DetectorWeights(self.layout, flat, self.dtype)
+        self.teacher = DetectorWeights(self.layout, tflat, self.dtype)
+        self.student.enable_dgrad()
+        self.nt = self.layout.num_trainable
+        self.grad = torch.zeros(self.nt, device=self.device)
+        self.momentum_buf = torch.zeros(self.nt, device=self.device)
+        self.student.refresh()
+        self.teacher.refresh()
+        self.loss_acc = torch.zeros(16, device=self.device)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.pg = process_group
+        self.iter = 0
+        self.h2d_bytes = 0
+        self.last_pseudo = None
+        self.debug = {}
+
+    # ---- aldi/ema.py:52-57 -------------------------------------------------------------------------
+    def ema_update(self, it):
+        alpha = 0.0 if it <= self.cfg.ema_start_iter else self.cfg.ema_alpha
+        ops.ema_update(self.teacher.flat, self.student.flat, alpha)
+        self.teacher.refresh()
+
+    # ---- aldi/trainer.py:28-117 ----------------------------------------------------------------------
+    def run_model(self, data):
+        labeled_weak, labeled_strong, unlabeled_weak, unlabeled_strong = data
+        cfg = self.cfg
+        mb = cfg.ims_per_gpu
+        do_weak, do_strong = labeled_weak is not None, labeled_strong is not None
+        do_distill = cfg.distill_enabled and unlabeled_weak is not None
+        total = sum(len(s or []) for s in (labeled_weak, labeled_strong, unlabeled_weak))
+        accum = total // mb
+        assert accum >= 1, "SOLVER.IMS_PER_GPU larger than the per-GPU batch"
+        gscale = 1.0 / accum
+        self.loss_acc.zero_()
+        self.h2d_bytes = 0
+        self.seed = random.randint(0, 2 ** 32 - 1)          # aldi/helpers.py:19-23
+        self.seed_log = {}
+        out_keys = []
+        pass_id = 0
+        for tag, d in (("source_weak", labeled_weak), ("source_strong", labeled_strong)):
+            if d is None:
+                continue
+            for i in range(0, len(d), mb):
+                self.seed_log[pass_id] = self.seed
+                self._source_microbatch(d[i:i + mb], gscale, pass_id)
+                pass_id += 1
+            out_keys += [(k + "_" + tag, j) for j, k in enumerate(SRC_KEYS)]
+        if do_distill:
+            assert len(unlabeled_weak) == len(unlabeled_strong), "Teacher and student data must be the same length."
+            for i in range(0, len(unlabeled_weak), mb):
+                self.seed = random.randint(0, 2 ** 32 - 1)  # seeder.reset_seed(), aldi/distill.py:150
+                self.seed_log[100 + pass_id] = self.seed
+                self._distill_microbatch(unlabeled_weak[i:i + mb], unlabeled_strong[i:i + mb], gscale, 100 + pass_id)
+                pass_id += 1
+            out_keys += [(k + "_distill", 4 + j) for j, k in enumerate(SRC_KEYS)]
+            soft_on = (cfg.do_obj_dst, cfg.do_rpn_reg_dst, cfg.do_cls_dst, cfg.do_roih_reg_dst)
+            out_keys += [(k + "_distill", 8 + j) for j, (k, on) in enumerate(zip(SOFT_KEYS, soft_on)) if on]
+        self._out_keys = out_keys
+        return LossDict(self, out_keys)
+
+    def losses_to_host(self, out_keys=None):
+        vals = self.loss_acc.cpu()  # one D2H read of the step's loss vector (the reference syncs per loss)
+        if int(self.err_flag.item()):
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+        return {k: float(vals[j]) for k, j in (out_keys or self._out_keys)}
+
+    # ---- one source micro-batch: student forward + backward with hard losses --------------------------
+    def _source_microbatch(self, data, gscale, pass_id):
+        cfg, det, W = self.cfg, self.det, self.student
+        b = Batch(data, self.device, with_gt=True)
+        self.h2d_bytes += b.h2d_bytes
+        fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=True)
+        n = b.n
+        d_rpn = torch.zeros(n, fw["lv"].total_locs, 64, device=self.device, dtype=self.dtype)
+        ops.call("aldi_rpn_loss", fw["rpn_out"], _l.ctypes.byref(fw["lv"]), n, fw["labels"], fw["matched"], b.gt.boxes,
+                 b.gt.counts, b.gt.gmax, cfg.rpn_batch, 1.0, 1.0, gscale, d_rpn, self.dtc, 64, 0, self.loss_acc[2:4])
+        m = n * cfg.roi_batch
+        dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
+        ops.call("aldi_roi_loss", fw["pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"], fw["rois"], fw["roi_gt"],
+                 fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)), 1.0, 1.0, gscale, dpred, self.dtc, 64,
+                 self.loss_acc[0:2])
+        det.backward(W, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"], dpred,
+                     fw["rois"], fw["roi_batch"])
+
+    def _student_forward(self, b, gt, pass_id, want_rpn_labels):
+        cfg, det, W = self.cfg, self.det, self.student
+        n = b.n
+        feats, saved = det.backbone(W, b.images, b.sizes, save=True)
+        lv = det.levels(feats)
+        rpn_out, rpn_ts = det.rpn_head(W, feats, lv, save=True)
+        out = {"feats": feats, "saved": saved, "lv": lv, "rpn_out": rpn_out, "rpn_ts": rpn_ts}
+        if want_rpn_labels:
+            out["labels"], out["matched"], out["rpn_stats"] = self._label_anchors(lv, n, gt, pass_id, sampling.SITE_RPN)
+        props = det.proposals(rpn_out, lv, b.sizes, cfg.rpn_pre_topk[0], cfg.rpn_post_topk[0], cfg.rpn_nms_thresh,
+                              self.err_flag)
+        out["props"] = props
+        m = n * cfg.roi_batch
+        rois = torch.empty(m, 4, device=self.device)
+        roi_gt = torch.empty(m, 4, device=self.device)
+        roi_batch = torch.empty(m, dtype=torch.int32, device=self.device)
+        roi_class = torch.empty(m, dtype=torch.int32, device=self.device)
+        roi_src = torch.empty(m, dtype=torch.int32, device=self.device)
+        roi_count = torch.zeros(n, dtype=torch.int32, device=self.device)
+        roi_stats = torch.zeros(n, 2, dtype=torch.int32, device=self.device)
+        salts = self._salts(n, pass_id, sampling.SITE_ROI)
+        ops.call("aldi_roi_label_sample", props["boxes"], props["count"], props["boxes"].shape[1], n, gt.boxes,
+                 gt.classes, gt.counts, gt.gmax, cfg.roi_iou, cfg.num_classes, cfg.roi_batch, cfg.roi_pos_fraction,
+                 self.seed, salts, 1, rois, roi_batch, roi_class, roi_gt, roi_src, roi_count, roi_stats)
+        pred, head_saved = det.box_head(W, feats, rois, roi_batch, save=True)
+        out.update(rois=rois, roi_gt=roi_gt, roi_batch=roi_batch, roi_class=roi_class, roi_src=roi_src,
+                   roi_count=roi_count, roi_stats=roi_stats, pred=pred, head_saved=head_saved)
+        return out
+
+    def _salts(self, n, pass_id, site):
+        return torch.tensor([sampling.make_salt(pass_id, site, i) for i in range(n)],
+                            dtype=torch.int32).to(self.device)
+
+    def _label_anchors(self, lv, n, gt, pass_id, site):
+        cfg = self.cfg
+        total = lv.total_locs * lv.num_anchors
+        labels = torch.empty(n, total, dtype=torch.int8, device=self.device)
+        matched = torch.empty(n, total, dtype=torch.int32, device=self.device)
+        stats = torch.zeros(n, 2, dtype=torch.int32, device=self.device)
+        ws = torch.empty(n, gt.gmax, dtype=torch.int32, device=self.device)
+        ops.call("aldi_rpn_label_anchors", _l.ctypes.byref(lv), n, gt.boxes, gt.counts, gt.gmax, cfg.rpn_iou[0],
+                 cfg.rpn_iou[1], cfg.rpn_batch, cfg.rpn_pos_fraction, self.seed, self._salts(n, pass_id, site), ws,
+                 labels, matched, stats)
+        return labels, matched, stats
+
+    # ---- teacher: trunk + RPN once, eval-mode detections -> pseudo labels --------------------------------
+    def teacher_forward(self, b):
+        cfg, det, W = self.cfg, self.det, self.teacher
+        feats, _ = det.backbone(W, b.images, b.sizes, save=False)
+        lv = det.levels(feats)
+        rpn_out, _ = det.rpn_head(W, feats, lv, save=False)
+        return feats, lv, rpn_out
+
+    def pseudo_label(self, b, feats, lv, rpn_out, score_thresh=None):
+        """aldi/pseudolabeler.py:15-30: teacher.inference(do_postprocess=False) then scores > threshold."""
+        cfg, det, W = self.cfg, self.det, self.teacher
+        n = b.n
+        props = det.proposals(rpn_out, lv, b.sizes, cfg.rpn_pre_topk[1], cfg.rpn_post_topk[1], cfg.rpn_nms_thresh)
+        p = props["boxes"].shape[1]
+        roi_batch = torch.arange(n, dtype=torch.int32, device=self.device).repeat_interleave(p)
+        pred, _ = det.box_head(W, feats, props["boxes"].view(n * p, 4), roi_batch, save=False)
+        # greedy NMS in descending score order: a detection's fate depends only on higher-scoring ones, so
+        # candidates below the pseudo-label threshold can never change the thresholded result
+        thr = max(cfg.test_score_thresh, cfg.pseudo_threshold) if score_thresh is None else score_thresh
+        dets = det.detections(pred, props, b.sizes, thr, cfg.test_nms_thresh, cfg.test_topk)
+        gmax = 128
+        gb = torch.zeros(n, gmax, 4, device=self.device)
+        gc = torch.zeros(n, gmax, dtype=torch.int32, device=self.device)
+        gs = torch.zeros(n, gmax, device=self.device)
+        cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
+        ops.call("aldi_pseudo_label_threshold", dets["boxes"], dets["scores"], dets["cats"], dets["count"],
+                 cfg.test_topk, n, cfg.pseudo_threshold, gb, gc, gs, cnt, gmax)
+        return GroundTruth(gb, gc, cnt, gmax, gs), dets
+
+    # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
+    def _distill_microbatch(self, weak, strong, gscale, pass_id):
+        cfg, det = self.cfg, self.det
+        bw = Batch(weak, self.device, with_gt=False)
+        bs = Batch(strong, self.device, with_gt=False)
+        self.h2d_bytes += bw.h2d_bytes + bs.h2d_bytes
+        n = bw.n
+        t_feats, t_lv, t_rpn_out = self.teacher_forward(bw)
+        pseudo, _ = self.pseudo_label(bw, t_feats, t_lv, t_rpn_out)
+        self.last_pseudo = pseudo
+        hard_rpn = cfg.do_hard_obj or cfg.do_hard_rpn_reg
+        fw = self._student_forward(bs, pseudo, pass_id, want_rpn_labels=hard_rpn)
+        # teacher RoI head on the student's sampled proposals (ReplaceProposalsOnce + shared seed)
+        t_pred, _ = det.box_head(self.teacher, t_feats, fw["rois"], fw["roi_batch"], save=False)
+        # fresh anchor sampling by the TEACHER's RPN on the pseudo labels (T2)
+        labels, _, stats = self._label_anchors(t_lv, n, pseudo, pass_id, sampling.SITE_RPN_DISTILL)
+        lv = fw["lv"]
+        d_rpn = torch.zeros(n, lv.total_locs, 64, device=self.device, dtype=self.dtype)
+        acc = 0
+        if hard_rpn:
+            ops.call("aldi_rpn_loss", fw["rpn_out"], _l.ctypes.byref(lv), n, fw["labels"], fw["matched"], pseudo.boxes,
+                     pseudo.counts, pseudo.gmax, cfg.rpn_batch, 1.0 if cfg.do_hard_obj else 0.0,
+                     1.0 if cfg.do_hard_rpn_reg else 0.0, gscale, d_rpn, self.dtc, 64, 0, self.loss_acc[6:8])
+            acc = 1
+        ops.call("aldi_distill_rpn_loss", fw["rpn_out"], t_rpn_out, _l.ctypes.byref(lv), n, labels, stats,
+                 cfg.obj_temperature, 1.0 if cfg.do_obj_dst else 0.0, 1.0 if cfg.do_rpn_reg_dst else 0.0, gscale, d_rpn,
+                 self.dtc, 64, acc, self.loss_acc[8:10])
+        m = n * cfg.roi_batch
+        dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
+        acc = 0
+        if cfg.do_hard_cls or cfg.do_hard_roi_reg:
+            ops.call("aldi_roi_loss", fw["pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"], fw["rois"],
+                     fw["roi_gt"], fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)),
+                     1.0 if cfg.do_hard_cls else 0.0, 1.0 if cfg.do_hard_roi_reg else 0.0, gscale, dpred, self.dtc, 64,
+                     self.loss_acc[4:6])
+            acc = 1
+        ops.call("aldi_distill_roi_loss", fw["pred"], t_pred, det.PRED_CH, m, cfg.num_classes, fw["roi_class"],
+                 fw["roi_count"], n, cfg.cls_temperature, 1 if cfg.cls_loss_type == "KL" else 0,
+                 1.0 if cfg.do_cls_dst else 0.0, 1.0 if cfg.do_roih_reg_dst else 0.0, gscale, dpred, self.dtc, 64, acc,
+                 self.loss_acc[10:12])
+        self.debug = {"fw": fw, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": labels, "stats": stats,
+                      "pseudo": pseudo} if self.debug is not None else None
+        det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, lv, fw["head_saved"],
+                     dpred, fw["rois"], fw["roi_batch"])
+
+    # ---- aldi/dropin.py:121 optimizer.step() (torch.optim.SGD via D2 build_optimizer) ---------------------
+    def lr_at(self, it, warmup_iters=100, warmup_factor=0.01, steps=(), gamma=0.1):
+        """detectron2 WarmupMultiStepLR (linear warm-up), configs/Base-RCNN-FPN.yaml:12-21."""
+        lr = self.cfg.base_lr * gamma ** sum(1 for s in steps if it >= s)
+        if it < warmup_iters:
+            a = it / warmup_iters
+            lr *= warmup_factor * (1 - a) + a
+        return lr
+
+    def allreduce_grads(self):
+        """One sum-all-reduce of the flat gradient buffer per step (DDP averages per micro-batch backward)."""
+        if self.pg is not None and dist.get_world_size(self.pg) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            return 1.0 / dist.get_world_size(self.pg)
+        return 1.0
+
+    def optimizer_step(self, lr=None):
+        lr = self.lr_at(self.iter) if lr is None else lr
+        gs = self.allreduce_grads()
+        p = self.student.flat[:self.nt]
+        ops.sgd_momentum_step(p, self.momentum_buf, self.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
+        self.grad.zero_()
+        self.student.refresh()
+        self.iter += 1
+
+    # ---- a whole iteration: before_step + run_step ----------------------------------------------------------
+    def step(self, data, lr=None):
+        self.ema_update(self.iter)
+        losses = self.run_model(data)
+        self.optimizer_step(lr)
+        return losses
+
+    def state_dict(self, which="student"):
+        w = self.student if which == "student" else self.teacher
+        return self.layout.unpack_state_dict(w.flat)
+
+
+class LossDict(dict):
+    """dict[str -> float] materialised lazily with ONE device->host read (keys known without a sync)."""
+
+    def __init__(self, step, keys):
+        super().__init__()
+        self._step, self._keys, self._done = step, keys, False
+        for k, _ in keys:
+            dict.__setitem__(self, k, None)
+
+    def _materialise(self):
+        if not self._done:
+            for k, v in self._step.losses_to_host(self._keys).items():
+                dict.__setitem__(self, k, v)
+            self._done = True
+
+    def __getitem__(self, k):
+        self._materialise()
+        return dict.__getitem__(self, k)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)

@@ -245,8 +245,11 @@ class ALDIDistiller:
         s_logits, s_deltas = self.io["s_rpn_head"]
         t_logits, t_deltas = self.io["t_rpn_head"]
         rpn = self.teacher.proposal_generator
+        d2.SAMPLE_CTX["site_override"] = "rpn_distill"
         labels = torch.stack(rpn.label_and_sample_anchors(
             self.io["t_anchors"], [i["instances"].to(self.teacher.device) for i in teacher_inputs])[0])
+        d2.SAMPLE_CTX["site_override"] = None
+        self.io["distill_labels"] = labels
         valid_mask = torch.flatten(labels >= 0)
         fg_mask = labels == 1
         t_probs = torch.sigmoid(d2.cat([torch.flatten(t) for t in t_logits]) / self.obj_temperature)
@@ -318,8 +321,12 @@ def run_model_labeled_unlabeled(model, distiller, data, model_batch_size, backwa
             losses = {k: v * 0 if not cond(k) else v for k, v in losses.items()}
             do_backward(sum(losses.values()) / num_grad_accum_steps)
 
+    passes = [0]
+
     def do_training_step(d, name, cond, **kw):
         for i in range(0, len(d), model_batch_size):
+            d2.SAMPLE_CTX["pass"] = passes[0]
+            passes[0] += 1
             loss = model(d[i:i + model_batch_size], **kw)
             maybe_do_backward(loss, cond)
             add_to_loss_dict(loss, name, cond)
@@ -334,6 +341,8 @@ def run_model_labeled_unlabeled(model, distiller, data, model_batch_size, backwa
     if do_distill:
         assert len(unlabeled_weak) == len(unlabeled_strong)
         for i in range(0, len(unlabeled_weak), model_batch_size):
+            d2.SAMPLE_CTX["pass"] = 100 + passes[0]
+            passes[0] += 1
             dl = distiller(unlabeled_weak[i:i + model_batch_size], unlabeled_strong[i:i + model_batch_size])
             maybe_do_backward(dl, lambda k: k != "_")
             add_to_loss_dict(dl, "distill", lambda k: k != "_")

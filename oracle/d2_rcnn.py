@@ -375,17 +375,20 @@ class Matcher:
 # needs an injectable, platform-independent choice (SURVEY.md §7 hard parts, T3).  `None` = reference
 # behaviour; tests install a callable (num_candidates, num_take, tag) -> LongTensor of positions.
 _CHOOSER = None
+# where in the step the current subsample_labels call sits (only read by an installed chooser)
+SAMPLE_CTX = {"pass": 0, "site": None, "site_override": None, "image": 0}
 
 
 def set_sample_chooser(fn):
+    """fn(candidate_indices: LongTensor, take: int, tag: 'pos'|'neg', ctx: dict) -> LongTensor of positions."""
     global _CHOOSER
     _CHOOSER = fn
 
 
-def _choose(numel, take, tag, device):
+def _choose(candidates, take, tag):
     if _CHOOSER is not None:
-        return _CHOOSER(numel, take, tag).to(device)
-    return torch.randperm(numel, device=device)[:take]
+        return _CHOOSER(candidates, take, tag, dict(SAMPLE_CTX)).to(candidates.device)
+    return torch.randperm(candidates.numel(), device=candidates.device)[:take]
 
 
 def subsample_labels(labels, num_samples, positive_fraction, bg_label):
@@ -395,8 +398,8 @@ def subsample_labels(labels, num_samples, positive_fraction, bg_label):
     num_pos = min(positive.numel(), num_pos)
     num_neg = num_samples - num_pos
     num_neg = min(negative.numel(), num_neg)
-    perm1 = _choose(positive.numel(), num_pos, "pos", positive.device)
-    perm2 = _choose(negative.numel(), num_neg, "neg", negative.device)
+    perm1 = _choose(positive, num_pos, "pos")
+    perm2 = _choose(negative, num_neg, "neg")
     return positive[perm1], negative[perm2]
 
 
@@ -744,7 +747,8 @@ class RPN(nn.Module):
         anchors = Boxes.cat(anchors)
         gt_boxes = [x.gt_boxes for x in gt_instances]
         gt_labels, matched_gt_boxes = [], []
-        for gt_boxes_i in gt_boxes:
+        for i, gt_boxes_i in enumerate(gt_boxes):
+            SAMPLE_CTX["site"], SAMPLE_CTX["image"] = SAMPLE_CTX["site_override"] or "rpn", i
             match_quality_matrix = pairwise_iou(gt_boxes_i, anchors)
             matched_idxs, gt_labels_i = self.anchor_matcher(match_quality_matrix)
             gt_labels_i = gt_labels_i.to(device=gt_boxes_i.device)
@@ -1045,7 +1049,8 @@ class StandardROIHeads(nn.Module):
             proposals = add_ground_truth_to_proposals(targets, proposals)
         proposals_with_gt = []
         num_fg_samples, num_bg_samples = [], []
-        for proposals_per_image, targets_per_image in zip(proposals, targets):
+        for i, (proposals_per_image, targets_per_image) in enumerate(zip(proposals, targets)):
+            SAMPLE_CTX["site"], SAMPLE_CTX["image"] = "roi", i
             has_gt = len(targets_per_image) > 0
             match_quality_matrix = pairwise_iou(targets_per_image.gt_boxes, proposals_per_image.proposal_boxes)
             matched_idxs, matched_labels = self.proposal_matcher(match_quality_matrix)

@@ -1,0 +1,77 @@
+"""Shared helpers for the GPU parity tests: run the CPU oracle and the B200 step on identical inputs."""
+import random
+
+import numpy as np
+import torch
+
+from aldi_b200 import arch, sampling, synth_data
+from oracle import aldi_ref, d2_rcnn as d2
+
+SITE = {"rpn": sampling.SITE_RPN, "roi": sampling.SITE_ROI, "rpn_distill": sampling.SITE_RPN_DISTILL}
+SOFT = dict(do_cls_dst=True, do_obj_dst=True, do_rpn_reg_dst=True, do_roih_reg_dst=True)
+
+
+def install_device_sampler(seed_log):
+    """Make the oracle draw the samples the device's hash sampler draws (see aldi_b200/sampling.py)."""
+
+    def chooser(candidates, take, tag, ctx):
+        salt = sampling.make_salt(ctx["pass"], SITE[ctx["site"]], ctx["image"])
+        pos = sampling.choose(seed_log[ctx["pass"]], salt, tag == "neg", candidates.cpu().numpy(), take)
+        return torch.from_numpy(pos)
+
+    d2.set_sample_chooser(chooser)
+
+
+def make_inputs(seed, n_l, n_u, h, w, teacher_mix=0.05):
+    s = arch.synthetic_state_dict(seed=seed)
+    o = arch.synthetic_state_dict(seed=seed + 1000)
+    t = {k: (1 - teacher_mix) * s[k] + teacher_mix * o[k] for k in s}
+    ls, uw, us = synth_data.synthetic_batch(seed, n_l, n_u, h, w)
+    return s, t, ls, uw, us
+
+
+def to_d2(batch, labeled):
+    out = []
+    for d in batch:
+        e = {"image": d["image"].clone(), "height": d["height"], "width": d["width"]}
+        if labeled:
+            e["instances"] = d2.Instances((d["height"], d["width"]), gt_boxes=d2.Boxes(d["boxes"].clone()),
+                                          gt_classes=d["classes"].clone())
+        out.append(e)
+    return out
+
+
+def oracle_models(sd_s, sd_t):
+    student, teacher = aldi_ref.ALDI(num_classes=8), aldi_ref.ALDI(num_classes=8)
+    student.load_state_dict(sd_s)
+    teacher.load_state_dict(sd_t)
+    return student.train(), teacher.train()
+
+
+def rel_err(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rpn_out_to_d2(rpn_out, lv, n):
+    """device (N, total_locs, 16) -> detectron2 head outputs ([N,A,H,W] logits, [N,4A,H,W] deltas) per level."""
+    logits, deltas = [], []
+    r = rpn_out.cpu()
+    for i in range(lv.num_levels):
+        h, w, off = lv.h[i], lv.w[i], lv.loc_off[i]
+        blk = r[:, off:off + h * w, :].reshape(n, h, w, -1)
+        logits.append(blk[..., :3].permute(0, 3, 1, 2).contiguous())
+        deltas.append(blk[..., 3:15].permute(0, 3, 1, 2).contiguous())
+    return logits, deltas
+
+
+def oracle_grads_internal(layout, model):
+    """oracle parameter gradients -> the flat-buffer element order of the device gradient."""
+    named = dict(model.named_parameters())
+    out = {}
+    for (layer, field), (off, n, key, shape) in layout.entries.items():
+        if off >= layout.num_trainable or field not in ("weight", "bias"):
+            continue
+        g = named[key].grad
+        out[key] = (off, n, None if g is None else layout.to_internal(layer, field, g))
+    return out

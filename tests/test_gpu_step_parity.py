@@ -1,0 +1,140 @@
+"""Whole-step parity: the B200 path in fp32 parity mode (CUDA-core fp32 convs, same kernels otherwise) against
+the CPU oracle on identical seeded inputs.  Tolerance from BASELINE north_star: 1e-3 relative on floats,
+bit-exact on box-index / NMS / sampling selections."""
+import random
+
+import pytest
+import torch
+
+import parity_utils as pu
+from oracle import aldi_ref, d2_rcnn as d2
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+
+def run_device(sd_s, sd_t, data, **cfg_kw):
+    from aldi_b200.train_step import B200TrainStep, StepConfig
+    cfg = StepConfig(dtype="fp32", ema_start_iter=-1, **cfg_kw)
+    step = B200TrainStep(cfg, sd_s, teacher_state_dict=sd_t)
+    random.seed(1234)
+    losses = step.run_model(data)
+    losses = dict(losses.items())
+    torch.cuda.synchronize()
+    return step, losses
+
+
+def check_losses(dev, ora):
+    assert set(dev) == set(ora), (sorted(dev), sorted(ora))
+    for k in ora:
+        o = float(ora[k])
+        assert abs(dev[k] - o) <= RTOL * max(abs(o), 1e-3), (k, dev[k], o)
+
+
+def check_grads(step, student):
+    g = step.grad.cpu()
+    worst = ("", 0.0)
+    for key, (off, n, ref) in pu.oracle_grads_internal(step.layout, student).items():
+        got = g[off:off + n]
+        if ref is None:
+            assert float(got.abs().max()) == 0.0, key
+            continue
+        e = pu.rel_err(got, ref)
+        if e > worst[1]:
+            worst = (key, e)
+        assert e < 5e-3, (key, e, float(ref.abs().max()))
+    return worst
+
+
+def test_source_only_step_matches_oracle():
+    """BASELINE config 1 shape of step: labeled_strong only (burn-in), hard losses."""
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(41, 2, 0, 128, 160)
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, None, None), ims_per_gpu=2)
+    pu.install_device_sampler(step.seed_log)
+    student, teacher = pu.oracle_models(sd_s, sd_t)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, aldi_ref.NullDistiller(), (None, pu.to_d2(ls, True), None, None),
+                                                   2, False, lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    check_losses(dev_losses, ora)
+    worst = check_grads(step, student)
+    print("source-only: losses", dev_losses, "worst grad rel err", worst)
+    # optimizer step (torch.optim.SGD) and EMA (aldi/ema.py)
+    params = [p for p in student.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt.step()
+    step.optimizer_step(lr=0.01)
+    new = step.state_dict("student")
+    for k, v in student.state_dict().items():
+        assert pu.rel_err(new[k], v) < 1e-4, k
+    ema = aldi_ref.EMA(teacher, 0.9996, -1)
+    ema.update_weights(student, 3)
+    step.ema_update(3)
+    tnew = step.state_dict("teacher")
+    for k, v in ema.model.state_dict().items():
+        assert torch.allclose(tnew[k], v, rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.parametrize("n_l,n_u,mb,h,w", [(2, 2, 2, 128, 160), (3, 3, 2, 96, 96)])
+def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w):
+    """ALDI++ step: source + distillation micro-batches (incl. the uneven T9 case)."""
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(21 + n_l, n_l, n_u, h, w)
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, uw, us), ims_per_gpu=mb)
+    pu.install_device_sampler(step.seed_log)
+    student, teacher = pu.oracle_models(sd_s, sd_t)
+    dist = aldi_ref.ALDIDistiller(teacher, student, **pu.SOFT)
+    uw_o, us_o = pu.to_d2(uw, False), pu.to_d2(us, False)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, pu.to_d2(ls, True), uw_o, us_o), mb, False,
+                                                   lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    # --- last distillation micro-batch: intermediate tensors, in pipeline order (first mismatch = culprit)
+    dbg = step.debug
+    n_last = len(uw) - (len(uw) - 1) // mb * mb
+    lv = dbg["fw"]["lv"]
+    t_log, t_del = pu.rpn_out_to_d2(dbg["t_rpn_out"], lv, n_last)
+    for a, b in zip(t_log + t_del, list(dist.io["t_rpn_head"][0]) + list(dist.io["t_rpn_head"][1])):
+        assert pu.rel_err(a, b) < RTOL, "teacher RPN head outputs"
+    pseudo = dbg["pseudo"]
+    cnt = pseudo.counts.cpu().tolist()
+    for i, d in enumerate(uw_o[-n_last:]):
+        inst = d["instances"]
+        assert cnt[i] == len(inst), ("pseudo-label count", i, cnt[i], len(inst))
+        assert torch.equal(pseudo.classes[i, :cnt[i]].cpu().long(), inst.gt_classes), "pseudo-label classes"
+        assert torch.allclose(pseudo.boxes[i, :cnt[i]].cpu(), inst.gt_boxes.tensor, rtol=1e-4, atol=1e-2)
+        assert torch.allclose(pseudo.scores[i, :cnt[i]].cpu(), inst.scores, rtol=1e-4, atol=1e-5)
+    s_log, s_del = pu.rpn_out_to_d2(dbg["fw"]["rpn_out"], lv, n_last)
+    for a, b in zip(s_log + s_del, list(dist.io["s_rpn_head"][0]) + list(dist.io["s_rpn_head"][1])):
+        assert pu.rel_err(a, b) < RTOL, "student RPN head outputs"
+    # sampled anchors of the distillation RPN loss: exact
+    assert torch.equal(dbg["labels"].cpu().to(torch.int8), dist.io["distill_labels"].to(torch.int8)), "distill anchor labels"
+    # box predictor outputs on the (identically sampled, identically ordered) RoIs
+    counts = dbg["fw"]["roi_count"].cpu().tolist()
+    rows = torch.cat([torch.arange(c) + i * step.cfg.roi_batch for i, c in enumerate(counts)])
+    K = step.cfg.num_classes
+    for name, dev_pred, ora_pred in (("student", dbg["fw"]["pred"], dist.io["s_boxpred"]),
+                                     ("teacher", dbg["t_pred"], dist.io["t_boxpred"])):
+        dp = dev_pred.cpu()[rows]
+        assert dp.shape[0] == ora_pred[0].shape[0], ("sampled RoI count", dp.shape, ora_pred[0].shape)
+        assert pu.rel_err(dp[:, :K + 1], ora_pred[0].detach()) < RTOL, name + " class logits"
+        assert pu.rel_err(dp[:, K + 1:5 * K + 1], ora_pred[1].detach()) < RTOL, name + " box deltas"
+    check_losses(dev_losses, ora)
+    worst = check_grads(step, student)
+    print("aldi step: losses", dev_losses, "pseudo counts", cnt, "worst grad rel err", worst)
+
+
+def test_empty_pseudo_labels():
+    """T2: no detection above the threshold -> 256 negatives per image still feed loss_obj_bce; loss_rpn_l1 == 0."""
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(77, 0, 2, 96, 128)
+    step, dev_losses = run_device(sd_s, sd_t, (None, None, uw, us), ims_per_gpu=2, pseudo_threshold=0.9999)
+    assert step.debug["pseudo"].counts.cpu().tolist() == [0, 0]
+    pu.install_device_sampler(step.seed_log)
+    student, teacher = pu.oracle_models(sd_s, sd_t)
+    dist = aldi_ref.ALDIDistiller(teacher, student, pseudo_label_threshold=0.9999, **pu.SOFT)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, None, pu.to_d2(uw, False), pu.to_d2(us, False)), 2,
+                                                   False, lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    check_losses(dev_losses, ora)
+    assert dev_losses["loss_rpn_l1_distill"] == 0.0
+    check_grads(step, student)
