@@ -246,7 +246,7 @@ class Detector:
         if W.stem_gemm:
             col = torch.empty(n, ho, wo, 192, device=dev, dtype=dt)
             ops.call("aldi_stem_im2col", images_u8, sizes, col, n, hp, wp, ho, wo, mean, std)
-            ops.conv(col, W.fwd["stem"], stem_out, scale=W.scale["stem"], bias=W.shift["stem"], relu=True)
+            ops.conv(col, W.fwd["stem"], stem_out, scale=W.scale["stem"], bias=W.shift["stem"], relu=True, algo_cin=147)
             del col
         else:
             x0 = torch.empty(n, hp, wp, 4, device=dev, dtype=torch.float32)

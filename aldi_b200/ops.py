@@ -13,6 +13,42 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelProfiler:
+    """Per-launch device timing with CUDA events on the launching stream (bench.py roofline numbers)."""
+
+    def __init__(self):
+        self.records = []  # (name, flops, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, e0, e1 in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["launches"] += 1
+        return out
+
+
+_PROFILER = None
+
+
+def set_profiler(p):
+    global _PROFILER
+    _PROFILER = p
+
+
+def _launch(name, fn, flops=0.0):
+    if _PROFILER is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    _PROFILER.records.append((name, flops, e0, e1))
+    return rc
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -60,12 +96,13 @@ def pack_weight(w, out, *, dgrad=False, scale=None, cout, taps, cin, cout_p, cin
     assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == cout * taps * cin
     assert out.is_contiguous() and out.numel() == cout_p * taps * cin_p
     L = _l.load()
-    _l.check(L.aldi_pack_weight(_ptr(w), _ptr(scale), _ptr(out), _dt(out), int(bool(dgrad)), cout, taps, cin, cout_p,
-                                cin_p, _stream()), "aldi_pack_weight")
+    _l.check(_launch("aldi_pack_weight", lambda: L.aldi_pack_weight(_ptr(w), _ptr(scale), _ptr(out), _dt(out),
+                                                                     int(bool(dgrad)), cout, taps, cin, cout_p, cin_p,
+                                                                     _stream())), "aldi_pack_weight")
 
 
 def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, bias=None, residual=None,
-         res_mode=0, mask=None, relu=False, accumulate=False, cout_store=None):
+         res_mode=0, mask=None, relu=False, accumulate=False, cout_store=None, algo_cin=None):
     """Implicit-GEMM conv/linear (forward or data-gradient).  x, out, residual, mask are channels-last
     (N,H,W,C) views; wp is the packed (cout_p, taps*C) operand.  bf16 inputs -> tcgen05 path, fp32 -> CUDA cores."""
     n, xh, xw, xc, x_sn, x_sh, x_sw = _cl4(x, "x")
@@ -102,10 +139,11 @@ def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
     p.out_sw = o_sw; p.out_sh = o_sh; p.out_sn = o_sn
     p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate))
     L = _l.load()
+    flops = 2.0 * n * oh * ow * p.cout_store * taps_h * taps_w * (algo_cin or xc)
     if x.dtype == torch.bfloat16:
-        _l.check(L.aldi_conv_tc(ctypes.byref(p), _stream()), "aldi_conv_tc")
+        _l.check(_launch("aldi_conv_tc", lambda: L.aldi_conv_tc(ctypes.byref(p), _stream()), flops), "aldi_conv_tc")
     else:
-        _l.check(L.aldi_conv_f32(ctypes.byref(p), _stream()), "aldi_conv_f32")
+        _l.check(_launch("aldi_conv_f32", lambda: L.aldi_conv_f32(ctypes.byref(p), _stream()), flops), "aldi_conv_f32")
 
 
 def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, cout_store=None,
@@ -126,10 +164,11 @@ def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
     p.cin_store = int(cin_store if cin_store is not None else xc)
     assert dw.numel() == p.cout_store * taps_h * taps_w * p.cin_store
     L = _l.load()
+    flops = 2.0 * n * oh * ow * p.cout_store * taps_h * taps_w * p.cin_store
     if x.dtype == torch.bfloat16:
-        _l.check(L.aldi_wgrad_tc(ctypes.byref(p), _stream()), "aldi_wgrad_tc")
+        _l.check(_launch("aldi_wgrad_tc", lambda: L.aldi_wgrad_tc(ctypes.byref(p), _stream()), flops), "aldi_wgrad_tc")
     else:
-        _l.check(L.aldi_wgrad_f32(ctypes.byref(p), _stream()), "aldi_wgrad_f32")
+        _l.check(_launch("aldi_wgrad_f32", lambda: L.aldi_wgrad_f32(ctypes.byref(p), _stream()), flops), "aldi_wgrad_f32")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -143,7 +182,8 @@ def _arg(a):
 
 def call(name, *args):
     L = _l.load()
-    _l.check(getattr(L, name)(*[_arg(a) for a in args], _stream()), name)
+    cargs = [_arg(a) for a in args]
+    _l.check(_launch(name, lambda: getattr(L, name)(*cargs, _stream())), name)
 
 
 def host_floats(vals):
@@ -195,7 +235,9 @@ def roi_align(feats, rois, roi_batch, out=None, dout=None, dfeats=None, *, scale
     L = _l.load()
     if dout is None:
         p.out = out.data_ptr()
-        _l.check(L.aldi_roi_align_forward(ctypes.byref(p), _stream()), "aldi_roi_align_forward")
+        _l.check(_launch("aldi_roi_align_forward", lambda: L.aldi_roi_align_forward(ctypes.byref(p), _stream())),
+                 "aldi_roi_align_forward")
     else:
         p.dout = dout.data_ptr()
-        _l.check(L.aldi_roi_align_backward(ctypes.byref(p), _stream()), "aldi_roi_align_backward")
+        _l.check(_launch("aldi_roi_align_backward", lambda: L.aldi_roi_align_backward(ctypes.byref(p), _stream())),
+                 "aldi_roi_align_backward")

@@ -81,14 +81,11 @@ class Batch:
         hp = (max(hs) + 31) // 32 * 32
         wp = (max(ws) + 31) // 32 * 32
         same = all(h == hp and w == wp for h, w in zip(hs, ws))
-        if same:
-            self.images = torch.stack([d["image"] for d in data]).to(device, non_blocking=True)
-        else:
-            canvas = torch.zeros(n, 3, hp, wp, dtype=torch.uint8)
-            for i, d in enumerate(data):
-                canvas[i, :, :hs[i], :ws[i]] = d["image"]
-            self.images = canvas.to(device, non_blocking=True)
-        self.h2d_bytes = self.images.numel()
+        # per-image async copies straight from the (pinned) host tensors into the device canvas
+        self.images = (torch.empty if same else torch.zeros)(n, 3, hp, wp, dtype=torch.uint8, device=device)
+        for i, d in enumerate(data):
+            self.images[i, :, :hs[i], :ws[i]].copy_(d["image"], non_blocking=True)
+        self.h2d_bytes = sum(d["image"].numel() for d in data if not d["image"].is_cuda)
         self.n, self.hp, self.wp = n, hp, wp
         self.sizes = torch.tensor([[h, w] for h, w in zip(hs, ws)], dtype=torch.int32).to(device, non_blocking=True)
         self.gt = None

@@ -1,0 +1,180 @@
+"""Selection kernels against the oracle's Detectron2 primitives on IDENTICAL inputs: index sets must be exact."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+import parity_utils as pu
+from oracle import d2_rcnn as d2
+
+pytestmark = pytest.mark.gpu
+
+
+def _levels(shapes):
+    from aldi_b200 import ops
+    from aldi_b200.detector import FPN_STRIDES, SCALE_CLAMP, cell_anchors
+    return ops.make_rpn_levels(shapes, FPN_STRIDES, cell_anchors(), 16, SCALE_CLAMP, 0.0)
+
+
+def _anchors(shapes):
+    gen = d2.DefaultAnchorGenerator()
+    return gen([torch.zeros(1, 1, h, w) for h, w in shapes])
+
+
+def _rand_gt(gen, n, h, w, count):
+    out = []
+    for _ in range(n):
+        k = count
+        xy = torch.rand(k, 2, generator=gen) * torch.tensor([w * 0.7, h * 0.7])
+        wh = 8 + torch.rand(k, 2, generator=gen) * torch.tensor([w * 0.3, h * 0.3])
+        out.append(torch.cat([xy, xy + wh], 1))
+    return out
+
+
+@pytest.mark.parametrize("count", [0, 1, 7, 40])
+def test_rpn_label_and_sample_exact(count):
+    from aldi_b200 import ops, sampling
+    from aldi_b200 import lib as _l
+    shapes = [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3)]
+    H, W, n = 128, 160, 3
+    gen = torch.Generator().manual_seed(count)
+    gts = _rand_gt(gen, n, H, W, count)
+    if count == 7:
+        gts[1][0] = torch.tensor([0., 0., 0., 0.])       # degenerate GT: IoU 0 with every anchor (D2 low-quality quirk)
+    lv = _levels(shapes)
+    seed, pass_id = 12345, 3
+    pu.install_device_sampler({pass_id: seed})
+    d2.SAMPLE_CTX["pass"] = pass_id
+    rpn = d2.RPN()
+    insts = [d2.Instances((H, W), gt_boxes=d2.Boxes(g), gt_classes=torch.zeros(len(g), dtype=torch.int64)) for g in gts]
+    ref_labels, ref_boxes = rpn.label_and_sample_anchors(_anchors(shapes), insts)
+    d2.set_sample_chooser(None)
+    gmax = 64
+    gb = torch.zeros(n, gmax, 4)
+    cnt = torch.zeros(n, dtype=torch.int32)
+    for i, g in enumerate(gts):
+        gb[i, :len(g)] = g
+        cnt[i] = len(g)
+    dev = "cuda"
+    total = lv.total_locs * 3
+    labels = torch.empty(n, total, dtype=torch.int8, device=dev)
+    matched = torch.empty(n, total, dtype=torch.int32, device=dev)
+    stats = torch.zeros(n, 2, dtype=torch.int32, device=dev)
+    ws = torch.empty(n, gmax, dtype=torch.int32, device=dev)
+    salts = torch.tensor([sampling.make_salt(pass_id, sampling.SITE_RPN, i) for i in range(n)], dtype=torch.int32, device=dev)
+    ops.call("aldi_rpn_label_anchors", ctypes.byref(lv), n, gb.to(dev), cnt.to(dev), gmax, 0.3, 0.7, 256, 0.5, seed, salts,
+             ws, labels, matched, stats)
+    torch.cuda.synchronize()
+    for i in range(n):
+        got, want = labels[i].cpu(), ref_labels[i]
+        diff = (got != want).nonzero().flatten()
+        assert diff.numel() == 0, ("image", i, "mismatches", diff.numel(), diff[:10].tolist(), got[diff[:10]].tolist(),
+                                   want[diff[:10]].tolist(), stats.cpu().tolist())
+        if count:
+            pos = (want == 1).nonzero().flatten()
+            mb = gb[i][matched[i].cpu().long()[pos]]
+            assert torch.equal(mb, ref_boxes[i][pos]), "matched gt boxes of positive anchors"
+
+
+def test_roi_label_sample_exact():
+    from aldi_b200 import ops, sampling
+    H, W, n, P = 128, 160, 2, 300
+    gen = torch.Generator().manual_seed(5)
+    gts = _rand_gt(gen, n, H, W, 6)
+    props = _rand_gt(gen, n, H, W, P)
+    for i in range(n):  # make some proposals overlap the gt well
+        props[i][:6] = gts[i] + torch.randn(6, 4, generator=gen) * 2
+    classes = [torch.randint(0, 8, (6,), generator=gen) for _ in range(n)]
+    seed, pass_id = 777, 100
+    pu.install_device_sampler({pass_id: seed})
+    d2.SAMPLE_CTX["pass"] = pass_id
+    heads = d2.StandardROIHeads(num_classes=8)
+    plist = [d2.Instances((H, W), proposal_boxes=d2.Boxes(p), objectness_logits=torch.zeros(P)) for p in props]
+    tlist = [d2.Instances((H, W), gt_boxes=d2.Boxes(g), gt_classes=c) for g, c in zip(gts, classes)]
+    with d2.EventStorage():
+        ref = heads.label_and_sample_proposals(plist, tlist)
+    d2.set_sample_chooser(None)
+    dev = "cuda"
+    gmax, S = 32, 512
+    gb = torch.zeros(n, gmax, 4); gc = torch.zeros(n, gmax, dtype=torch.int32); cnt = torch.full((n,), 6, dtype=torch.int32)
+    for i in range(n):
+        gb[i, :6] = gts[i]; gc[i, :6] = classes[i].int()
+    pb = torch.stack(props).to(dev)
+    pc = torch.full((n,), P, dtype=torch.int32, device=dev)
+    m = n * S
+    rois = torch.empty(m, 4, device=dev); rgt = torch.empty(m, 4, device=dev)
+    rb = torch.empty(m, dtype=torch.int32, device=dev); rc = torch.empty(m, dtype=torch.int32, device=dev)
+    rs = torch.empty(m, dtype=torch.int32, device=dev); rcount = torch.zeros(n, dtype=torch.int32, device=dev)
+    salts = torch.tensor([sampling.make_salt(pass_id, sampling.SITE_ROI, i) for i in range(n)], dtype=torch.int32, device=dev)
+    ops.call("aldi_roi_label_sample", pb, pc, P, n, gb.to(dev), gc.to(dev), cnt.to(dev), gmax, 0.5, 8, S, 0.25, seed, salts, 1,
+             rois, rb, rc, rgt, rs, rcount, None)
+    torch.cuda.synchronize()
+    for i in range(n):
+        c = int(rcount[i])
+        assert c == len(ref[i]), (c, len(ref[i]))
+        sl = slice(i * S, i * S + c)
+        assert torch.equal(rois[sl].cpu(), ref[i].proposal_boxes.tensor), "sampled boxes (order: fg asc, bg asc)"
+        assert torch.equal(rc[sl].cpu().long(), ref[i].gt_classes), "assigned classes"
+        fg = ref[i].gt_classes < 8
+        assert torch.equal(rgt[sl].cpu()[fg], ref[i].gt_boxes.tensor[fg]), "matched gt boxes"
+        assert bool((rc[i * S + c:(i + 1) * S] == -1).all()), "padding rows"
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_rpn_proposals_exact(training):
+    from aldi_b200.detector import Detector
+    shapes = [(64, 80), (32, 40), (16, 20), (8, 10), (4, 5)]
+    n, H, W = 2, 256, 320
+    gen = torch.Generator().manual_seed(3)
+    det = Detector(8)
+    lv = _levels(shapes)
+    rpn_out = torch.zeros(n, lv.total_locs, 16)
+    rpn_out[..., :3] = torch.randn(n, lv.total_locs, 3, generator=gen) * 2
+    rpn_out[..., 3:15] = torch.randn(n, lv.total_locs, 12, generator=gen) * 0.5
+    logits, deltas = pu.rpn_out_to_d2(rpn_out, lv, n)
+    rpn = d2.RPN()
+    rpn.train(training)
+    anchors = _anchors(shapes)
+    lg = [s.permute(0, 2, 3, 1).flatten(1) for s in logits]
+    dl = [x.view(n, -1, 4, x.shape[-2], x.shape[-1]).permute(0, 3, 4, 1, 2).flatten(1, -2) for x in deltas]
+    ref = rpn.predict_proposals(anchors, lg, dl, [(H, W - 7), (H - 30, W)])
+    sizes = torch.tensor([[H, W - 7], [H - 30, W]], dtype=torch.int32, device="cuda")
+    pre = 2000 if training else 1000
+    out = det.proposals(rpn_out.cuda(), lv, sizes, pre, 1000, 0.7)
+    torch.cuda.synchronize()
+    for i in range(n):
+        c = int(out["count"][i])
+        assert c == len(ref[i]), (i, c, len(ref[i]))
+        assert torch.equal(out["scores"][i, :c].cpu(), ref[i].objectness_logits), "proposal order / selection"
+        assert torch.allclose(out["boxes"][i, :c].cpu(), ref[i].proposal_boxes.tensor, rtol=1e-5, atol=1e-3)
+
+
+def test_roi_inference_exact():
+    from aldi_b200.detector import Detector
+    n, P, K, H, W = 2, 200, 8, 256, 320
+    gen = torch.Generator().manual_seed(9)
+    det = Detector(K)
+    props = torch.stack(_rand_gt(gen, n, H, W, P))
+    pred = torch.zeros(n * P, 64)
+    pred[:, :K + 1] = torch.randn(n * P, K + 1, generator=gen) * 3
+    pred[:, K + 1:5 * K + 1] = torch.randn(n * P, 4 * K, generator=gen)
+    layer = d2.FastRCNNOutputLayers(num_classes=K)
+    plist = [d2.Instances((H, W), proposal_boxes=d2.Boxes(props[i])) for i in range(n)]
+    ref, _ = layer.inference((pred[:, :K + 1], pred[:, K + 1:5 * K + 1]), plist)
+    pd = {"boxes": props.cuda(), "scores": torch.zeros(n, P, device="cuda"),
+          "count": torch.full((n,), P, dtype=torch.int32, device="cuda")}
+    sizes = torch.tensor([[H, W]] * n, dtype=torch.int32, device="cuda")
+    for thr in (0.05, 0.8):
+        out = det.detections(pred.cuda(), pd, sizes, thr)
+        torch.cuda.synchronize()
+        for i in range(n):
+            keep = ref[i].scores > thr
+            c = int(out["count"][i])
+            want = ref[i].scores[keep]
+            if thr == 0.05:
+                assert c == len(ref[i])
+            # with a higher candidate threshold the surviving detections above it are unchanged (greedy NMS)
+            assert torch.allclose(out["scores"][i, :len(want)].cpu(), want, rtol=1e-5), (thr, c, len(want))
+            assert torch.equal(out["cats"][i, :len(want)].cpu().long(), ref[i].pred_classes[keep])
+            assert torch.allclose(out["boxes"][i, :len(want)].cpu(), ref[i].pred_boxes.tensor[keep], rtol=1e-5, atol=1e-3)

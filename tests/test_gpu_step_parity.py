@@ -107,7 +107,11 @@ def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w):
     for a, b in zip(s_log + s_del, list(dist.io["s_rpn_head"][0]) + list(dist.io["s_rpn_head"][1])):
         assert pu.rel_err(a, b) < RTOL, "student RPN head outputs"
     # sampled anchors of the distillation RPN loss: exact
-    assert torch.equal(dbg["labels"].cpu().to(torch.int8), dist.io["distill_labels"].to(torch.int8)), "distill anchor labels"
+    got_l, want_l = dbg["labels"].cpu().to(torch.int8), dist.io["distill_labels"].to(torch.int8)
+    diff = (got_l != want_l).nonzero()
+    assert diff.shape[0] == 0, ("distill anchor labels", diff.shape[0], diff[:8].tolist(),
+                                got_l[got_l != want_l][:8].tolist(), want_l[got_l != want_l][:8].tolist(),
+                                dbg["stats"].cpu().tolist(), [(want_l[i] == 1).sum().item() for i in range(want_l.shape[0])])
     # box predictor outputs on the (identically sampled, identically ordered) RoIs
     counts = dbg["fw"]["roi_count"].cpu().tolist()
     rows = torch.cat([torch.arange(c) + i * step.cfg.roi_batch for i, c in enumerate(counts)])
