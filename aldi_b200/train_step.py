@@ -141,6 +141,10 @@ class B200TrainStep:
         self.h2d_bytes = 0
         self.last_pseudo = None
         self.debug = {}
+        # test seam (cf. the reference's DEBUG dict, aldi/trainer.py:24-25): pseudo labels to use INSTEAD of the
+        # device-computed ones, one GroundTruth per distillation micro-batch
+        self.pseudo_override = None
+        self.pseudo_log = []
 
     # ---- aldi/ema.py:52-57 -------------------------------------------------------------------------
     def ema_update(self, it):
@@ -163,6 +167,7 @@ class B200TrainStep:
         self.h2d_bytes = 0
         self.seed = random.randint(0, 2 ** 32 - 1)          # aldi/helpers.py:19-23
         self.seed_log = {}
+        self.pseudo_log = []
         out_keys = []
         pass_id = 0
         for tag, d in (("source_weak", labeled_weak), ("source_strong", labeled_strong)):
@@ -294,6 +299,10 @@ class B200TrainStep:
         t_feats, t_lv, t_rpn_out = self.teacher_forward(bw)
         pseudo, _ = self.pseudo_label(bw, t_feats, t_lv, t_rpn_out)
         self.last_pseudo = pseudo
+        if self.debug is not None:
+            self.pseudo_log.append(pseudo)
+        if self.pseudo_override is not None:
+            pseudo = self.pseudo_override[len(self.pseudo_log) - 1]
         hard_rpn = cfg.do_hard_obj or cfg.do_hard_rpn_reg
         fw = self._student_forward(bs, pseudo, pass_id, want_rpn_labels=hard_rpn)
         # teacher RoI head on the student's sampled proposals (ReplaceProposalsOnce + shared seed)

@@ -75,3 +75,35 @@ def oracle_grads_internal(layout, model):
         g = named[key].grad
         out[key] = (off, n, None if g is None else layout.to_internal(layer, field, g))
     return out
+
+
+def predict_seed_log(py_seed, n_source_mb, n_distill_mb):
+    """The sampling seeds B200TrainStep.run_model will draw after random.seed(py_seed)."""
+    rng = random.Random(py_seed)
+    log = {}
+    s0 = rng.randint(0, 2 ** 32 - 1)
+    p = 0
+    for _ in range(n_source_mb):
+        log[p] = s0
+        p += 1
+    for _ in range(n_distill_mb):
+        log[100 + p] = rng.randint(0, 2 ** 32 - 1)
+        p += 1
+    return log
+
+
+def pseudo_to_device(insts, device):
+    """oracle pseudo-label Instances of one micro-batch -> aldi_b200.train_step.GroundTruth."""
+    from aldi_b200.train_step import GroundTruth
+    n, gmax = len(insts), 128
+    b = torch.zeros(n, gmax, 4)
+    c = torch.zeros(n, gmax, dtype=torch.int32)
+    sc = torch.zeros(n, gmax)
+    cnt = torch.zeros(n, dtype=torch.int32)
+    for i, inst in enumerate(insts):
+        k = len(inst)
+        b[i, :k] = inst.gt_boxes.tensor
+        c[i, :k] = inst.gt_classes.int()
+        sc[i, :k] = inst.scores
+        cnt[i] = k
+    return GroundTruth(b.to(device), c.to(device), cnt.to(device), gmax, sc.to(device))

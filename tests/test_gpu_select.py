@@ -145,8 +145,14 @@ def test_rpn_proposals_exact(training):
     torch.cuda.synchronize()
     for i in range(n):
         c = int(out["count"][i])
-        assert c == len(ref[i]), (i, c, len(ref[i]))
-        assert torch.equal(out["scores"][i, :c].cpu(), ref[i].objectness_logits), "proposal order / selection"
+        got_s, want_s = out["scores"][i, :c].cpu(), ref[i].objectness_logits
+        m = min(c, len(want_s))
+        neq = (got_s[:m] != want_s[:m]).nonzero().flatten()
+        first = int(neq[0]) if neq.numel() else -1
+        info = (i, "count", c, len(want_s), "first mismatch", first,
+                got_s[max(first - 2, 0):first + 3].tolist(), want_s[max(first - 2, 0):first + 3].tolist(),
+                "n mismatches", neq.numel())
+        assert c == len(ref[i]) and neq.numel() == 0, info
         assert torch.allclose(out["boxes"][i, :c].cpu(), ref[i].proposal_boxes.tensor, rtol=1e-5, atol=1e-3)
 
 
