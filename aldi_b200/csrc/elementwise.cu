@@ -42,55 +42,100 @@ preprocess_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes,
 
 // ---- stem 7x7/2 conv as a GEMM: fused normalise + im2col of the uint8 image -------------------------
 // out: bf16 (N, Ho, Wo, 192): k = (r*7 + s)*3 + c for the 147 real taps, zero for k >= 147.
-// One thread produces 8 consecutive k (16 B store); zero padding = conv padding and canvas padding.
+// One block = 4 x 64 output pixels: the (13 x 133 x 3) input patch is read once, coalesced, into shared
+// memory (normalised, zero outside the valid image = conv padding + canvas padding); the 256 x 384 B of
+// output rows are then written as consecutive 16-byte vectors (fully coalesced, write-bound kernel).
+constexpr int ST_TH = 4, ST_TW = 64, ST_PH = 2 * ST_TH + 5, ST_PW = 2 * ST_TW + 5;
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes, __nv_bfloat16* __restrict__ out,
                    int n, int hin, int win, int ho, int wo, Norm3 nm) {
-  const size_t total = (size_t)n * ho * wo * 24;  // 24 vectors of 8 per output pixel
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int kv = (int)(i % 24);
-    size_t r = i / 24;
-    const int ox = (int)(r % wo);
-    r /= wo;
-    const int oy = (int)(r % ho);
-    const int b = (int)(r / ho);
-    const int vh = sizes[2 * b], vw = sizes[2 * b + 1];
+  __shared__ float patch[3][ST_PH][ST_PW + 1];
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
+  const int vh = sizes[2 * b], vw = sizes[2 * b + 1];
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < 3 * ST_PH * ST_PW; i += 256) {
+    const int px = i % ST_PW;
+    const int r = i / ST_PW;
+    const int py = r % ST_PH, c = r / ST_PH;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < vh && ix >= 0 && ix < vw)
+      v = __fdiv_rn(__fsub_rn((float)__ldg(in + (((size_t)b * 3 + c) * hin + iy) * win + ix), nm.mean[c]), nm.stdv[c]);
+    patch[c][py][px] = v;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < ST_TH * ST_TW * 24; v += 256) {
+    const int kv = v % 24;
+    const int pix = v / 24;
+    const int lx = pix % ST_TW, ly = pix / ST_TW;
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    if (oy >= ho || ox >= wo) continue;
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = kv * 8 + e;
-      float v = 0.f;
+      float val = 0.f;
       if (k < 147) {
         const int tap = k / 3, c = k - tap * 3;
         const int rr = tap / 7, ss = tap - rr * 7;
-        const int iy = oy * 2 + rr - 3, ix = ox * 2 + ss - 3;
-        if (iy >= 0 && iy < vh && ix >= 0 && ix < vw)
-          v = __fdiv_rn(__fsub_rn((float)__ldg(in + (((size_t)b * 3 + c) * hin + iy) * win + ix), nm.mean[c]),
-                        nm.stdv[c]);
+        val = patch[c][ly * 2 + rr][lx * 2 + ss];
       }
-      f[e] = v;
+      f[e] = val;
     }
     uint4 q;
     __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
     for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-    reinterpret_cast<uint4*>(out)[i] = q;
+    reinterpret_cast<uint4*>(out)[(((size_t)b * ho + oy) * wo + ox) * 24 + kv] = q;
   }
 }
 
-// ---- max_pool2d(kernel 3, stride 2, padding 1) on channels-last ------------------------------------
+// ---- max_pool2d(kernel 3, stride 2, padding 1) on channels-last, 16 bytes of channels per thread ------
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* f) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h, int w, int c, int ho, int wo) {
-  const size_t total = (size_t)n * ho * wo * c;
+  constexpr int V = Vec16<T>::N;
+  const int cv = c / V;
+  const size_t total = (size_t)n * ho * wo * cv;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c);
-    size_t r = i / c;
+    const int ch = (int)(i % cv) * V;
+    size_t r = i / cv;
     const int ox = (int)(r % wo);
     r /= wo;
     const int oy = (int)(r % ho);
     const int b = (int)(r / ho);
-    float m = -INFINITY;
+    float m[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) m[k] = -INFINITY;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
       const int iy = oy * 2 + dy;
@@ -99,10 +144,13 @@ maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h, int 
       for (int dx = -1; dx <= 1; ++dx) {
         const int ix = ox * 2 + dx;
         if (ix < 0 || ix >= w) continue;
-        m = fmaxf(m, to_f32<T>(in[(((size_t)b * h + iy) * w + ix) * c + ch]));
+        float f[V];
+        Vec16<T>::load(in + (((size_t)b * h + iy) * w + ix) * c + ch, f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], f[k]);
       }
     }
-    out[i] = from_f32<T>(m);
+    Vec16<T>::store(out + (((size_t)b * ho + oy) * wo + ox) * c + ch, m);
   }
 }
 
@@ -110,26 +158,46 @@ maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 sum2x2_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int h, int w, int c) {
-  const size_t total = (size_t)n * h * w * c;
+  constexpr int V = Vec16<T>::N;
+  const int cv = c / V;
+  const size_t total = (size_t)n * h * w * cv;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c);
-    size_t r = i / c;
+    const int ch = (int)(i % cv) * V;
+    size_t r = i / cv;
     const int x = (int)(r % w);
     r /= w;
     const int y = (int)(r % h);
     const int b = (int)(r / h);
     const size_t base = (((size_t)b * 2 * h + 2 * y) * 2 * w + 2 * x) * c + ch;
     const size_t row = (size_t)2 * w * c;
-    float s = to_f32<T>(src[base]) + to_f32<T>(src[base + c]) + to_f32<T>(src[base + row]) +
-              to_f32<T>(src[base + row + c]);
-    dst[i] = from_f32<T>(to_f32<T>(dst[i]) + s);
+    float a0[V], a1[V], a2[V], a3[V], d[V];
+    Vec16<T>::load(src + base, a0);
+    Vec16<T>::load(src + base + c, a1);
+    Vec16<T>::load(src + base + row, a2);
+    Vec16<T>::load(src + base + row + c, a3);
+    T* dp = dst + (((size_t)b * h + y) * w + x) * c + ch;
+    Vec16<T>::load(dp, d);
+#pragma unroll
+    for (int k = 0; k < V; ++k) d[k] += a0[k] + a1[k] + a2[k] + a3[k];
+    Vec16<T>::store(dp, d);
   }
 }
 
-// ---- dst += src (fp32 source, e.g. RoIAlign's atomic gradient buffer) -------------------------------
+// ---- dst += src (fp32 source, e.g. RoIAlign's atomic gradient buffer); n multiple of 8 --------------
 template <typename T>
 __global__ void __launch_bounds__(256) add_f32_kernel(T* __restrict__ dst, const float* __restrict__ src, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  constexpr int V = Vec16<T>::N;
+  const size_t nv = n / V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+    float d[V], s[V];
+    Vec16<T>::load(dst + i * V, d);
+#pragma unroll
+    for (int k = 0; k < V; k += 4) Vec16<float>::load(src + i * V + k, s + k);
+#pragma unroll
+    for (int k = 0; k < V; ++k) d[k] += s[k];
+    Vec16<T>::store(dst + i * V, d);
+  }
+  for (size_t i = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = from_f32<T>(to_f32<T>(dst[i]) + src[i]);
 }
 
@@ -189,8 +257,8 @@ extern "C" int aldi_stem_im2col(const uint8_t* images, const int* sizes, void* o
   ALDI_CHECK_ARG(images && sizes && out_bf16 && h_mean && h_std, "aldi_stem_im2col: null pointer");
   Norm3 nm;
   for (int i = 0; i < 3; ++i) { nm.mean[i] = h_mean[i]; nm.stdv[i] = h_std[i]; }
-  stem_im2col_kernel<<<grid_for((size_t)n * ho * wo * 24, 256), 256, 0, stream>>>(
-      images, sizes, (__nv_bfloat16*)out_bf16, n, hin, win, ho, wo, nm);
+  dim3 grid((wo + ST_TW - 1) / ST_TW, (ho + ST_TH - 1) / ST_TH, n);
+  stem_im2col_kernel<<<grid, 256, 0, stream>>>(images, sizes, (__nv_bfloat16*)out_bf16, n, hin, win, ho, wo, nm);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_stem_im2col");
   return ALDI_OK;
@@ -200,7 +268,8 @@ extern "C" int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, in
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(in && out, "aldi_maxpool3x3s2: null pointer");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  const int grid = grid_for((size_t)n * ho * wo * c, 256);
+  ALDI_CHECK_ARG(c % 8 == 0, "aldi_maxpool3x3s2: channels must be a multiple of 8");
+  const int grid = grid_for((size_t)n * ho * wo * c / 4, 256);
   if (dtype == ALDI_DTYPE_BF16)
     maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n, h, w, c, ho, wo);
   else
@@ -213,7 +282,8 @@ extern "C" int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, in
 extern "C" int aldi_sum2x2_accum(const void* fine, void* coarse, int dtype, int n, int h, int w, int c, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(fine && coarse, "aldi_sum2x2_accum: null pointer");
-  const int grid = grid_for((size_t)n * h * w * c, 256);
+  ALDI_CHECK_ARG(c % 8 == 0, "aldi_sum2x2_accum: channels must be a multiple of 8");
+  const int grid = grid_for((size_t)n * h * w * c / 4, 256);
   if (dtype == ALDI_DTYPE_BF16)
     sum2x2_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)fine, (__nv_bfloat16*)coarse, n, h, w, c);
   else
@@ -227,7 +297,7 @@ extern "C" int aldi_add_f32(void* dst, int dtype, const float* src, size_t n, vo
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(dst && src, "aldi_add_f32: null pointer");
   if (n == 0) return ALDI_OK;
-  const int grid = grid_for(n, 256);
+  const int grid = grid_for(n / 4 + 1, 256);
   if (dtype == ALDI_DTYPE_BF16)
     add_f32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((__nv_bfloat16*)dst, src, n);
   else

@@ -153,7 +153,10 @@ def test_rpn_proposals_exact(training):
                 got_s[max(first - 2, 0):first + 3].tolist(), want_s[max(first - 2, 0):first + 3].tolist(),
                 "n mismatches", neq.numel())
         assert c == len(ref[i]) and neq.numel() == 0, info
-        assert torch.allclose(out["boxes"][i, :c].cpu(), ref[i].proposal_boxes.tensor, rtol=1e-4, atol=1e-2)
+        gb, wb = out["boxes"][i, :c].cpu(), ref[i].proposal_boxes.tensor
+        bad = ((gb - wb).abs() > 1e-3 + 1e-5 * wb.abs()).any(1).nonzero().flatten()
+        assert bad.numel() == 0, ("boxes", i, bad.numel(), bad[:4].tolist(), gb[bad[:4]].tolist(), wb[bad[:4]].tolist(),
+                                  got_s[bad[:4]].tolist(), out["cats"][i, bad[:4]].tolist())
 
 
 def test_roi_inference_exact():
