@@ -382,9 +382,12 @@ class Detector:
                  cout_store=g.cin)
         return out
 
-    def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch):
+    def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch, on_ready=None):
         """Accumulate d(loss)/d(params) into the flat gradient buffer G.
-        d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64)."""
+        d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64).
+        on_ready(tag): called when a bucket of G ("heads", "fpn", "res5", "res4", "res3") has received its last
+        contribution of this backward (data_parallel.GradReducer starts that bucket's all-reduce)."""
+        on_ready = on_ready or (lambda tag: None)
         dt = W.dtype
         dtc = _l.BF16 if dt == torch.bfloat16 else _l.F32
         dev = d_rpn.device
@@ -427,6 +430,7 @@ class Detector:
                 tgt = dP[l] if l < 6 else dP[5][:, ::2, ::2, :]
                 self._dgrad(W, "rpn_conv", dt_, tgt, accumulate=True)
                 del dt_
+        on_ready("heads")
         # ---- FPN: p_l = output_l(prev_l); prev_l = lateral_l(res_l) + up2(prev_{l+1})
         dprev, dres = {}, {}
         for l in (2, 3, 4, 5):
@@ -445,6 +449,7 @@ class Detector:
                 dres[l] = torch.empty_like(r)
                 self._dgrad(W, "fpn_lateral%d" % l, dprev[l], dres[l], mask=r)
             dprev[l] = None
+        on_ready("fpn")
         # ---- ResNet res5 -> res3 (stem + res2 frozen: aldi configs keep D2's FREEZE_AT=2)
         for stage in (5, 4, 3):
             dout = dres[stage]
@@ -474,6 +479,7 @@ class Detector:
                     dout = dx
                 del dh1
             dres[stage] = None
+            on_ready("res%d" % stage)
 
     def _wgrad_strided_bias(self, W, G, name, x, dy):
         """wgrad + bias grad where dy is a strided level view of the concatenated RPN gradient map."""

@@ -17,15 +17,18 @@ class KernelProfiler:
     """Per-launch device timing with CUDA events on the launching stream (bench.py roofline numbers)."""
 
     def __init__(self):
-        self.records = []  # (name, flops, start_event, end_event)
+        self.records = []  # (name, flops, bytes, key, start_event, end_event)
 
-    def summary(self):
+    def summary(self, by_key=False):
+        """Aggregate per entry point (or per (entry point, shape key) with by_key=True)."""
         torch.cuda.synchronize()
         out = {}
-        for name, flops, e0, e1 in self.records:
-            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        for name, flops, nbytes, key, e0, e1 in self.records:
+            k = (name, key) if by_key else name
+            d = out.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
+            d["bytes"] += nbytes
             d["launches"] += 1
         return out
 
@@ -38,14 +41,14 @@ def set_profiler(p):
     _PROFILER = p
 
 
-def _launch(name, fn, flops=0.0):
+def _launch(name, fn, flops=0.0, nbytes=0.0, key=None):
     if _PROFILER is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = fn()
     e1.record()
-    _PROFILER.records.append((name, flops, e0, e1))
+    _PROFILER.records.append((name, flops, nbytes, key() if callable(key) else key, e0, e1))
     return rc
 
 
@@ -140,10 +143,20 @@ def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
     p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate))
     L = _l.load()
     flops = 2.0 * n * oh * ow * p.cout_store * taps_h * taps_w * (algo_cin or xc)
+    # algorithmic bytes: every operand element touched once (input pixels the taps reach ~ the view itself)
+    pix = n * oh * ow
+    nbytes = (n * xh * xw * xc + wp.numel()) * x.element_size() + pix * p.cout_store * out.element_size() * \
+        (2 if accumulate else 1) + (pix * p.cout_store * 2 // (4 if res_mode == 2 else 1) if residual is not None else 0) + \
+        (pix * p.cout_store * 2 if mask is not None else 0)
+    key = lambda: "%dx%d c%d->%d px%dx%dx%d%s%s%s%s" % (  # noqa: E731
+        taps_h, taps_w, xc, p.cout_store, n, oh, ow, " s2" if x_sw != xc else "", " +res%d" % res_mode if res_mode else "",
+        " mask" if mask is not None else "", " acc" if accumulate else "")
     if x.dtype == torch.bfloat16:
-        _l.check(_launch("aldi_conv_tc", lambda: L.aldi_conv_tc(ctypes.byref(p), _stream()), flops), "aldi_conv_tc")
+        _l.check(_launch("aldi_conv_tc", lambda: L.aldi_conv_tc(ctypes.byref(p), _stream()), flops, nbytes, key),
+                 "aldi_conv_tc")
     else:
-        _l.check(_launch("aldi_conv_f32", lambda: L.aldi_conv_f32(ctypes.byref(p), _stream()), flops), "aldi_conv_f32")
+        _l.check(_launch("aldi_conv_f32", lambda: L.aldi_conv_f32(ctypes.byref(p), _stream()), flops, nbytes, key),
+                 "aldi_conv_f32")
 
 
 def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, cout_store=None,
@@ -165,10 +178,15 @@ def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
     assert dw.numel() == p.cout_store * taps_h * taps_w * p.cin_store
     L = _l.load()
     flops = 2.0 * n * oh * ow * p.cout_store * taps_h * taps_w * p.cin_store
+    nbytes = (n * xh * xw * xc + n * oh * ow * dc) * x.element_size() + dw.numel() * 8
+    key = lambda: "%dx%d c%d->%d px%dx%dx%d%s" % (taps_h, taps_w, p.cin_store, p.cout_store, n, oh, ow,  # noqa: E731
+                                                 " s2" if x_sw != xc else "")
     if x.dtype == torch.bfloat16:
-        _l.check(_launch("aldi_wgrad_tc", lambda: L.aldi_wgrad_tc(ctypes.byref(p), _stream()), flops), "aldi_wgrad_tc")
+        _l.check(_launch("aldi_wgrad_tc", lambda: L.aldi_wgrad_tc(ctypes.byref(p), _stream()), flops, nbytes, key),
+                 "aldi_wgrad_tc")
     else:
-        _l.check(_launch("aldi_wgrad_f32", lambda: L.aldi_wgrad_f32(ctypes.byref(p), _stream()), flops), "aldi_wgrad_f32")
+        _l.check(_launch("aldi_wgrad_f32", lambda: L.aldi_wgrad_f32(ctypes.byref(p), _stream()), flops, nbytes, key),
+                 "aldi_wgrad_f32")
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from . import lib as _l
 from . import ops, sampling
+from .data_parallel import GradReducer
 from .detector import Detector, DetectorWeights, FlatLayout
 
 SRC_KEYS = ("loss_cls", "loss_box_reg", "loss_rpn_cls", "loss_rpn_loc")
@@ -137,6 +138,8 @@ class B200TrainStep:
         self.loss_acc = torch.zeros(16, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pg = process_group
+        self.reducer = GradReducer(self.layout, self.grad, process_group)
+        self._last_backward = False
         self.iter = 0
         self.h2d_bytes = 0
         self.last_pseudo = None
@@ -170,11 +173,14 @@ class B200TrainStep:
         self.pseudo_log = []
         out_keys = []
         pass_id = 0
+        n_backward = sum(-(-len(d) // mb) for d in (labeled_weak, labeled_strong) if d is not None) + \
+            (-(-len(unlabeled_weak) // mb) if do_distill else 0)
         for tag, d in (("source_weak", labeled_weak), ("source_strong", labeled_strong)):
             if d is None:
                 continue
             for i in range(0, len(d), mb):
                 self.seed_log[pass_id] = self.seed
+                self._last_backward = pass_id == n_backward - 1
                 self._source_microbatch(d[i:i + mb], gscale, pass_id)
                 pass_id += 1
             out_keys += [(k + "_" + tag, j) for j, k in enumerate(SRC_KEYS)]
@@ -183,6 +189,7 @@ class B200TrainStep:
             for i in range(0, len(unlabeled_weak), mb):
                 self.seed = random.randint(0, 2 ** 32 - 1)  # seeder.reset_seed(), aldi/distill.py:150
                 self.seed_log[100 + pass_id] = self.seed
+                self._last_backward = pass_id == n_backward - 1
                 self._distill_microbatch(unlabeled_weak[i:i + mb], unlabeled_strong[i:i + mb], gscale, 100 + pass_id)
                 pass_id += 1
             out_keys += [(k + "_distill", 4 + j) for j, k in enumerate(SRC_KEYS)]
@@ -213,7 +220,7 @@ class B200TrainStep:
                  fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)), 1.0, 1.0, gscale, dpred, self.dtc, 64,
                  self.loss_acc[0:2])
         det.backward(W, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"], dpred,
-                     fw["rois"], fw["roi_batch"])
+                     fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready())
 
     def _student_forward(self, b, gt, pass_id, want_rpn_labels):
         cfg, det, W = self.cfg, self.det, self.student
@@ -336,7 +343,7 @@ class B200TrainStep:
         self.debug = {"fw": fw, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": labels, "stats": stats,
                       "pseudo": pseudo} if self.debug is not None else None
         det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, lv, fw["head_saved"],
-                     dpred, fw["rois"], fw["roi_batch"])
+                     dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready())
 
     # ---- aldi/dropin.py:121 optimizer.step() (torch.optim.SGD via D2 build_optimizer) ---------------------
     def lr_at(self, it, warmup_iters=100, warmup_factor=0.01, steps=(), gamma=0.1):
@@ -347,12 +354,14 @@ class B200TrainStep:
             lr *= warmup_factor * (1 - a) + a
         return lr
 
+    def _bucket_ready(self):
+        """Gradient buckets become final only in the step's LAST backward; earlier micro-batches just accumulate."""
+        return self.reducer.ready if (self._last_backward and self.reducer.active) else None
+
     def allreduce_grads(self):
-        """One sum-all-reduce of the flat gradient buffer per step (DDP averages per micro-batch backward)."""
-        if self.pg is not None and dist.get_world_size(self.pg) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
-            return 1.0 / dist.get_world_size(self.pg)
-        return 1.0
+        """One sum-all-reduce of the flat gradient buffer per step, started bucket by bucket during the last
+        backward (data_parallel.GradReducer); DDP in the reference averages inside every micro-batch backward."""
+        return self.reducer.finish()
 
     def optimizer_step(self, lr=None):
         lr = self.lr_at(self.iter) if lr is None else lr

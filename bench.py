@@ -166,6 +166,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def write_layer_table(path, by_key, peaks, ms_step):
+    """Per (entry point, layer shape): launches, device ms, achieved TFLOP/s and GB/s, and the roofline time
+    max(flops / tensor peak, algorithmic bytes / HBM peak) each launch is bounded by."""
+    tf, bw = float(peaks.get("bf16_tflops_sustained", 1400.0)), float(peaks.get("hbm_gbs", 6650.0))
+    rows = []
+    for (name, key), d in by_key.items():
+        floor_ms = max(d["flops"] / (tf * 1e12), d["bytes"] / (bw * 1e9)) * 1e3
+        rows.append((d["ms"], name, key or "", d["launches"], d["flops"], d["bytes"], floor_ms))
+    rows.sort(reverse=True)
+    tot = sum(r[0] for r in rows)
+    with open(path, "w") as fh:
+        fh.write("# per-layer kernel table (CUDA events around each launch inside one step; step = %.2f ms)\n\n" % ms_step)
+        fh.write("peaks: %.0f TFLOP/s bf16 sustained, %.0f GB/s HBM (MEASURED_PEAKS.json); floor = max(flops/peak, "
+                 "bytes/peak); sum of timed launches = %.2f ms\n\n" % (tf, bw, tot))
+        fh.write("| entry point | shape | launches | ms | TFLOP/s | GB/s | floor ms | floor/actual |\n|---|---|---:|---:|---:|---:|---:|---:|\n")
+        for ms, name, key, n, fl, by, floor in rows:
+            fh.write("| %s | %s | %d | %.3f | %s | %s | %.3f | %s |\n" % (
+                name, key, n, ms, "%.0f" % (fl / ms / 1e9) if fl else "-", "%.0f" % (by / ms / 1e6) if by else "-", floor,
+                "%.2f" % (floor / ms) if floor else "-"))
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -204,14 +225,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = {}
+
     def timed(batches, k, read_losses):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lib.reset_launch_count()
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(k):
             one_step(batches, read_losses)
         e1.record()
+        host_issue["ms_per_step"] = (time.perf_counter() - t0) / k * 1e3
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.launch_count()
@@ -225,6 +250,7 @@ def run_ours(args):
         one_step(dev, False)
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches = timed(dev, args.steps, False)
+    host_ms = host_issue["ms_per_step"]
     clocks = sampler.stop() if sampler else None
     ms_step = ms / args.steps
     value = imgs_per_step / (ms_step / 1e3)
@@ -243,6 +269,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     ops.set_profiler(None)
     summ = prof.summary()
+    if args.profile_out and rank == 0:
+        write_layer_table(args.profile_out, prof.summary(by_key=True), peaks, ms_step)
     roofline = None
     if "aldi_conv_tc" in summ:
         s = summ["aldi_conv_tc"]
@@ -275,7 +303,7 @@ def run_ours(args):
                            "global_batch": imgs_per_step,
                            "l2": "inputs larger than L2: 75 MB of uint8 views + >4 GB of activations per micro-batch vs 126 MB L2",
                            "algorithmic_tflop_per_step_per_gpu": 24.0},
-                "clocks": clocks, "gpu_launches": int(launches // args.steps),
+                "clocks": clocks, "gpu_launches": int(launches // args.steps), "host_issue_ms_per_step": host_ms,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
@@ -291,6 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-layer-shape kernel table (markdown) here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
