@@ -8,8 +8,16 @@
 // is exactly the convolution's zero padding, so no im2col buffer and no predication exist anywhere.
 // The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle = the canonical
 // K-major UMMA operand layout.  Warp roles (persistent CTA, one per SM):
-//   warp 0: TMA producer   warp 1: TMEM alloc + tcgen05.mma issuer   warps 2-5: epilogue
+//   warp 0: TMA producer (A/B stages)      warp 1: TMEM alloc + tcgen05.mma issuer
+//   warps 2-5: epilogue                    warp 6: TMA producer of the epilogue operands
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// Epilogue (bf16 outputs): most ResNet layers here are HBM-bound (1x1 convs with a residual), so the
+// epilogue is built like a copy kernel: residual / ReLU-mask tiles are TMA-loaded (warp 6, double buffered,
+// 64 channels = 128-byte rows at a time) while the main loop runs, the finished 128 x 64 bf16 chunk is staged
+// in 128B-swizzled shared memory and leaves with ONE TMA store, which also clips partial tiles.  `accumulate`
+// is the same path with the output tile as the residual.  fp32 outputs (RPN head / box predictor rows,
+// 15 / 41 channels) keep direct per-thread stores.
 //
 // Replaces the cuDNN/cuBLAS calls detectron2 makes for ResNet/FPN/RPN/box-head layers
 // (reached from aldi/trainer.py:87, aldi/distill.py:157,162, aldi/pseudolabeler.py:21).
@@ -25,7 +33,11 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                      // bf16 elements = 128 B = swizzle span
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 224;
+constexpr int kEpiChunk = 64;                    // channels per epilogue chunk (128-byte rows)
+constexpr int kEpiBytes = kBlockM * kEpiChunk * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 226 * 1024;     // dynamic budget (static barriers etc. live in the remaining 1 KB)
 
 struct ConvArgs {
   int n, ho, wo;
@@ -45,18 +57,22 @@ struct ConvArgs {
   int cout_store;
   long long out_sw, out_sh, out_sn;
   int relu, accumulate;
+  int stages;        // A/B pipeline depth (runtime: the epilogue buffers share the 227 KB)
+  int tma_epi;       // bf16 output through shared memory + TMA store
+  int epi_res, epi_mask;  // residual / mask tiles arrive by TMA (tma_epi only)
 };
 
 template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
 };
+
+__device__ __forceinline__ uint32_t swz128(int row, int chunk16) {  // byte offset inside a 128B-swizzled tile
+  return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -77,30 +93,44 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmM, const ConvArgs a) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // [stages x (A | B)] [out x2] [res x2] [mask x2]   (all 16 KB pieces, 1024-byte aligned)
+  uint8_t* s_out = smem + a.stages * C::kStageBytes;
+  uint8_t* s_res = s_out + 2 * kEpiBytes;
+  uint8_t* s_mask = s_res + (a.epi_res ? 2 * kEpiBytes : 0);
 
-  __shared__ __align__(8) uint64_t full_bar[C::kStages];
-  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t epi_full_bar[2];
+  __shared__ __align__(8) uint64_t epi_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool epi_loads = a.epi_res || a.epi_mask;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int i = 0; i < C::kStages; ++i) {
+    if (a.tma_epi) prefetch_tmap(&tmO);
+    if (a.epi_res) prefetch_tmap(&tmR);
+    if (a.epi_mask) prefetch_tmap(&tmM);
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&epi_full_bar[i], 1);
+      mbar_init(&epi_empty_bar[i], 4);
     }
     fence_barrier_init();
   }
@@ -132,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, w0 + s - a.pad_w, h0 + r - a.pad_h, img);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -161,16 +191,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== TMA producer of the epilogue operands (residual / mask tiles) =====================
+    if (lane == 0 && epi_loads) {
+      int buf = 0;
+      uint32_t phase = 0;
+      const uint32_t res_bytes = a.res_mode == 2 ? kEpiBytes / 4 : kEpiBytes;
+      const uint32_t bytes = (a.epi_res ? res_bytes : 0u) + (a.epi_mask ? (uint32_t)kEpiBytes : 0u);
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % a.num_n_tiles;
+        int m_tile = tile / a.num_n_tiles;
+        const int twi = m_tile % a.tiles_w;
+        m_tile /= a.tiles_w;
+        const int thi = m_tile % a.tiles_h;
+        const int img = m_tile / a.tiles_h;
+        const int h0 = thi * a.th, w0 = twi * a.tw;
+        for (int c0 = 0; c0 < BLOCK_N; c0 += kEpiChunk) {
+          const int cbase = n_tile * BLOCK_N + c0;
+          if (cbase >= a.cout_store) break;
+          mbar_wait(&epi_empty_bar[buf], phase ^ 1);
+          mbar_expect_tx(&epi_full_bar[buf], bytes);
+          if (a.epi_res) {
+            if (a.res_mode == 2)
+              tma_load_4d(s_res + buf * kEpiBytes, &tmR, &epi_full_bar[buf], cbase, w0 >> 1, h0 >> 1, img);
+            else
+              tma_load_4d(s_res + buf * kEpiBytes, &tmR, &epi_full_bar[buf], cbase, w0, h0, img);
+          }
+          if (a.epi_mask) tma_load_4d(s_mask + buf * kEpiBytes, &tmM, &epi_full_bar[buf], cbase, w0, h0, img);
+          if (++buf == 2) { buf = 0; phase ^= 1; }
+        }
       }
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
+    const int hl = row >> a.tw_shift, wl = row & (a.tw - 1);
+    const bool leader = (threadIdx.x == 64);
+    // residual row of this thread inside the TMA-loaded tile (res_mode 2: the (TH/2 x TW/2) coarse tile)
+    const int rrow = (a.res_mode == 2) ? ((hl >> 1) * (a.tw >> 1) + (wl >> 1)) : row;
     int it = 0;
+    int ebuf = 0, obuf = 0;
+    uint32_t ephase = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -180,100 +247,186 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       m_tile /= a.tiles_w;
       const int thi = m_tile % a.tiles_h;
       const int img = m_tile / a.tiles_h;
-      const int h = thi * a.th + (row >> a.tw_shift);
-      const int w = twi * a.tw + (row & (a.tw - 1));
-      const bool valid = (h < a.ho) && (w < a.wo);
+      const int h0 = thi * a.th, w0 = twi * a.tw;
+      const int h = h0 + hl, w = w0 + wl;
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
 
-      const long long out_off = (long long)img * a.out_sn + (long long)h * a.out_sh + (long long)w * a.out_sw;
-      long long res_off = 0, mask_off = 0;
-      if (a.res_mode == 1)
-        res_off = (long long)img * a.res_sn + (long long)h * a.res_sh + (long long)w * a.res_sw;
-      else if (a.res_mode == 2)
-        res_off = (long long)img * a.res_sn + (long long)(h >> 1) * a.res_sh + (long long)(w >> 1) * a.res_sw;
-      if (a.mask) mask_off = (long long)img * a.mask_sn + (long long)h * a.mask_sh + (long long)w * a.mask_sw;
-
+      if (a.tma_epi) {
+        // ---------- bf16 output: 64-channel chunks through swizzled shared memory, TMA in / TMA out ----------
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), raw);
-        tmem_ld_wait();
-        const int cbase = n_tile * BLOCK_N + c0;
-        if (valid && cbase < a.cout_store) {
-          float v[32];
+        for (int c0 = 0; c0 < BLOCK_N; c0 += kEpiChunk) {
+          const int cbase = n_tile * BLOCK_N + c0;
+          if (cbase >= a.cout_store) break;
+          uint32_t raw0[32], raw1[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+          tmem_ld_32x32(taddr, raw0);
+          tmem_ld_32x32(taddr + 32, raw1);
+          tmem_ld_wait();
+          float v[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw0[j]); v[32 + j] = __uint_as_float(raw1[j]); }
           if (a.scale) {
+            const float4* sp = reinterpret_cast<const float4*>(a.scale + cbase);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= __ldg(a.scale + cbase + j);
+            for (int g = 0; g < 16; ++g) {
+              const float4 t = __ldg(sp + g);
+              v[4 * g] *= t.x; v[4 * g + 1] *= t.y; v[4 * g + 2] *= t.z; v[4 * g + 3] *= t.w;
+            }
           }
           if (a.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + cbase);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cbase + j);
+            for (int g = 0; g < 16; ++g) {
+              const float4 t = __ldg(bp + g);
+              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+            }
           }
-          if (a.res_mode) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + res_off + cbase);
+          if (epi_loads) mbar_wait(&epi_full_bar[ebuf], ephase);
+          if (a.epi_res && !a.accumulate) {
+            const uint8_t* rb = s_res + ebuf * kEpiBytes;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 8; ++g) {
               float f[8];
-              unpack_bf16x8(__ldg(rp + g), f);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(rrow, g)), f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
             }
           }
           if (a.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (a.mask) {
-            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + mask_off + cbase);
+          if (a.epi_mask) {
+            const uint8_t* mb = s_mask + ebuf * kEpiBytes;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 8; ++g) {
               float f[8];
-              unpack_bf16x8(__ldg(mp + g), f);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(mb + swz128(row, g)), f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] = (f[j] > 0.f) ? v[g * 8 + j] : 0.f;
             }
           }
-          if (a.out_f32) {
-            float* op = reinterpret_cast<float*>(a.out) + out_off + cbase;
-            if (cbase + 32 <= a.cout_store && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+          if (a.epi_res && a.accumulate) {  // out += v: the old output tile arrived as the "residual"
+            const uint8_t* rb = s_res + ebuf * kEpiBytes;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                if (a.accumulate) {
-                  float4 old = reinterpret_cast<float4*>(op)[g];
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                reinterpret_cast<float4*>(op)[g] = o;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < a.cout_store) op[j] = a.accumulate ? op[j] + v[j] : v[j];
+            for (int g = 0; g < 8; ++g) {
+              float f[8];
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(row, g)), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
             }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + out_off + cbase;
-            if (cbase + 32 <= a.cout_store) {
-              uint4* o4 = reinterpret_cast<uint4*>(op);
+          }
+          if (epi_loads) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&epi_empty_bar[ebuf]);
+            if (++ebuf == 2) { ebuf = 0; ephase ^= 1; }
+          }
+          // the store that last read s_out[obuf] (two chunks ago) must have finished reading it
+          if (leader) bulk_wait_group_read<1>();
+          named_bar_sync(1, 128);
+          uint8_t* ob = s_out + obuf * kEpiBytes;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(ob + swz128(row, g)) = pack_bf16x8(v + g * 8);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_4d(&tmO, ob, cbase, w0, h0, img);
+            bulk_commit_group();
+          }
+          obuf ^= 1;
+        }
+      } else {
+        // ---------- fp32 (or unaligned) output: direct per-thread row-segment stores ----------
+        const bool valid = (h < a.ho) && (w < a.wo);
+        const long long out_off = (long long)img * a.out_sn + (long long)h * a.out_sh + (long long)w * a.out_sw;
+        long long res_off = 0, mask_off = 0;
+        if (a.res_mode == 1)
+          res_off = (long long)img * a.res_sn + (long long)h * a.res_sh + (long long)w * a.res_sw;
+        else if (a.res_mode == 2)
+          res_off = (long long)img * a.res_sn + (long long)(h >> 1) * a.res_sh + (long long)(w >> 1) * a.res_sw;
+        if (a.mask) mask_off = (long long)img * a.mask_sn + (long long)h * a.mask_sh + (long long)w * a.mask_sw;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), raw);
+          tmem_ld_wait();
+          const int cbase = n_tile * BLOCK_N + c0;
+          if (valid && cbase < a.cout_store) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            if (a.scale) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= __ldg(a.scale + cbase + j);
+            }
+            if (a.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cbase + j);
+            }
+            if (a.res_mode) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + res_off + cbase);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                if (a.accumulate) {
-                  float f[8];
-                  unpack_bf16x8(o4[g], f);
+                float f[8];
+                unpack_bf16x8(__ldg(rp + g), f);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (a.mask) {
+              const uint4* mp = reinterpret_cast<const uint4*>(a.mask + mask_off + cbase);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+                unpack_bf16x8(__ldg(mp + g), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] = (f[j] > 0.f) ? v[g * 8 + j] : 0.f;
+              }
+            }
+            if (a.out_f32) {
+              float* op = reinterpret_cast<float*>(a.out) + out_off + cbase;
+              if (cbase + 32 <= a.cout_store && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                  if (a.accumulate) {
+                    float4 old = reinterpret_cast<float4*>(op)[g];
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  reinterpret_cast<float4*>(op)[g] = o;
                 }
-                o4[g] = pack_bf16x8(v + g * 8);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (cbase + j < a.cout_store) op[j] = a.accumulate ? op[j] + v[j] : v[j];
               }
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < a.cout_store) {
-                  float o = v[j];
-                  if (a.accumulate) o += __bfloat162float(op[j]);
-                  op[j] = __float2bfloat16_rn(o);
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + out_off + cbase;
+              if (cbase + 32 <= a.cout_store) {
+                uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  if (a.accumulate) {
+                    float f[8];
+                    unpack_bf16x8(o4[g], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+                  }
+                  o4[g] = pack_bf16x8(v + g * 8);
                 }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (cbase + j < a.cout_store) {
+                    float o = v[j];
+                    if (a.accumulate) o += __bfloat162float(op[j]);
+                    op[j] = __float2bfloat16_rn(o);
+                  }
+              }
             }
           }
         }
@@ -282,6 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (a.tma_epi && leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires
   }
 
   tc_fence_before();
@@ -293,12 +447,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BLOCK_N>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+int launch_conv(const CUtensorMap* tm, const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
+                                         kSmemLimit);
     if (e != cudaSuccess) {
       aldi_set_error("aldi_conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ALDI_ERR_CUDA;
@@ -306,16 +459,16 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& 
     attr_set = true;
   }
   int grid = a.num_tiles < aldi_num_sms() ? a.num_tiles : aldi_num_sms();
-  conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_conv_tc");
   return ALDI_OK;
 }
 
 // spatial patch (TH x TW = 128) that wastes the fewest pixels for an (ho, wo) output
-void pick_patch(int ho, int wo, int* th, int* tw) {
+void pick_patch(int ho, int wo, int max_tw, int* th, int* tw) {
   long best = -1;
-  for (int t = 128; t >= 8; t >>= 1) {
+  for (int t = max_tw; t >= 8; t >>= 1) {
     int hh = 128 / t;
     long cover = (long)((wo + t - 1) / t) * t * (long)((ho + hh - 1) / hh) * hh;
     if (best < 0 || cover < best) {
@@ -324,6 +477,15 @@ void pick_patch(int ho, int wo, int* th, int* tw) {
       *th = hh;
     }
   }
+}
+
+// 4-D channels-last tensor map {c, w, h, n} over a strided view, box {64, bw, bh, 1}
+int make_cl_tmap(CUtensorMap* tm, const void* base, int c, int w, int h, int n, long long sw, long long sh,
+                 long long sn, int bw, int bh) {
+  uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+  uint64_t strides[3] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)sn * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  return aldi_make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
 
 }  // namespace
@@ -357,9 +519,24 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
                    "aldi_conv_tc: mask must be 16-byte aligned with strides multiple of 8");
   }
 
+  // bf16 outputs whose channel extent is a whole number of 64-channel chunks leave through TMA; `accumulate`
+  // becomes "residual = the output tile itself" (never combined with another residual by the callers)
+  const bool tma_epi = p->out_dtype == ALDI_DTYPE_BF16 && p->cout_store % 64 == 0 && !(p->accumulate && p->res_mode);
+  const bool epi_res = tma_epi && (p->res_mode || p->accumulate);
+  const bool epi_mask = tma_epi && p->mask;
+  const int res_mode = (tma_epi && p->accumulate) ? 1 : p->res_mode;
+
   int block_n = (p->cout_p % 256 == 0) ? 256 : (p->cout_p % 128 == 0) ? 128 : 64;
+  const int epi_bytes = tma_epi ? (2 + (epi_res ? 2 : 0) + (epi_mask ? 2 : 0)) * kEpiBytes : 0;
+  // keep at least 3 pipeline stages: narrow the N tile when the epilogue buffers crowd them out
+  while (block_n > 64 && (kSmemLimit - 1024 - epi_bytes) / (kABytes + block_n * kBlockK * 2) < 3) block_n >>= 1;
+  const int stage_bytes = kABytes + block_n * kBlockK * 2;
+  int stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
+
   int th, tw;
-  pick_patch(p->ho, p->wo, &th, &tw);
+  pick_patch(p->ho, p->wo, (tma_epi && res_mode == 2) ? 64 : 128, &th, &tw);
 
   ConvArgs a;
   a.n = p->n; a.ho = p->ho; a.wo = p->wo;
@@ -376,7 +553,7 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.scale = p->scale; a.bias = p->bias;
   a.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
-  a.res_mode = p->res_mode;
+  a.res_mode = res_mode;
   a.res_sw = p->res_sw; a.res_sh = p->res_sh; a.res_sn = p->res_sn;
   a.mask = reinterpret_cast<const __nv_bfloat16*>(p->mask);
   a.mask_sw = p->mask_sw; a.mask_sh = p->mask_sh; a.mask_sn = p->mask_sn;
@@ -385,26 +562,43 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   a.cout_store = p->cout_store;
   a.out_sw = p->out_sw; a.out_sh = p->out_sh; a.out_sn = p->out_sn;
   a.relu = p->relu; a.accumulate = p->accumulate;
+  a.stages = stages;
+  a.tma_epi = tma_epi; a.epi_res = epi_res; a.epi_mask = epi_mask;
 
-  CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[4] = {(uint64_t)p->x_c, (uint64_t)p->x_w, (uint64_t)p->x_h, (uint64_t)p->x_n};
-    uint64_t strides[3] = {(uint64_t)p->x_sw * 2, (uint64_t)p->x_sh * 2, (uint64_t)p->x_sn * 2};
-    uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
-    int rc = aldi_make_tmap_bf16(&tmA, p->x, 4, dims, strides, box);
-    if (rc) return rc;
-  }
+  CUtensorMap tm[5];
+  int rc = make_cl_tmap(&tm[0], p->x, p->x_c, p->x_w, p->x_h, p->x_n, p->x_sw, p->x_sh, p->x_sn, tw, th);
+  if (rc) return rc;
   {
     uint64_t ktot = (uint64_t)p->taps_h * p->taps_w * p->x_c;
     uint64_t dims[2] = {ktot, (uint64_t)p->cout_p};
     uint64_t strides[1] = {ktot * 2};
     uint32_t box[2] = {64, (uint32_t)block_n};
-    int rc = aldi_make_tmap_bf16(&tmB, p->w, 2, dims, strides, box);
+    rc = aldi_make_tmap_bf16(&tm[1], p->w, 2, dims, strides, box);
     if (rc) return rc;
   }
+  tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];  // placeholders when unused
+  if (tma_epi) {
+    rc = make_cl_tmap(&tm[2], p->out, p->cout_store, p->wo, p->ho, p->n, p->out_sw, p->out_sh, p->out_sn, tw, th);
+    if (rc) return rc;
+    if (epi_res) {
+      if (p->accumulate)
+        rc = make_cl_tmap(&tm[3], p->out, p->cout_store, p->wo, p->ho, p->n, p->out_sw, p->out_sh, p->out_sn, tw, th);
+      else if (res_mode == 2)
+        rc = make_cl_tmap(&tm[3], p->residual, p->cout_store, (p->wo + 1) / 2, (p->ho + 1) / 2, p->n, p->res_sw,
+                          p->res_sh, p->res_sn, tw / 2, th / 2);
+      else
+        rc = make_cl_tmap(&tm[3], p->residual, p->cout_store, p->wo, p->ho, p->n, p->res_sw, p->res_sh, p->res_sn, tw,
+                          th);
+      if (rc) return rc;
+    }
+    if (epi_mask) {
+      rc = make_cl_tmap(&tm[4], p->mask, p->cout_store, p->wo, p->ho, p->n, p->mask_sw, p->mask_sh, p->mask_sn, tw, th);
+      if (rc) return rc;
+    }
+  }
   switch (block_n) {
-    case 256: return launch_conv<256>(tmA, tmB, a, stream);
-    case 128: return launch_conv<128>(tmA, tmB, a, stream);
-    default: return launch_conv<64>(tmA, tmB, a, stream);
+    case 256: return launch_conv<256>(tm, a, smem_bytes, stream);
+    case 128: return launch_conv<128>(tm, a, smem_bytes, stream);
+    default: return launch_conv<64>(tm, a, smem_bytes, stream);
   }
 }

@@ -131,6 +131,35 @@ def case_fwd_epilogue():
     return ok
 
 
+def case_fwd_epilogue2():
+    """TMA epilogue stress: many tiles per CTA, several N tiles, every operand combination the detector uses."""
+    import torch
+    from aldi_b200 import ops
+    ok = run_fwd("fwd 1x1 64->256 +res1+relu, 4x96x160 (480 tiles)", 4, 96, 160, 64, 256, 1, scale=True, res=1, relu=True)
+    ok &= run_fwd("fwd 1x1 128->512 +res1+relu, 2 N tiles", 2, 40, 72, 128, 512, 1, scale=True, res=1, relu=True)
+    ok &= run_fwd("fwd 1x1 256->512 mask+res1 (conv1 dgrad join)", 2, 36, 52, 256, 512, 1, mask=True, res=1)
+    ok &= run_fwd("fwd 3x3 128->128 mask", 2, 36, 52, 128, 128, 3, mask=True)
+    ok &= run_fwd("fwd 1x1 512->256 +res2, ragged 50x70", 2, 50, 70, 512, 256, 1, scale=True, res=2)
+    ok &= run_fwd("fwd 3x3 256->256 acc", 2, 30, 44, 256, 256, 3, acc=True)
+    ok &= run_fwd("fwd 1x1 64->64 plain 3x7x9 (tiny ragged)", 3, 7, 9, 64, 64, 1)
+    # accumulate into the even positions of a larger map (stride-2 dgrad scatter) with a mask view
+    n, h, w, cin, cout = 2, 20, 28, 128, 256
+    x, wt = make_case(n, h, w, cin, cout, 1)
+    want = ref_conv(x, wt, 0)
+    g = torch.Generator().manual_seed(11)
+    big = _bf(torch.randn(n, 2 * h, 2 * w, cout, generator=g))
+    m = _bf(torch.randn(n, 2 * h, 2 * w, cout, generator=g))
+    wp = torch.zeros(cout, cin, device="cuda", dtype=torch.bfloat16)
+    ops.pack_weight(wt.float().cuda().contiguous(), wp, cout=cout, taps=1, cin=cin, cout_p=cout, cin_p=cin)
+    out = big.cuda().clone()
+    ops.conv(x.cuda(), wp, out[:, ::2, ::2, :], mask=m.cuda()[:, ::2, ::2, :], accumulate=True)
+    torch.cuda.synchronize()
+    ref = big.float().clone()
+    ref[:, ::2, ::2, :] += want * (m.float()[:, ::2, ::2, :] > 0)
+    ok &= report("fwd 1x1 mask+acc into strided (::2, ::2) output view", out, ref)
+    return ok
+
+
 def case_fwd_f32():
     ok = run_fwd("f32 fwd 3x3 64->128 1x20x24", 1, 20, 24, 64, 128, 3, dtype="f32")
     ok &= run_fwd("f32 fwd 3x3 epilogue", 1, 16, 32, 48, 40, 3, dtype="f32", scale=True, res=1, relu=True, mask=True)
@@ -318,7 +347,8 @@ def case_perf():
 
 CASES = [
     "optim", "fwd_f32", "bwd_f32",
-    "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "stride2_view", "fc",
+    "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "fwd_epilogue2",
+    "stride2_view", "fc",
     "bwd_1x1", "bwd_1x1_big", "bwd_3x3", "bwd_3x3_big", "perf",
 ]
 
