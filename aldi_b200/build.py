@@ -20,7 +20,7 @@ FLAGS = [
 
 
 # selection kernels must reproduce the reference's float expressions bit-for-bit: no FMA contraction
-EXACT_SOURCES = ("select.cu",)
+EXACT_SOURCES = ("select.cu", "select_mb.cu")
 
 
 def _sources():

@@ -91,6 +91,50 @@ stem_im2col_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes
   }
 }
 
+// ---- stem 7x7/2 conv without im2col: fused normalise + 2x2 space-to-depth of the uint8 image ---------------
+// out: bf16 (N, Ho, Wo + 4, 16): pixel (i, jp) holds the 2x2 input block at rows 2i..2i+1, columns 2(jp-2)..2(jp-2)+1
+// as channel (dy*2+dx)*4 + c (c == 3 and everything outside the valid image are zero; two zero columns on the left,
+// two on the right).  With r+1 = 2a+dy, s+1 = 2b+dx the 7x7 stride-2 pad-3 conv becomes a 4x4 stride-1 conv over
+// this map, and the four column taps b of one output pixel are 64 CONTIGUOUS values starting at column jp = ox: the
+// conv kernel reads them as one 128-byte TMA row of an overlapping-row view (row stride 16 elements), row taps a by
+// TMA coordinate, zero rows above/below by TMA out-of-bounds fill.
+__global__ void __launch_bounds__(256)
+stem_s2d_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes, __nv_bfloat16* __restrict__ out, int n,
+                int hin, int win, int ho, int wp, Norm3 nm) {
+  const size_t total = (size_t)n * ho * wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int jp = (int)(i % wp);
+    size_t r = i / wp;
+    const int y = (int)(r % ho);
+    const int b = (int)(r / ho);
+    const int vh = sizes[2 * b], vw = sizes[2 * b + 1];
+    const int x0 = 2 * (jp - 2), y0 = 2 * y;
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = 0.f;
+    if (x0 >= 0 && x0 < win) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int iy = y0 + dy;
+        if (iy >= vh) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint8_t* p = in + (((size_t)b * 3 + c) * hin + iy) * win + x0;
+          const uchar2 px = (x0 + 1 < win) ? *reinterpret_cast<const uchar2*>(p) : make_uchar2(*p, 0);
+          if (x0 < vw) f[(dy * 2 + 0) * 4 + c] = __fdiv_rn(__fsub_rn((float)px.x, nm.mean[c]), nm.stdv[c]);
+          if (x0 + 1 < vw) f[(dy * 2 + 1) * 4 + c] = __fdiv_rn(__fsub_rn((float)px.y, nm.mean[c]), nm.stdv[c]);
+        }
+      }
+    }
+    uint4 q[2];
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    reinterpret_cast<uint4*>(out)[i * 2] = q[0];
+    reinterpret_cast<uint4*>(out)[i * 2 + 1] = q[1];
+  }
+}
+
 // ---- max_pool2d(kernel 3, stride 2, padding 1) on channels-last, 16 bytes of channels per thread ------
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
@@ -261,6 +305,21 @@ extern "C" int aldi_stem_im2col(const uint8_t* images, const int* sizes, void* o
   stem_im2col_kernel<<<grid, 256, 0, stream>>>(images, sizes, (__nv_bfloat16*)out_bf16, n, hin, win, ho, wo, nm);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_stem_im2col");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_stem_s2d(const uint8_t* images, const int* sizes, void* out_bf16, int n, int hin, int win,
+                             const float* h_mean, const float* h_std, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(images && sizes && out_bf16 && h_mean && h_std, "aldi_stem_s2d: null pointer");
+  ALDI_CHECK_ARG(n > 0 && hin % 2 == 0 && win % 2 == 0, "aldi_stem_s2d: canvas must have even height and width");
+  Norm3 nm;
+  for (int i = 0; i < 3; ++i) { nm.mean[i] = h_mean[i]; nm.stdv[i] = h_std[i]; }
+  const int ho = hin / 2, wp = win / 2 + 4;
+  stem_s2d_kernel<<<grid_for((size_t)n * ho * wp, 256), 256, 0, stream>>>(images, sizes, (__nv_bfloat16*)out_bf16, n, hin,
+                                                                         win, ho, wp, nm);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_stem_s2d");
   return ALDI_OK;
 }
 

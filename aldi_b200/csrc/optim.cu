@@ -102,6 +102,78 @@ pack_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ scale, 
   }
 }
 
+// ---- batched operand refresh: every pack / FrozenBN fold / bias copy of a model in ONE launch ---------------
+// A block handles kRefreshChunk consecutive output elements of one descriptor; block_start[] (prefix sums of the
+// per-descriptor block counts) maps blockIdx -> descriptor by binary search.
+constexpr int kRefreshChunk = 2048;
+
+__device__ __forceinline__ float bn_scale(const aldi_refresh_desc& d, int co) {
+  return __fmul_rn(__ldg(d.bn_w + co), __frsqrt_rn(__fadd_rn(__ldg(d.bn_var + co), d.eps)));
+}
+
+template <typename T>
+__device__ void refresh_pack(const aldi_refresh_desc& d, size_t begin, size_t end) {
+  T* out = reinterpret_cast<T*>(d.out);
+  for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    float v = 0.f;
+    if (d.kind == 0) {  // out[co][t][ci]
+      const int ci = (int)(i % d.cin_p);
+      size_t r = i / d.cin_p;
+      const int t = (int)(r % d.taps);
+      const int co = (int)(r / d.taps);
+      if (co < d.cout && ci < d.cin) v = __ldg(d.w + ((size_t)co * d.taps + t) * d.cin + ci);
+    } else {            // out[ci][taps-1-t][co] = w[co][t][ci] * scale[co]
+      const int co = (int)(i % d.cout_p);
+      size_t r = i / d.cout_p;
+      const int tf = (int)(r % d.taps);
+      const int ci = (int)(r / d.taps);
+      if (co < d.cout && ci < d.cin) {
+        v = __ldg(d.w + ((size_t)co * d.taps + (d.taps - 1 - tf)) * d.cin + ci);
+        if (d.bn_w) v *= bn_scale(d, co);
+      }
+    }
+    out[i] = from_f32<T>(v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+refresh_kernel(const aldi_refresh_desc* __restrict__ descs, const int* __restrict__ block_start, int n_desc) {
+  // binary search: last descriptor whose first block <= blockIdx.x
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (block_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const aldi_refresh_desc d = descs[lo];
+  const size_t begin = (size_t)(blockIdx.x - block_start[lo]) * kRefreshChunk;
+  if (d.kind <= 1) {
+    const size_t total = (d.kind == 0 ? (size_t)d.cout_p * d.taps * d.cin_p : (size_t)d.cin_p * d.taps * d.cout_p);
+    const size_t end = begin + kRefreshChunk < total ? begin + kRefreshChunk : total;
+    if (d.out_dtype == ALDI_DTYPE_BF16) refresh_pack<__nv_bfloat16>(d, begin, end);
+    else refresh_pack<float>(d, begin, end);
+  } else if (d.kind == 4) {  // stem 7x7x3 -> 4x4 taps over the 2x2 space-to-depth map: out[co][a][b][dy][dx][c4], bf16
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+    const size_t total = (size_t)d.cout_p * 256;
+    for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < total; i += blockDim.x) {
+      const int co = (int)(i >> 8), rem = (int)(i & 255);
+      const int a = rem >> 6, b = (rem >> 4) & 3, dy = (rem >> 3) & 1, dx = (rem >> 2) & 1, c = rem & 3;
+      const int r = 2 * a + dy - 1, s = 2 * b + dx - 1;
+      float v = 0.f;
+      if (co < d.cout && r >= 0 && s >= 0 && c < 3) v = __ldg(d.w + (((size_t)co * 7 + r) * 7 + s) * 3 + c);
+      out[i] = __float2bfloat16_rn(v);
+    }
+  } else if (d.kind == 2) {  // FrozenBN fold: scale -> out, shift -> out2
+    for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < (size_t)d.cout; i += blockDim.x) {
+      const float sc = bn_scale(d, (int)i);
+      reinterpret_cast<float*>(d.out)[i] = sc;
+      d.out2[i] = __fsub_rn(__ldg(d.bn_b + i), __fmul_rn(__ldg(d.bn_mean + i), sc));
+    }
+  } else {                   // plain bias -> shift
+    for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < (size_t)d.cout; i += blockDim.x)
+      d.out2[i] = __ldg(d.w + i);
+  }
+}
+
 int grid_for(size_t work_items, int threads) {
   size_t blocks = (work_items + threads - 1) / threads;
   size_t cap = (size_t)aldi_num_sms() * 8;
@@ -139,6 +211,25 @@ extern "C" int aldi_sgd_momentum_step(float* params, float* momentum_buf, const 
                                                               (float)(1.0 - ema_alpha));
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_sgd_momentum_step");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_refresh_blocks(const aldi_refresh_desc* d) {
+  size_t total;
+  if (d->kind == 0) total = (size_t)d->cout_p * d->taps * d->cin_p;
+  else if (d->kind == 1) total = (size_t)d->cin_p * d->taps * d->cout_p;
+  else if (d->kind == 4) total = (size_t)d->cout_p * 256;
+  else total = (size_t)d->cout;
+  return (int)((total + kRefreshChunk - 1) / kRefreshChunk);
+}
+
+extern "C" int aldi_refresh_operands(const aldi_refresh_desc* d_descs, const int* d_block_start, int n_desc,
+                                     int total_blocks, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(d_descs && d_block_start && n_desc > 0 && total_blocks > 0, "aldi_refresh_operands: bad args");
+  refresh_kernel<<<total_blocks, 256, 0, stream>>>(d_descs, d_block_start, n_desc);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_refresh_operands");
   return ALDI_OK;
 }
 

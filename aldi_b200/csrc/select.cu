@@ -8,261 +8,11 @@
 // Replaces: detectron2 find_top_rpn_proposals / batched_nms / Matcher / subsample_labels /
 // fast_rcnn_inference (reached from aldi/pseudolabeler.py:21, aldi/distill.py:157,162,200-202,
 // aldi/trainer.py:87).
-#include "common.cuh"
-#include "../../include/aldi_b200.h"
-#include <float.h>
+#include "select_common.cuh"
+
+using namespace aldi_sel;
 
 namespace {
-
-// ------------------------------------------------------------------------------------------------
-// order-preserving float <-> uint32
-__device__ __forceinline__ uint32_t fkey(float f) {
-  uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// murmur3 finaliser based counter hash: the sampling "random permutation" is the order of these keys.
-// Must stay in sync with aldi_b200/sampling.py (host/oracle emulation).
-__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h;
-}
-__host__ __device__ __forceinline__ uint32_t sample_hash(uint32_t seed, uint32_t salt, uint32_t index) {
-  uint32_t s = fmix32(seed ^ (salt * 0x27D4EB2Fu + 0x165667B1u));
-  return fmix32((index * 0x9E3779B1u) ^ s);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Block-wide selection of the k LARGEST 32-bit keys among n candidates (MSB-first radix select).
-// kf(i, key) -> bool valid.  Result: every element with key > T is selected, plus `take_eq` of the
-// elements with key == T (lowest index first); count_eq = number of elements with key == T.
-struct SelectResult {
-  uint32_t T;
-  int take_eq, count_eq;
-};
-
-template <typename KeyFn>
-__device__ SelectResult block_select(int n, int k, KeyFn kf, uint32_t* s_hist /*>=260 words*/) {
-  SelectResult res;
-  uint32_t prefix = 0, mask = 0;
-  int remaining = k;
-  for (int pass = 3; pass >= 0; --pass) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    const int shift = 8 * pass;
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-      const int i = i0 + threadIdx.x;
-      uint32_t key = 0;
-      bool ok = (i < n) && kf(i, key) && ((key & mask) == prefix);
-      const uint32_t bin = (key >> shift) & 255u;
-      // warp-aggregated histogram update (values cluster in few bins on the high digits)
-      const uint32_t active = __ballot_sync(0xffffffffu, ok);
-      if (ok) {
-        const uint32_t peers = __match_any_sync(active, bin);
-        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int cum = 0, b = 255;
-      for (; b > 0; --b) {
-        if (cum + (int)s_hist[b] >= remaining) break;
-        cum += (int)s_hist[b];
-      }
-      s_hist[256] = (uint32_t)b;
-      s_hist[257] = (uint32_t)(remaining - cum);
-      s_hist[258] = s_hist[b];
-    }
-    __syncthreads();
-    prefix |= s_hist[256] << shift;
-    mask |= 255u << shift;
-    remaining = (int)s_hist[257];
-    res.count_eq = (int)s_hist[258];
-    __syncthreads();
-  }
-  res.T = prefix;
-  res.take_eq = remaining;
-  return res;
-}
-
-// Ordered (index-ascending) compaction of the selected set into out[0..k): used by every selector.
-// Elements > T are written in index order interleaved with the first take_eq elements == T.
-template <typename KeyFn, typename Emit>
-__device__ void block_emit_selected(int n, int k, const SelectResult& r, KeyFn kf, Emit emit, int* s_scan /*>=40*/) {
-  // running counters: s_scan[32] = written so far, s_scan[33] = eq taken so far
-  if (threadIdx.x == 0) { s_scan[32] = 0; s_scan[33] = 0; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-    const int i = i0 + threadIdx.x;
-    uint32_t key = 0;
-    const bool ok = (i < n) && kf(i, key);
-    const bool gt = ok && key > r.T;
-    const bool eq = ok && key == r.T;
-    // ordered ranks of eq elements (needed only to cap them at take_eq)
-    const uint32_t beq = __ballot_sync(0xffffffffu, eq);
-    if (lane == 0) s_scan[warp] = __popc(beq);
-    __syncthreads();
-    int eq_before = s_scan[33];
-    for (int w = 0; w < warp; ++w) eq_before += s_scan[w];
-    const int eq_rank = eq_before + __popc(beq & ((1u << lane) - 1u));
-    const bool sel = gt || (eq && eq_rank < r.take_eq);
-    int eq_total = 0;
-    for (int w = 0; w < nwarps; ++w) eq_total += s_scan[w];
-    __syncthreads();
-    const uint32_t bsel = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0) s_scan[warp] = __popc(bsel);
-    __syncthreads();
-    int before = s_scan[32];
-    for (int w = 0; w < warp; ++w) before += s_scan[w];
-    const int pos = before + __popc(bsel & ((1u << lane) - 1u));
-    if (sel && pos < k) emit(pos, i, key);
-    int sel_total = 0;
-    for (int w = 0; w < nwarps; ++w) sel_total += s_scan[w];
-    __syncthreads();
-    if (threadIdx.x == 0) { s_scan[32] += sel_total; s_scan[33] += eq_total; }
-    __syncthreads();
-    if (s_scan[32] >= k) break;
-  }
-  __syncthreads();
-}
-
-// Emission in arbitrary order (the caller sorts afterwards); falls back to the ordered pass only when
-// equal keys straddle the cut (lowest index wins).
-template <typename KeyFn, typename Emit>
-__device__ void block_emit_any_order(int n, int k, const SelectResult& r, KeyFn kf, Emit emit, int* s_scan) {
-  if (r.count_eq > r.take_eq) {
-    block_emit_selected(n, k, r, kf, emit, s_scan);
-    return;
-  }
-  if (threadIdx.x == 0) s_scan[32] = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    uint32_t key = 0;
-    if (kf(i, key) && key >= r.T) {
-      const int pos = atomicAdd(&s_scan[32], 1);
-      if (pos < k) emit(pos, i, key);
-    }
-  }
-  __syncthreads();
-}
-
-// in-place bitonic sort (descending) of n_pow2 64-bit keys in shared memory
-__device__ void block_bitonic_desc(unsigned long long* s, int n_pow2) {
-  for (int size = 2; size <= n_pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = s[lo], b = s[hi];
-        if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Box2BoxTransform.apply_deltas + Boxes.clip (detectron2 box_regression.py:88-116, boxes.py clip)
-__device__ __forceinline__ void apply_deltas(const float* box, float d0, float d1, float d2, float d3, float wx,
-                                             float wy, float ww, float wh, float clampv, float* out) {
-  const float widths = box[2] - box[0], heights = box[3] - box[1];
-  const float ctr_x = box[0] + 0.5f * widths, ctr_y = box[1] + 0.5f * heights;
-  const float dx = d0 / wx, dy = d1 / wy;
-  float dw = d2 / ww, dh = d3 / wh;
-  dw = fminf(dw, clampv);
-  dh = fminf(dh, clampv);
-  const float pcx = dx * widths + ctr_x, pcy = dy * heights + ctr_y;
-  const float pw = expf(dw) * widths, ph = expf(dh) * heights;
-  out[0] = pcx - 0.5f * pw;
-  out[1] = pcy - 0.5f * ph;
-  out[2] = pcx + 0.5f * pw;
-  out[3] = pcy + 0.5f * ph;
-}
-__device__ __forceinline__ void clip_box(float* b, float h, float w) {
-  b[0] = fminf(fmaxf(b[0], 0.f), w);
-  b[1] = fminf(fmaxf(b[1], 0.f), h);
-  b[2] = fminf(fmaxf(b[2], 0.f), w);
-  b[3] = fminf(fmaxf(b[3], 0.f), h);
-}
-__device__ __forceinline__ void anchor_box(const aldi_rpn_levels& L, int lvl, int e, float* out) {
-  // e = (h*W + w)*A + a ; DefaultAnchorGenerator: shift (w*stride, h*stride) + cell anchor
-  const int A = L.num_anchors;
-  const int a = e % A;
-  const int loc = e / A;
-  const int w = loc % L.w[lvl], h = loc / L.w[lvl];
-  const float sx = (float)(w * L.stride[lvl]), sy = (float)(h * L.stride[lvl]);
-  const float* c = L.cell[lvl][a];
-  out[0] = sx + c[0]; out[1] = sy + c[1]; out[2] = sx + c[2]; out[3] = sy + c[3];
-}
-// detectron2 pairwise_iou (boxes1 = gt `g`, boxes2 = `b`)
-__device__ __forceinline__ float d2_iou(const float* g, float garea, const float* b, float barea) {
-  float w = fminf(g[2], b[2]) - fmaxf(g[0], b[0]);
-  float h = fminf(g[3], b[3]) - fmaxf(g[1], b[1]);
-  w = fmaxf(w, 0.f);
-  h = fmaxf(h, 0.f);
-  const float inter = w * h;
-  return inter > 0.f ? inter / (garea + barea - inter) : 0.f;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: per (image, level): top-k objectness logits (sorted descending), decode, clip, validity.
-// grid = (levels, N), block = 1024.
-__global__ void __launch_bounds__(1024)
-rpn_topk_decode_kernel(const float* __restrict__ rpn_out, aldi_rpn_levels L, int pre_topk, const int* __restrict__ img_sizes,
-                       float* __restrict__ cand_box, float* __restrict__ cand_score, int* __restrict__ cand_cat,
-                       int* __restrict__ cand_idx, unsigned char* __restrict__ cand_valid, int cand_stride,
-                       int* __restrict__ err_flag) {
-  extern __shared__ unsigned long long s_keys[];  // 2048 entries
-  __shared__ uint32_t s_hist[260];
-  __shared__ int s_scan[40];
-  const int lvl = blockIdx.x, img = blockIdx.y;
-  const int A = L.num_anchors;
-  const int n = L.h[lvl] * L.w[lvl] * A;
-  const int k = n < pre_topk ? n : pre_topk;
-  int cand_off = 0;
-  for (int l = 0; l < lvl; ++l) {
-    const int nl = L.h[l] * L.w[l] * A;
-    cand_off += nl < pre_topk ? nl : pre_topk;
-  }
-  const float* base = rpn_out + ((size_t)img * L.total_locs + L.loc_off[lvl]) * L.ch_stride;
-  auto kf = [&](int i, uint32_t& key) -> bool {
-    const int loc = i / A, a = i - loc * A;
-    key = fkey(__ldg(base + (size_t)loc * L.ch_stride + a));
-    return true;
-  };
-  const SelectResult r = block_select(n, k, kf, s_hist);
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_keys[i] = 0ull;
-  __syncthreads();
-  auto emit = [&](int pos, int i, uint32_t key) {
-    s_keys[pos] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
-  };
-  block_emit_any_order(n, k, r, kf, emit, s_scan);
-  block_bitonic_desc(s_keys, 2048);
-  const float img_h = (float)img_sizes[2 * img], img_w = (float)img_sizes[2 * img + 1];
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const int e = (int)(0xFFFFFFFFu - (uint32_t)(s_keys[j] & 0xFFFFFFFFull));
-    const int loc = e / A, a = e - loc * A;
-    const float* row = base + (size_t)loc * L.ch_stride;
-    const float score = row[a];
-    float anc[4], box[4];
-    anchor_box(L, lvl, e, anc);
-    const float* d = row + A + a * 4;
-    apply_deltas(anc, d[0], d[1], d[2], d[3], 1.f, 1.f, 1.f, 1.f, L.scale_clamp, box);
-    const bool finite = isfinite(box[0]) && isfinite(box[1]) && isfinite(box[2]) && isfinite(box[3]) && isfinite(score);
-    if (!finite && err_flag) atomicOr(err_flag, 1);
-    clip_box(box, img_h, img_w);
-    const bool nonempty = (box[2] - box[0] > L.min_box_size) && (box[3] - box[1] > L.min_box_size);
-    const size_t o = (size_t)img * cand_stride + cand_off + j;
-    cand_box[o * 4 + 0] = box[0]; cand_box[o * 4 + 1] = box[1]; cand_box[o * 4 + 2] = box[2]; cand_box[o * 4 + 3] = box[3];
-    cand_score[o] = score;
-    cand_cat[o] = lvl;
-    cand_idx[o] = e;
-    cand_valid[o] = (finite && nonempty) ? 1 : 0;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // K3a: per image: sort valid candidates by score (descending, ties by position) and gather.
@@ -341,40 +91,57 @@ nms_mask_kernel(const float* __restrict__ sbox, const int* __restrict__ scat, co
   mask[((size_t)img * cpad + i) * words + cb] = bits;
 }
 
-// K3c: greedy scan in score order, 64 boxes at a time.  grid = N, block = 256 (thread w owns word w of
-// the `removed` bitmap).  Writes the first `post_topk` kept boxes.
+// K3c: greedy scan in score order, 64 boxes at a time.  grid = N, block = 256, dynamic smem = post_topk ints.
+// "Pull" formulation: the kept boxes so far live in a shared list; for chunk c every thread ORs column word c of
+// its share of the kept rows (independent loads, one round trip), a block OR-reduction yields the chunk's
+// `removed` word, one thread resolves the 64 boxes serially against the diagonal words staged in shared memory
+// (prefetched a chunk ahead), and the newly kept boxes are written out in parallel.
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const float* __restrict__ sbox,
                 const float* __restrict__ sscore, const int* __restrict__ scat, const int* __restrict__ sperm,
                 const int* __restrict__ nvalid, int cpad, int post_topk, float* __restrict__ out_box,
                 float* __restrict__ out_score, int* __restrict__ out_cat, int* __restrict__ out_src,
                 int* __restrict__ out_count) {
+  extern __shared__ int s_keptlist[];  // sorted-order indices of the kept boxes
   const int img = blockIdx.x;
   const int nv = nvalid[img];
   const int words = cpad >> 6;
-  const int w = threadIdx.x;
-  __shared__ unsigned long long s_kept, s_removed_c;
-  __shared__ int s_total;
-  unsigned long long removed = 0ull;  // this thread's word of the removed bitmap
-  if (threadIdx.x == 0) s_total = 0;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned long long* mrow = mask + (size_t)img * cpad * words;
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned long long s_part[8];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_total, s_base;
+  if (t == 0) s_total = 0;
   __syncthreads();
   const int nchunks = (nv + 63) >> 6;
+  unsigned long long diag_next = 0ull;
+  if (t < 64 && t < nv) diag_next = mrow[(size_t)t * words];
   for (int c = 0; c < nchunks; ++c) {
-    if (w == c) s_removed_c = removed;
+    const int total0 = s_total;
+    unsigned long long part = 0ull;
+    for (int k = t; k < total0; k += 256) part |= mrow[(size_t)s_keptlist[k] * words + c];
+    uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)part);
+    uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(part >> 32));
+    if (lane == 0) s_part[warp] = ((unsigned long long)hi << 32) | lo;
+    if (t < 64) s_diag[t] = diag_next;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long rem = s_removed_c, kept = 0ull;
+    if (t < 64 && c + 1 < nchunks) {
+      const int r = (c + 1) * 64 + t;
+      diag_next = (r < nv) ? mrow[(size_t)r * words + c + 1] : 0ull;
+    }
+    if (t == 0) {
+      unsigned long long rem = 0ull, kept = 0ull;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rem |= s_part[i];
       const int lim = min(64, nv - c * 64);
-      int total = s_total;
+      int total = total0;
+      s_base = total;
       for (int b = 0; b < lim && total < post_topk; ++b) {
         if (!((rem >> b) & 1ull)) {
           kept |= 1ull << b;
-          rem |= mask[((size_t)img * cpad + c * 64 + b) * words + c];
-          const size_t src = (size_t)img * cpad + c * 64 + b, dst = (size_t)img * post_topk + total;
-          reinterpret_cast<float4*>(out_box)[dst] = reinterpret_cast<const float4*>(sbox)[src];
-          out_score[dst] = sscore[src];
-          out_cat[dst] = scat[src];
-          out_src[dst] = sperm[src];
+          rem |= s_diag[b];
+          s_keptlist[total] = c * 64 + b;
           ++total;
         }
       }
@@ -382,19 +149,19 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const float* __rest
       s_total = total;
     }
     __syncthreads();
-    if (s_total >= post_topk) break;
-    unsigned long long kept = s_kept;
-    if (w > c && w < words) {
-      while (kept) {
-        const int b = __ffsll((long long)kept) - 1;
-        kept &= kept - 1;
-        removed |= mask[((size_t)img * cpad + c * 64 + b) * words + w];
-      }
+    const unsigned long long kept = s_kept;
+    if (t < 64 && ((kept >> t) & 1ull)) {
+      const int rank = __popcll(kept & ((1ull << t) - 1ull));
+      const size_t src = (size_t)img * cpad + c * 64 + t, dst = (size_t)img * post_topk + s_base + rank;
+      reinterpret_cast<float4*>(out_box)[dst] = reinterpret_cast<const float4*>(sbox)[src];
+      out_score[dst] = sscore[src];
+      out_cat[dst] = scat[src];
+      out_src[dst] = sperm[src];
     }
-    __syncthreads();
+    if (s_total >= post_topk) break;
   }
   __syncthreads();
-  if (threadIdx.x == 0) out_count[img] = s_total;
+  if (t == 0) out_count[img] = s_total;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -457,65 +224,6 @@ rpn_match_kernel(aldi_rpn_levels L, const float* __restrict__ gt_boxes, const in
     for (int i = threadIdx.x; i < g; i += blockDim.x)
       if (s_best[i] > 0) atomicMax(gt_best + (size_t)img * gmax + i, s_best[i]);
   }
-}
-
-// K4b: subsample_labels on a dense label array: keep num_pos positives / num_neg negatives with the
-// smallest hash keys, everything else -> -1.  grid = N, block = 1024.
-__global__ void __launch_bounds__(1024)
-subsample_kernel(signed char* __restrict__ labels, int n, int num_samples, float pos_fraction, uint32_t seed,
-                 const uint32_t* __restrict__ salts, int* __restrict__ stats /*N*2: num_pos,num_neg*/) {
-  __shared__ uint32_t s_hist[260];
-  __shared__ int s_cnt[2];
-  const int img = blockIdx.x;
-  signed char* lab = labels + (size_t)img * n;
-  const uint32_t salt = salts[img];
-  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  int cp = 0, cn = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const signed char v = lab[i];
-    cp += (v == 1);
-    cn += (v == 0);
-  }
-  cp = warp_sum_i(cp);
-  cn = warp_sum_i(cn);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], cp); atomicAdd(&s_cnt[1], cn); }
-  __syncthreads();
-  int num_pos = (int)(num_samples * pos_fraction);
-  num_pos = min(s_cnt[0], num_pos);
-  int num_neg = min(s_cnt[1], num_samples - num_pos);
-  __syncthreads();
-  // positives: keep the num_pos smallest hashes == largest ~hash
-  auto kpos = [&](int i, uint32_t& key) -> bool { key = ~sample_hash(seed, salt * 2u + 0u, (uint32_t)i); return lab[i] == 1; };
-  auto kneg = [&](int i, uint32_t& key) -> bool { key = ~sample_hash(seed, salt * 2u + 1u, (uint32_t)i); return lab[i] == 0; };
-  SelectResult rp, rn;
-  rp.T = 0xFFFFFFFFu; rp.take_eq = 0; rp.count_eq = 0;
-  rn = rp;
-  if (num_pos > 0) rp = block_select(n, num_pos, kpos, s_hist);
-  if (num_neg > 0) rn = block_select(n, num_neg, kneg, s_hist);
-  // ties at the threshold are resolved lowest-index-first; with 32-bit hashes they are rare, so the
-  // (sequential) ordered pass only runs when count_eq > take_eq
-  __syncthreads();
-  const bool tie_p = num_pos > 0 && rp.count_eq > rp.take_eq;
-  const bool tie_n = num_neg > 0 && rn.count_eq > rn.take_eq;
-  if ((tie_p || tie_n) && threadIdx.x == 0) {
-    int tp = 0, tn = 0;
-    for (int i = 0; i < n; ++i) {
-      uint32_t key;
-      if (tie_p && kpos(i, key) && key == rp.T) { if (tp >= rp.take_eq) lab[i] = -2; ++tp; }
-      if (tie_n && kneg(i, key) && key == rn.T) { if (tn >= rn.take_eq) lab[i] = -2; ++tn; }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const signed char v = lab[i];
-    signed char o = -1;
-    uint32_t key;
-    if (v == 1 && num_pos > 0) { kpos(i, key); if (key >= rp.T) o = 1; }
-    else if (v == 0 && num_neg > 0) { kneg(i, key); if (key >= rn.T) o = 0; }
-    lab[i] = o;
-  }
-  if (threadIdx.x == 0 && stats) { stats[2 * img] = num_pos; stats[2 * img + 1] = num_neg; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,29 +413,6 @@ __global__ void pseudo_threshold_kernel(const float* __restrict__ box, const flo
 }  // namespace
 
 // =================================================================================================
-extern "C" int aldi_rpn_topk_decode(const float* rpn_out, const aldi_rpn_levels* L, int n_images, int pre_topk,
-                                    const int* img_sizes, float* cand_box, float* cand_score, int* cand_cat,
-                                    int* cand_idx, unsigned char* cand_valid, int cand_stride, int* err_flag,
-                                    void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ALDI_CHECK_ARG(rpn_out && L && img_sizes && cand_box && cand_score && cand_cat && cand_idx && cand_valid,
-                 "aldi_rpn_topk_decode: null pointer");
-  ALDI_CHECK_ARG(pre_topk > 0 && pre_topk <= 2048, "aldi_rpn_topk_decode: pre_topk must be in (0, 2048]");
-  ALDI_CHECK_ARG(L->num_levels >= 1 && L->num_levels <= 5 && L->num_anchors >= 1 && L->num_anchors <= 3,
-                 "aldi_rpn_topk_decode: bad level table");
-  int need = 0;
-  for (int l = 0; l < L->num_levels; ++l) {
-    int nl = L->h[l] * L->w[l] * L->num_anchors;
-    need += nl < pre_topk ? nl : pre_topk;
-  }
-  ALDI_CHECK_ARG(cand_stride >= need, "aldi_rpn_topk_decode: cand_stride %d < %d", cand_stride, need);
-  rpn_topk_decode_kernel<<<dim3(L->num_levels, n_images), 1024, 2048 * sizeof(unsigned long long), stream>>>(
-      rpn_out, *L, pre_topk, img_sizes, cand_box, cand_score, cand_cat, cand_idx, cand_valid, cand_stride, err_flag);
-  ALDI_COUNT_LAUNCH();
-  ALDI_CUDA_LAUNCH_CHECK("aldi_rpn_topk_decode");
-  return ALDI_OK;
-}
-
 extern "C" size_t aldi_nms_workspace_bytes(int n_images, int cand_stride) {
   size_t cpad = 64;
   while ((int)cpad < cand_stride) cpad <<= 1;
@@ -765,24 +450,41 @@ extern "C" int aldi_nms_sorted(const float* cand_box, const float* cand_score, c
                                                                 cand_stride, cpad, sbox, sscore, scat, sperm, nvalid);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_nms_sorted(sort)");
-  nms_mask_kernel<<<dim3(words, words, n_images), 64, 0, stream>>>(sbox, scat, nvalid, cpad, iou_thresh, mask);
+  const int wused = (cand_stride + 63) / 64;  // nvalid <= cand_stride: blocks beyond it would exit immediately
+  nms_mask_kernel<<<dim3(wused, wused, n_images), 64, 0, stream>>>(sbox, scat, nvalid, cpad, iou_thresh, mask);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_nms_sorted(mask)");
-  nms_scan_kernel<<<n_images, 256, 0, stream>>>(mask, sbox, sscore, scat, sperm, nvalid, cpad, post_topk, out_box,
+  ALDI_CHECK_ARG(post_topk > 0 && post_topk <= 8192, "aldi_nms_sorted: post_topk must be in (0, 8192]");
+  nms_scan_kernel<<<n_images, 256, (size_t)post_topk * sizeof(int), stream>>>(mask, sbox, sscore, scat, sperm, nvalid, cpad, post_topk, out_box,
                                                 out_score, out_cat, out_src, out_count);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_nms_sorted(scan)");
   return ALDI_OK;
 }
 
+// multi-block subsample_labels (select_mb.cu)
+size_t aldi_subsample_workspace_bytes(int n_images);
+int aldi_subsample_labels(signed char* labels, int n_images, int n, int num_samples, float pos_fraction,
+                          unsigned int seed, const unsigned int* salts, int* stats, void* workspace, cudaStream_t stream);
+
+extern "C" size_t aldi_rpn_label_workspace_bytes(int n_images, int gmax) {
+  return (((size_t)n_images * gmax * sizeof(int) + 255) & ~size_t(255)) + aldi_subsample_workspace_bytes(n_images) + 256;
+}
+
 extern "C" int aldi_rpn_label_anchors(const aldi_rpn_levels* L, int n_images, const float* gt_boxes,
                                       const int* gt_counts, int gmax, float iou_lo, float iou_hi, int num_samples,
                                       float pos_fraction, unsigned int seed, const unsigned int* salts,
-                                      int* gt_best_ws, signed char* labels, int* matched, int* stats, void* stream_) {
+                                      void* workspace, size_t workspace_bytes, signed char* labels, int* matched,
+                                      int* stats, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ALDI_CHECK_ARG(L && gt_boxes && gt_counts && salts && gt_best_ws && labels && matched,
+  ALDI_CHECK_ARG(L && gt_boxes && gt_counts && salts && workspace && labels && matched,
                  "aldi_rpn_label_anchors: null pointer");
   ALDI_CHECK_ARG(gmax > 0 && gmax <= 2048, "aldi_rpn_label_anchors: gmax must be in (0, 2048]");
+  ALDI_CHECK_ARG(workspace_bytes >= aldi_rpn_label_workspace_bytes(n_images, gmax),
+                 "aldi_rpn_label_anchors: workspace too small");
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  int* gt_best_ws = reinterpret_cast<int*>(ws);
+  void* sub_ws = ws + (((size_t)n_images * gmax * sizeof(int) + 255) & ~size_t(255));
   int total = 0;
   for (int l = 0; l < L->num_levels; ++l) total += L->h[l] * L->w[l] * L->num_anchors;
   cudaError_t e = cudaMemsetAsync(gt_best_ws, 0, (size_t)n_images * gmax * sizeof(int), stream);
@@ -796,11 +498,8 @@ extern "C" int aldi_rpn_label_anchors(const aldi_rpn_levels* L, int n_images, co
     ALDI_COUNT_LAUNCH();
     ALDI_CUDA_LAUNCH_CHECK("aldi_rpn_label_anchors(match)");
   }
-  if (num_samples > 0) {
-    subsample_kernel<<<n_images, 1024, 0, stream>>>(labels, total, num_samples, pos_fraction, seed, salts, stats);
-    ALDI_COUNT_LAUNCH();
-    ALDI_CUDA_LAUNCH_CHECK("aldi_rpn_label_anchors(subsample)");
-  }
+  if (num_samples > 0)
+    return aldi_subsample_labels(labels, n_images, total, num_samples, pos_fraction, seed, salts, stats, sub_ws, stream);
   return ALDI_OK;
 }
 

@@ -141,7 +141,7 @@ class DetectorWeights:
         for name, g in self.geom.items():
             taps = g.k * g.k
             if name == "stem":
-                kdim = 192 if self.stem_gemm else taps * 4
+                kdim = 256 if self.stem_gemm else taps * 4
                 self.fwd[name] = torch.zeros(g.cout_p, kdim, device=self.dev, dtype=dtype)
             else:
                 self.fwd[name] = torch.zeros(g.cout_p, taps * g.cin_p, device=self.dev, dtype=dtype)
@@ -149,6 +149,7 @@ class DetectorWeights:
                 self.scale[name] = torch.zeros(g.cout_p, device=self.dev)
             self.shift[name] = torch.zeros(g.cout_p, device=self.dev)
         self.no_dgrad = {"stem", "res3.0.conv1", "res3.0.shortcut", "fpn_lateral2"}
+        self._tables = {}
 
     # ---- flat views -------------------------------------------------------------------------------
     def view(self, layer, field, buf=None):
@@ -162,28 +163,67 @@ class DetectorWeights:
         for name, g in self.geom.items():
             if g.trainable and name not in self.no_dgrad and name not in self.dgrad:
                 self.dgrad[name] = torch.zeros(g.cin_p, g.k * g.k * g.cout_p, device=self.dev, dtype=self.dtype)
+        self._tables = {}
 
-    def refresh(self):
-        """Re-derive operands from the master weights (after load / optimizer step / EMA update)."""
+    # ---- operand refresh: ONE launch per table (csrc/optim.cu refresh_kernel) ------------------------------------
+    def _descs(self, trainable_only):
+        """Descriptor list re-deriving the GEMM operands / folded FrozenBN of (a subset of) the layers."""
+        dt = _l.BF16 if self.dtype == torch.bfloat16 else _l.F32
+        out = []
+
+        def desc(kind, **kw):
+            d = _l.RefreshDesc()
+            d.kind, d.out_dtype, d.eps = kind, dt, 1e-5
+            for k, v in kw.items():
+                setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+            out.append(d)
+
         for name, g in self.geom.items():
             taps = g.k * g.k
             w = self.view(name, "weight")
+            bn = {}
             if g.norm:
-                ops.call("aldi_frozenbn_fold", self.view(name, "norm.weight"), self.view(name, "norm.bias"),
-                         self.view(name, "norm.running_mean"), self.view(name, "norm.running_var"), 1e-5,
-                         self.scale[name], self.shift[name], g.cout)
-            else:
-                self.shift[name][:g.cout].copy_(self.view(name, "bias"))
+                bn = dict(bn_w=self.view(name, "norm.weight"), bn_b=self.view(name, "norm.bias"),
+                          bn_mean=self.view(name, "norm.running_mean"), bn_var=self.view(name, "norm.running_var"))
+            if not trainable_only:
+                # FrozenBN buffers / biases of frozen layers only move for the EMA teacher (aldi/ema.py covers buffers, T7)
+                if g.norm:
+                    desc(2, out=self.scale[name], out2=self.shift[name], cout=g.cout, **bn)
+            if not g.norm and (g.trainable or not trainable_only):
+                desc(3, w=self.view(name, "bias"), out2=self.shift[name], cout=g.cout)
+            if trainable_only and not g.trainable:
+                continue
             if name == "stem":
                 if self.stem_gemm:
-                    ops.pack_weight(w, self.fwd[name], cout=g.cout, taps=1, cin=147, cout_p=g.cout_p, cin_p=192)
+                    desc(4, w=w, out=self.fwd[name], cout=g.cout, cout_p=g.cout_p)
                 else:
-                    ops.pack_weight(w, self.fwd[name], cout=g.cout, taps=taps, cin=3, cout_p=g.cout_p, cin_p=4)
+                    desc(0, w=w, out=self.fwd[name], cout=g.cout, taps=taps, cin=3, cout_p=g.cout_p, cin_p=4)
             else:
-                ops.pack_weight(w, self.fwd[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
+                desc(0, w=w, out=self.fwd[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
             if name in self.dgrad:
-                ops.pack_weight(w, self.dgrad[name], dgrad=True, scale=self.scale.get(name), cout=g.cout, taps=taps,
-                                cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
+                desc(1, w=w, out=self.dgrad[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p, **bn)
+        return out
+
+    def _table(self, trainable_only):
+        key = bool(trainable_only)
+        if key not in self._tables:
+            L = _l.load()
+            descs = self._descs(trainable_only)
+            arr = (_l.RefreshDesc * len(descs))(*descs)
+            starts, tot = [], 0
+            for d in descs:
+                starts.append(tot)
+                tot += int(L.aldi_refresh_blocks(_l.ctypes.byref(d)))
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+            st = torch.tensor(starts, dtype=torch.int32).to(self.dev)
+            self._tables[key] = (raw, st, len(descs), tot)
+        return self._tables[key]
+
+    def refresh(self, trainable_only=False):
+        """Re-derive operands from the master weights (after load / optimizer step / EMA update).
+        trainable_only: the student after an optimizer step — frozen layers and FrozenBN buffers did not move."""
+        raw, st, n, tot = self._table(trainable_only)
+        ops.call("aldi_refresh_operands", raw, st, n, tot)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -244,10 +284,15 @@ class Detector:
         ho, wo = hp // 2, wp // 2
         stem_out = torch.empty(n, ho, wo, 64, device=dev, dtype=dt)
         if W.stem_gemm:
-            col = torch.empty(n, ho, wo, 192, device=dev, dtype=dt)
-            ops.call("aldi_stem_im2col", images_u8, sizes, col, n, hp, wp, ho, wo, mean, std)
-            ops.conv(col, W.fwd["stem"], stem_out, scale=W.scale["stem"], bias=W.shift["stem"], relu=True, algo_cin=147)
-            del col
+            # 7x7/2 conv == 4x4/1 conv over the normalised 2x2 space-to-depth map; the 4 column taps of an output
+            # pixel are 64 contiguous values, read through an overlapping-row view (row stride 16) as ONE TMA row
+            wpad = wo + 4
+            s2d = torch.empty(n, ho, wpad, 16, device=dev, dtype=dt)
+            ops.call("aldi_stem_s2d", images_u8, sizes, s2d, n, hp, wp, mean, std)
+            view = s2d.as_strided((n, ho, wo, 64), (ho * wpad * 16, wpad * 16, 16, 1))
+            ops.conv(view, W.fwd["stem"], stem_out, taps_h=4, taps_w=1, pad_h=2, pad_w=0, scale=W.scale["stem"],
+                     bias=W.shift["stem"], relu=True, algo_cin=147 / 4.0)
+            del view, s2d
         else:
             x0 = torch.empty(n, hp, wp, 4, device=dev, dtype=torch.float32)
             ops.call("aldi_preprocess", images_u8, sizes, x0, n, hp, wp, hp, wp, mean, std)
@@ -312,8 +357,10 @@ class Detector:
         cc = torch.empty(n, stride, dtype=torch.int32, device=dev)
         ci = torch.empty(n, stride, dtype=torch.int32, device=dev)
         cv = torch.empty(n, stride, dtype=torch.uint8, device=dev)
+        wsb = int(_l.load().aldi_rpn_topk_workspace_bytes(n, lv.num_levels))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         ops.call("aldi_rpn_topk_decode", rpn_out, _l.ctypes.byref(lv), n, pre_topk, sizes, cb, cs, cc, ci, cv, stride,
-                 err_flag)
+                 err_flag, ws, wsb)
         out = self.nms(cb, cs, cc, cv, None, nms_thresh, post_topk)
         out["cand"] = (cb, cs, cc, ci, cv)
         return out

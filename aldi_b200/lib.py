@@ -42,6 +42,14 @@ class WgradParams(ctypes.Structure):
     ]
 
 
+class RefreshDesc(ctypes.Structure):
+    _fields_ = [
+        ("kind", c_int), ("out_dtype", c_int), ("w", c_void_p), ("bn_w", c_void_p), ("bn_b", c_void_p),
+        ("bn_mean", c_void_p), ("bn_var", c_void_p), ("out", c_void_p), ("out2", c_void_p),
+        ("cout", c_int), ("taps", c_int), ("cin", c_int), ("cout_p", c_int), ("cin_p", c_int), ("eps", c_float),
+    ]
+
+
 class RoiAlignParams(ctypes.Structure):
     _fields_ = [
         ("feat", c_void_p * 4), ("dfeat", c_void_p * 4), ("feat_h", c_int * 4), ("feat_w", c_int * 4),
@@ -76,12 +84,15 @@ SIGNATURES = {
                                        c_void_p, c_double, c_void_p]),
     "aldi_pack_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
+    "aldi_refresh_blocks": (c_int, [ctypes.POINTER(RefreshDesc)]),
+    "aldi_refresh_operands": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "aldi_conv_tc": (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     "aldi_conv_f32": (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     "aldi_wgrad_tc": (c_int, [ctypes.POINTER(WgradParams), c_void_p]),
     "aldi_wgrad_f32": (c_int, [ctypes.POINTER(WgradParams), c_void_p]),
     "aldi_preprocess": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "aldi_stem_im2col": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "aldi_stem_s2d": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
     "aldi_maxpool3x3s2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_sum2x2_accum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_add_f32": (c_int, [P, c_int, P, c_size_t, P]),
@@ -89,11 +100,14 @@ SIGNATURES = {
     "aldi_frozenbn_fold": (c_int, [P, P, P, P, c_float, P, P, c_int, P]),
     "aldi_roi_align_forward": (c_int, [ctypes.POINTER(RoiAlignParams), P]),
     "aldi_roi_align_backward": (c_int, [ctypes.POINTER(RoiAlignParams), P]),
-    "aldi_rpn_topk_decode": (c_int, [P, ctypes.POINTER(RpnLevels), c_int, c_int, P, P, P, P, P, P, c_int, P, P]),
+    "aldi_rpn_topk_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "aldi_rpn_topk_decode": (c_int, [P, ctypes.POINTER(RpnLevels), c_int, c_int, P, P, P, P, P, P, c_int, P, P, c_size_t,
+                                     P]),
     "aldi_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aldi_nms_sorted": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_int, P, c_size_t, P, P, P, P, P, P]),
+    "aldi_rpn_label_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aldi_rpn_label_anchors": (c_int, [ctypes.POINTER(RpnLevels), c_int, P, P, c_int, c_float, c_float, c_int, c_float,
-                                       c_uint, P, P, P, P, P, P]),
+                                       c_uint, P, P, c_size_t, P, P, P, P]),
     "aldi_roi_label_sample": (c_int, [P, P, c_int, c_int, P, P, P, c_int, c_float, c_int, c_int, c_float, c_uint, P,
                                       c_int, P, P, P, P, P, P, P, P]),
     "aldi_roi_inference_candidates": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, c_float, P, c_float, P, P, P, P,

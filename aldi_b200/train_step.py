@@ -261,9 +261,10 @@ class B200TrainStep:
         labels = torch.empty(n, total, dtype=torch.int8, device=self.device)
         matched = torch.empty(n, total, dtype=torch.int32, device=self.device)
         stats = torch.zeros(n, 2, dtype=torch.int32, device=self.device)
-        ws = torch.empty(n, gt.gmax, dtype=torch.int32, device=self.device)
+        wsb = int(_l.load().aldi_rpn_label_workspace_bytes(n, gt.gmax))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
         ops.call("aldi_rpn_label_anchors", _l.ctypes.byref(lv), n, gt.boxes, gt.counts, gt.gmax, cfg.rpn_iou[0],
-                 cfg.rpn_iou[1], cfg.rpn_batch, cfg.rpn_pos_fraction, self.seed, self._salts(n, pass_id, site), ws,
+                 cfg.rpn_iou[1], cfg.rpn_batch, cfg.rpn_pos_fraction, self.seed, self._salts(n, pass_id, site), ws, wsb,
                  labels, matched, stats)
         return labels, matched, stats
 
@@ -369,7 +370,7 @@ class B200TrainStep:
         p = self.student.flat[:self.nt]
         ops.sgd_momentum_step(p, self.momentum_buf, self.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
         self.grad.zero_()
-        self.student.refresh()
+        self.student.refresh(trainable_only=True)
         self.iter += 1
 
     # ---- a whole iteration: before_step + run_step ----------------------------------------------------------

@@ -59,6 +59,31 @@ int aldi_sgd_momentum_step(float* params, float* momentum_buf, const float* grad
 int aldi_pack_weight(const float* w, const float* scale, void* out, int out_dtype, int dgrad, int cout, int taps,
                      int cin, int cout_p, int cin_p, void* stream);
 
+/* ---- batched operand refresh: all packs / FrozenBN folds / bias copies of one model in ONE launch.
+ * `d_descs` and `d_block_start` are DEVICE arrays built once by the host (block_start[i] = sum of
+ * aldi_refresh_blocks(desc[j]) for j < i; total_blocks = the full sum).
+ *   kind 0: forward operand pack (as aldi_pack_weight dgrad=0)
+ *   kind 1: data-gradient operand pack, FrozenBN scale derived in place from bn_w / bn_var (NULL: no scale)
+ *   kind 2: FrozenBN fold: out[i] = bn_w*rsqrt(bn_var+eps) (scale), out2[i] = bn_b - bn_mean*scale (shift), i < cout
+ *   kind 3: out2[i] = w[i], i < cout (conv bias -> epilogue shift)
+ *   kind 4: stem weights (cout,7,7,3) -> bf16 [cout_p][4][4][2][2][4] taps over the space-to-depth map
+ *           of aldi_stem_s2d (row tap a, column tap b, r+1 = 2a+dy, s+1 = 2b+dx, zero where r/s = -1, c = 3) */
+typedef struct {
+  int kind, out_dtype;
+  const float* w;
+  const float* bn_w;
+  const float* bn_b;
+  const float* bn_mean;
+  const float* bn_var;
+  void* out;
+  float* out2;
+  int cout, taps, cin, cout_p, cin_p;
+  float eps;
+} aldi_refresh_desc;
+int aldi_refresh_blocks(const aldi_refresh_desc* desc);
+int aldi_refresh_operands(const aldi_refresh_desc* d_descs, const int* d_block_start, int n_desc, int total_blocks,
+                          void* stream);
+
 /* ---- implicit-GEMM convolution / linear on tcgen05 tensor cores (bf16 in, fp32 accumulate) ----
  * Replaces cuDNN/cuBLAS calls under detectron2 ResNet/FPN/RPN/box-head (reached from aldi/trainer.py:87,
  * aldi/distill.py:157,162, aldi/pseudolabeler.py:21).  One call = forward OR data-gradient of one layer:
@@ -118,6 +143,11 @@ int aldi_preprocess(const uint8_t* images /*(N,3,hin,win) uint8*/, const int* si
 /* fused normalise + im2col of the stem's 7x7/2 conv: out bf16 (N,ho,wo,192), k=(r*7+s)*3+c, zero for k>=147 */
 int aldi_stem_im2col(const uint8_t* images, const int* sizes, void* out_bf16, int n, int hin, int win, int ho, int wo,
                      const float* h_mean, const float* h_std, void* stream);
+/* fused normalise + 2x2 space-to-depth of the uint8 canvas: out bf16 (N, hin/2, win/2 + 4, 16), channel
+ * (dy*2+dx)*4 + c, two zero columns each side; the stem conv reads it through an overlapping-row view
+ * (N, hin/2, win/2, 64) with element strides (.., (win/2+4)*16, 16, 1) as a 4x1-tap conv, pad_h 2 */
+int aldi_stem_s2d(const uint8_t* images, const int* sizes, void* out_bf16, int n, int hin, int win,
+                  const float* h_mean, const float* h_std, void* stream);
 int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, int h, int w, int c, void* stream);
 /* coarse[n,h,w,c] += sum of the 2x2 block of fine (backward of nearest-2x upsample + add in FPN top-down) */
 int aldi_sum2x2_accum(const void* fine, void* coarse, int dtype, int n, int h, int w, int c, void* stream);
@@ -159,9 +189,11 @@ typedef struct {
 } aldi_rpn_levels;
 /* detectron2 find_top_rpn_proposals front half: per (image, level) top-k logits (descending), decode
  * (Box2BoxTransform weights 1), clip, finite/non-empty validity.  Candidates are level-major.        */
+size_t aldi_rpn_topk_workspace_bytes(int n_images, int num_levels);
 int aldi_rpn_topk_decode(const float* rpn_out, const aldi_rpn_levels* levels, int n_images, int pre_topk,
                          const int* img_sizes, float* cand_box, float* cand_score, int* cand_cat, int* cand_idx,
-                         unsigned char* cand_valid, int cand_stride, int* err_flag, void* stream);
+                         unsigned char* cand_valid, int cand_stride, int* err_flag, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* batched_nms (per-category greedy NMS, IoU > thresh suppresses) + keep[:post_topk]; output in score order */
 size_t aldi_nms_workspace_bytes(int n_images, int cand_stride);
 int aldi_nms_sorted(const float* cand_box, const float* cand_score, const int* cand_cat,
@@ -169,10 +201,11 @@ int aldi_nms_sorted(const float* cand_box, const float* cand_score, const int* c
                     float iou_thresh, int post_topk, void* workspace, size_t workspace_bytes, float* out_box,
                     float* out_score, int* out_cat, int* out_src, int* out_count, void* stream);
 /* RPN.label_and_sample_anchors: Matcher([lo,hi],[0,-1,1], low-quality) + subsample_labels; labels (N,R) int8 */
+size_t aldi_rpn_label_workspace_bytes(int n_images, int gmax);
 int aldi_rpn_label_anchors(const aldi_rpn_levels* levels, int n_images, const float* gt_boxes, const int* gt_counts,
                            int gmax, float iou_lo, float iou_hi, int num_samples, float pos_fraction,
-                           unsigned int seed, const unsigned int* salts, int* gt_best_ws, signed char* labels,
-                           int* matched, int* stats, void* stream);
+                           unsigned int seed, const unsigned int* salts, void* workspace, size_t workspace_bytes,
+                           signed char* labels, int* matched, int* stats, void* stream);
 /* StandardROIHeads.label_and_sample_proposals: append GT, Matcher([thr],[0,1]), subsample; (N*num_samples) rows */
 int aldi_roi_label_sample(const float* prop_box, const int* prop_count, int prop_stride, int n_images,
                           const float* gt_boxes, const int* gt_classes, const int* gt_counts, int gmax,

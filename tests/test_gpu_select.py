@@ -61,10 +61,11 @@ def test_rpn_label_and_sample_exact(count):
     labels = torch.empty(n, total, dtype=torch.int8, device=dev)
     matched = torch.empty(n, total, dtype=torch.int32, device=dev)
     stats = torch.zeros(n, 2, dtype=torch.int32, device=dev)
-    ws = torch.empty(n, gmax, dtype=torch.int32, device=dev)
+    wsb = int(_l.load().aldi_rpn_label_workspace_bytes(n, gmax))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     salts = torch.tensor([sampling.make_salt(pass_id, sampling.SITE_RPN, i) for i in range(n)], dtype=torch.int32, device=dev)
     ops.call("aldi_rpn_label_anchors", ctypes.byref(lv), n, gb.to(dev), cnt.to(dev), gmax, 0.3, 0.7, 256, 0.5, seed, salts,
-             ws, labels, matched, stats)
+             ws, wsb, labels, matched, stats)
     torch.cuda.synchronize()
     for i in range(n):
         got, want = labels[i].cpu(), ref_labels[i]

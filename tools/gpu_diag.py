@@ -160,6 +160,48 @@ def case_fwd_epilogue2():
     return ok
 
 
+def case_stem():
+    """bf16 stem: normalise + space-to-depth + 4x1-tap conv over the overlapping-row view vs F.conv2d(7x7, s2, p3)."""
+    import torch
+    import torch.nn.functional as F
+    from aldi_b200 import arch
+    from aldi_b200.detector import Detector, DetectorWeights, FlatLayout, PIXEL_MEAN
+    ok = True
+    for (n, h, w, vh, vw) in ((2, 64, 96, 64, 96), (2, 96, 160, 81, 150)):
+        g = torch.Generator().manual_seed(h)
+        img = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8)
+        img[:, :, vh:, :] = 0
+        img[:, :, :, vw:] = 0
+        sizes = torch.tensor([[vh, vw]] * n, dtype=torch.int32)
+        layout = FlatLayout(8)
+        sd = arch.synthetic_state_dict(3)
+        W = DetectorWeights(layout, layout.pack_state_dict(sd).cuda(), torch.bfloat16)
+        W.refresh()
+        det = Detector(8)
+        # run only the stem part of backbone(): replicate its first lines
+        from aldi_b200 import ops
+        mean, std = ops.host_floats(PIXEL_MEAN), ops.host_floats((1.0, 1.0, 1.0))
+        ho, wo = h // 2, w // 2
+        wpad = wo + 4
+        s2d = torch.empty(n, ho, wpad, 16, device="cuda", dtype=torch.bfloat16)
+        ops.call("aldi_stem_s2d", img.cuda(), sizes.cuda(), s2d, n, h, w, mean, std)
+        view = s2d.as_strided((n, ho, wo, 64), (ho * wpad * 16, wpad * 16, 16, 1))
+        out = torch.empty(n, ho, wo, 64, device="cuda", dtype=torch.bfloat16)
+        ops.conv(view, W.fwd["stem"], out, taps_h=4, taps_w=1, pad_h=2, pad_w=0, scale=W.scale["stem"],
+                 bias=W.shift["stem"], relu=True)
+        torch.cuda.synchronize()
+        x = img.float() - torch.tensor(PIXEL_MEAN).view(1, 3, 1, 1)
+        x[:, :, vh:, :] = 0
+        x[:, :, :, vw:] = 0
+        wt = sd["backbone.bottom_up.stem.conv1.weight"]
+        y = F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), stride=2, padding=3)
+        bn = {k: sd["backbone.bottom_up.stem.conv1.norm." + k] for k in ("weight", "bias", "running_mean", "running_var")}
+        sc = bn["weight"] * torch.rsqrt(bn["running_var"] + 1e-5)
+        y = (y * sc.view(1, -1, 1, 1) + (bn["bias"] - bn["running_mean"] * sc).view(1, -1, 1, 1)).clamp_min(0)
+        ok &= report("stem s2d %dx%dx%d (valid %dx%d)" % (n, h, w, vh, vw), out, y.permute(0, 2, 3, 1))
+    return ok
+
+
 def case_fwd_f32():
     ok = run_fwd("f32 fwd 3x3 64->128 1x20x24", 1, 20, 24, 64, 128, 3, dtype="f32")
     ok &= run_fwd("f32 fwd 3x3 epilogue", 1, 16, 32, 48, 40, 3, dtype="f32", scale=True, res=1, relu=True, mask=True)
@@ -348,7 +390,7 @@ def case_perf():
 CASES = [
     "optim", "fwd_f32", "bwd_f32",
     "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "fwd_epilogue2",
-    "stride2_view", "fc",
+    "stride2_view", "fc", "stem",
     "bwd_1x1", "bwd_1x1_big", "bwd_3x3", "bwd_3x3_big", "perf",
 ]
 
