@@ -25,6 +25,7 @@
 #include "sm100.cuh"
 #include "tmap.h"
 #include "../../include/aldi_b200.h"
+#include <stdlib.h>
 
 using namespace sm100;
 
@@ -37,6 +38,7 @@ constexpr int kNumThreads = 224;
 constexpr int kEpiChunk = 64;                    // channels per epilogue chunk (128-byte rows)
 constexpr int kEpiBytes = kBlockM * kEpiChunk * 2;  // 16 KB
 constexpr int kMaxStages = 8;
+constexpr int kMaxEpiBufs = 4;
 constexpr int kSmemLimit = 226 * 1024;     // dynamic budget (static barriers etc. live in the remaining 1 KB)
 
 struct ConvArgs {
@@ -60,6 +62,7 @@ struct ConvArgs {
   int stages;        // A/B pipeline depth (runtime: the epilogue buffers share the 227 KB)
   int tma_epi;       // bf16 output through shared memory + TMA store
   int epi_res, epi_mask;  // residual / mask tiles arrive by TMA (tma_epi only)
+  int epi_bufs;      // depth of the residual / mask tile ring (2..4): bytes in flight for the HBM-bound layers
 };
 
 template <int BLOCK_N>
@@ -102,14 +105,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // [stages x (A | B)] [out x2] [res x2] [mask x2]   (all 16 KB pieces, 1024-byte aligned)
   uint8_t* s_out = smem + a.stages * C::kStageBytes;
   uint8_t* s_res = s_out + 2 * kEpiBytes;
-  uint8_t* s_mask = s_res + (a.epi_res ? 2 * kEpiBytes : 0);
+  uint8_t* s_mask = s_res + (a.epi_res ? a.epi_bufs * kEpiBytes : 0);
 
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ __align__(8) uint64_t epi_full_bar[2];
-  __shared__ __align__(8) uint64_t epi_empty_bar[2];
+  __shared__ __align__(8) uint64_t epi_full_bar[kMaxEpiBufs];
+  __shared__ __align__(8) uint64_t epi_empty_bar[kMaxEpiBufs];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -129,6 +132,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < kMaxEpiBufs; ++i) {
       mbar_init(&epi_full_bar[i], 1);
       mbar_init(&epi_empty_bar[i], 4);
     }
@@ -223,7 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(s_res + buf * kEpiBytes, &tmR, &epi_full_bar[buf], cbase, w0, h0, img);
           }
           if (a.epi_mask) tma_load_4d(s_mask + buf * kEpiBytes, &tmM, &epi_full_bar[buf], cbase, w0, h0, img);
-          if (++buf == 2) { buf = 0; phase ^= 1; }
+          if (++buf == a.epi_bufs) { buf = 0; phase ^= 1; }
         }
       }
     }
@@ -321,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (epi_loads) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&epi_empty_bar[ebuf]);
-            if (++ebuf == 2) { ebuf = 0; ephase ^= 1; }
+            if (++ebuf == a.epi_bufs) { ebuf = 0; ephase ^= 1; }
           }
           // the store that last read s_out[obuf] (two chunks ago) must have finished reading it
           if (leader) bulk_wait_group_read<1>();
@@ -527,10 +532,21 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   const int res_mode = (tma_epi && p->accumulate) ? 1 : p->res_mode;
 
   int block_n = (p->cout_p % 256 == 0) ? 256 : (p->cout_p % 128 == 0) ? 128 : 64;
-  const int epi_bytes = tma_epi ? (2 + (epi_res ? 2 : 0) + (epi_mask ? 2 : 0)) * kEpiBytes : 0;
-  // keep at least 3 pipeline stages: narrow the N tile when the epilogue buffers crowd them out
-  while (block_n > 64 && (kSmemLimit - 1024 - epi_bytes) / (kABytes + block_n * kBlockK * 2) < 3) block_n >>= 1;
+  // shared-memory plan: [stages x (A | B)] [2 output chunks] [epi_bufs x (residual chunk, mask chunk)].
+  // Keep >= 3 pipeline stages (narrowing the N tile if needed), then deepen the residual/mask ring up to 4 —
+  // for the HBM-bound 1x1 layers the bytes in flight per SM are what sets the achieved bandwidth.
+  const int num_kb = p->taps_h * p->taps_w * (p->x_c / 64);
+  const int set_bytes = ((epi_res ? 1 : 0) + (epi_mask ? 1 : 0)) * kEpiBytes;
+  const int out_bytes = tma_epi ? 2 * kEpiBytes : 0;
+  while (block_n > 64 && (kSmemLimit - 1024 - out_bytes - 2 * set_bytes) / (kABytes + block_n * kBlockK * 2) < 3) block_n >>= 1;
   const int stage_bytes = kABytes + block_n * kBlockK * 2;
+  const int min_stages = num_kb >= 4 ? 4 : 3;
+  int epi_bufs = 2;
+  static const char* force_bufs2 = getenv("ALDI_EPI_BUFS2");
+  while (!force_bufs2 && set_bytes && epi_bufs < kMaxEpiBufs &&
+         (kSmemLimit - 1024 - out_bytes - (epi_bufs + 1) * set_bytes) / stage_bytes >= min_stages)
+    ++epi_bufs;
+  const int epi_bytes = out_bytes + (set_bytes ? epi_bufs * set_bytes : 0);
   int stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
@@ -564,6 +580,7 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   a.relu = p->relu; a.accumulate = p->accumulate;
   a.stages = stages;
   a.tma_epi = tma_epi; a.epi_res = epi_res; a.epi_mask = epi_mask;
+  a.epi_bufs = epi_bufs;
 
   CUtensorMap tm[5];
   int rc = make_cl_tmap(&tm[0], p->x, p->x_c, p->x_w, p->x_h, p->x_n, p->x_sw, p->x_sh, p->x_sn, tw, th);

@@ -7,18 +7,24 @@
 // conv zero padding are again TMA coordinates + OOB zero fill.  Split-K over pixel tiles, partial
 // results reduced with vector fp32 atomics straight into the flat gradient buffer.
 //
+// The kernel is bound by L2 -> shared-memory traffic (every (tap, cout tile) item re-streams x), so layers
+// with >= 256 output channels use a 256-row M tile: two 128 x BLOCK_N accumulators share each x stage, which
+// halves the number of times x crosses the L2 (TMEM then holds 2 x 256 columns, single-buffered: items are
+// thousands of pixels long, the un-overlapped epilogue is noise).
+//
 // Replaces cuDNN wgrad / cuBLAS (linear weight grad) under autograd of detectron2 layers
 // (reached from aldi/trainer.py:79 `trainer.do_backward`).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tmap.h"
 #include "../../include/aldi_b200.h"
+#include <stdlib.h>
 
 using namespace sm100;
 
 namespace {
 
-constexpr int kBlockM = 128;   // cout per tile
+constexpr int kBlockM = 128;   // cout rows per MMA (one or two of them per item)
 constexpr int kPix = 64;       // pixels (K) per stage
 constexpr int kBoxBytes = kPix * 128;  // 8 KB per 64-channel box
 constexpr int kNumThreads = 192;
@@ -32,13 +38,16 @@ struct WgradArgs {
   int cout_store, cin_store;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MH>
 struct WCfg {
   static constexpr int kNB = BLOCK_N / 64;
-  static constexpr int kStageBytes = (2 + kNB) * kBoxBytes;
+  static constexpr int kABoxes = 2 * MH;                      // 64-channel dy boxes per stage
+  static constexpr int kStageBytes = (kABoxes + kNB) * kBoxBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kAccBufs = (2 * MH * BLOCK_N <= 512) ? 2 : 1;
+  static constexpr int kColsUsed = kAccBufs * MH * BLOCK_N;
+  static constexpr int kTmemCols = (kColsUsed <= 128) ? 128 : (kColsUsed <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
 };
 
@@ -51,10 +60,10 @@ __device__ __forceinline__ void decode_item(const WgradArgs& a, int item, int& t
   ks = item / a.m_tiles;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MH>
 __global__ void __launch_bounds__(kNumThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const WgradArgs a) {
-  using C = WCfg<BLOCK_N>;
+  using C = WCfg<BLOCK_N, MH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -105,10 +114,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           const int h0 = thi * a.th, w0 = twi * a.tw;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + 2 * kBoxBytes;
+          uint8_t* sb = sa + C::kABoxes * kBoxBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_4d(sa, &tmY, &full_bar[stage], mt * kBlockM, w0, h0, img);
-          tma_load_4d(sa + kBoxBytes, &tmY, &full_bar[stage], mt * kBlockM + 64, w0, h0, img);
+#pragma unroll
+          for (int b = 0; b < C::kABoxes; ++b)
+            tma_load_4d(sa + b * kBoxBytes, &tmY, &full_bar[stage], mt * kBlockM * MH + b * 64, w0, h0, img);
 #pragma unroll
           for (int b = 0; b < C::kNB; ++b)
             tma_load_4d(sb + b * kBoxBytes, &tmX, &full_bar[stage], nt * BLOCK_N + b * 64, w0 + s - a.pad_w,
@@ -128,21 +138,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         decode_item(a, item, tap, nt, mt, ks);
         const int pt0 = (int)((long long)a.pix_tiles * ks / a.ksplit);
         const int pt1 = (int)((long long)a.pix_tiles * (ks + 1) / a.ksplit);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it % C::kAccBufs;
+        const uint32_t acc_phase = (it / C::kAccBufs) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * MH * BLOCK_N;
         for (int pt = pt0; pt < pt1; ++pt) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t adesc = make_smem_desc_sw128(sa, kBoxBytes, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + 2 * kBoxBytes, kBoxBytes, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + C::kABoxes * kBoxBytes, kBoxBytes, 1024);
 #pragma unroll
-          for (int k = 0; k < kPix / 16; ++k) {
-            // 16 pixels (K) = two 8-row swizzle atoms = 2048 B -> +128 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (pt > pt0) || (k != 0));
+          for (int half = 0; half < MH; ++half) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + half * 2 * kBoxBytes, kBoxBytes, 1024);
+#pragma unroll
+            for (int k = 0; k < kPix / 16; ++k) {
+              // 16 pixels (K) = two 8-row swizzle atoms = 2048 B -> +128 in the (addr>>4) field
+              umma_bf16(d_tmem + half * BLOCK_N, adesc + 128 * k, bdesc + 128 * k, idesc, (pt > pt0) || (k != 0));
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -158,19 +171,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
       int tap, nt, mt, ks;
       decode_item(a, item, tap, nt, mt, ks);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int cout = mt * kBlockM + row;
-      const bool valid = cout < a.cout_store;
-      const float sc = (valid && a.scale) ? __ldg(a.scale + cout) : 1.f;
-      float* drow = a.dw + ((long long)cout * a.taps + tap) * a.cin_store;
-
+      const int acc = it % C::kAccBufs;
+      const uint32_t acc_phase = (it / C::kAccBufs) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int hc = 0; hc < MH * (BLOCK_N / 32); ++hc) {
+        const int half = hc / (BLOCK_N / 32), c0 = (hc - half * (BLOCK_N / 32)) * 32;
+        const int cout = (mt * MH + half) * kBlockM + row;
+        const bool valid = cout < a.cout_store;
+        const float sc = (valid && a.scale) ? __ldg(a.scale + cout) : 1.f;
+        float* drow = a.dw + ((long long)cout * a.taps + tap) * a.cin_store;
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), raw);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MH + half) * BLOCK_N + c0), raw);
         tmem_ld_wait();
         const int cbase = nt * BLOCK_N + c0;
         if (valid && cbase < a.cin_store) {
@@ -201,12 +214,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MH>
 int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t stream) {
-  using C = WCfg<BLOCK_N>;
+  using C = WCfg<BLOCK_N, MH>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) {
       aldi_set_error("aldi_wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -215,7 +228,7 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, const WgradArgs
     attr_set = true;
   }
   int grid = a.num_items < aldi_num_sms() ? a.num_items : aldi_num_sms();
-  wgrad_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmY, tmX, a);
+  wgrad_tc_kernel<BLOCK_N, MH><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmY, tmX, a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_wgrad_tc");
   return ALDI_OK;
@@ -263,7 +276,13 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
   a.taps = p->taps_h * p->taps_w;
   a.taps_w = p->taps_w;
   a.pad_h = p->pad_h; a.pad_w = p->pad_w;
-  a.m_tiles = aldi_div_up(p->cout_store, kBlockM);
+  // 256-row M tile when cout allows and the items are long enough (split-K atomics dominate short ones)
+  const int pix_tiles0 = p->n * aldi_div_up(p->ho, th) * aldi_div_up(p->wo, tw);
+  static const char* force_mh1 = getenv("ALDI_WGRAD_MH1");
+  static const char* force_mh2 = getenv("ALDI_WGRAD_MH2");  // test knob: the 256-row tile at any size
+  const bool long_items = force_mh2 || ((p->taps_h * p->taps_w > 1) ? pix_tiles0 >= 1024 : pix_tiles0 >= 4096);
+  const int mh = (!force_mh1 && p->dy_c % 256 == 0 && p->cout_store > kBlockM && long_items) ? 2 : 1;
+  a.m_tiles = aldi_div_up(p->cout_store, kBlockM * mh);
   a.n_tiles = aldi_div_up(p->cin_store, block_n);
   int base_items = a.taps * a.m_tiles * a.n_tiles;
   // split K so that there are ~2 waves of work items but each keeps >= 8 pixel tiles
@@ -291,9 +310,16 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
     int rc = aldi_make_tmap_bf16(&tmX, p->x, 4, dims, strides, box);
     if (rc) return rc;
   }
+  if (mh == 2) {
+    switch (block_n) {
+      case 256: return launch_wgrad<256, 2>(tmY, tmX, a, stream);
+      case 128: return launch_wgrad<128, 2>(tmY, tmX, a, stream);
+      default: return launch_wgrad<64, 2>(tmY, tmX, a, stream);
+    }
+  }
   switch (block_n) {
-    case 256: return launch_wgrad<256>(tmY, tmX, a, stream);
-    case 128: return launch_wgrad<128>(tmY, tmX, a, stream);
-    default: return launch_wgrad<64>(tmY, tmX, a, stream);
+    case 256: return launch_wgrad<256, 1>(tmY, tmX, a, stream);
+    case 128: return launch_wgrad<128, 1>(tmY, tmX, a, stream);
+    default: return launch_wgrad<64, 1>(tmY, tmX, a, stream);
   }
 }

@@ -286,6 +286,17 @@ def case_bwd_3x3_big():
     return run_bwd("bwd 3x3 256->256 2x32x48", 2, 32, 48, 256, 256, 3)
 
 
+def case_bwd_mh2():
+    """wgrad with the 256-row M tile at every BLOCK_N (cin 64 / 128 / 256) and ragged pixel counts."""
+    os.environ["ALDI_WGRAD_MH2"] = "1"   # read once, at the first aldi_wgrad_tc call of this process
+    ok = run_bwd("bwd 1x1 64->256 2x24x40 (N=64, M=256)", 2, 24, 40, 64, 256, 1)
+    ok &= run_bwd("bwd 1x1 128->512 2x24x40 (N=128, M=256)", 2, 24, 40, 128, 512, 1)
+    ok &= run_bwd("bwd 3x3 128->256 1x20x28 (N=128, M=256)", 1, 20, 28, 128, 256, 3)
+    ok &= run_bwd("bwd 1x1 512->256 3x17x23 (N=256, M=256)", 3, 17, 23, 512, 256, 1)
+    ok &= run_bwd("bwd 1x1 256->1024 2x64x64 (N=256, M=256, 4 M tiles)", 2, 64, 64, 256, 1024, 1)
+    return ok
+
+
 def case_bwd_f32():
     ok = run_bwd("f32 bwd 3x3 48->40 2x12x20", 2, 12, 20, 48, 40, 3, dtype="f32")
     ok &= run_bwd("f32 bwd 1x1 64->128 1x16x16", 1, 16, 16, 64, 128, 1, dtype="f32")
@@ -387,11 +398,39 @@ def case_perf():
     return ok
 
 
+def case_perf_mem():
+    """the HBM-bound ResNet layers at full size (for ncu): 1x1 expand + FrozenBN + residual + ReLU, and its dgrad."""
+    import torch
+    from aldi_b200 import ops
+    n, h, w, cin, cout = 4, 256, 512, 64, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    res = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+    sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+    bi = torch.randn(cout, device="cuda", generator=g)
+    out = torch.empty(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, kw in (("fwd 1x1 64->256 +bn+res1+relu", dict(scale=sc, bias=bi, residual=res, res_mode=1, relu=True)),
+                     ("fwd 1x1 64->256 plain", dict()),
+                     ("dgrad-like 1x1 64->256 mask", dict(mask=res))):
+        for _ in range(3):
+            ops.conv(x, wt, out, **kw)
+        e0.record()
+        for _ in range(10):
+            ops.conv(x, wt, out, **kw)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        nbytes = (x.numel() + out.numel() * (2 if kw else 1)) * 2
+        print("[perf_mem] %s: %.3f ms  %.0f GB/s" % (name, ms, nbytes / ms / 1e6), flush=True)
+    return True
+
+
 CASES = [
     "optim", "fwd_f32", "bwd_f32",
     "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "fwd_epilogue2",
     "stride2_view", "fc", "stem",
-    "bwd_1x1", "bwd_1x1_big", "bwd_3x3", "bwd_3x3_big", "perf",
+    "bwd_1x1", "bwd_1x1_big", "bwd_3x3", "bwd_3x3_big", "bwd_mh2", "perf",
 ]
 
 
