@@ -9,7 +9,10 @@
 // The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle = the canonical
 // K-major UMMA operand layout.  Warp roles (persistent CTA, one per SM):
 //   warp 0: TMA producer (A/B stages)      warp 1: TMEM alloc + tcgen05.mma issuer
-//   warps 2-5: epilogue                    warp 6: TMA producer of the epilogue operands
+//   warp 2: TMA producer of the epilogue operands (residual / mask tiles)       warp 3: idle
+//   warps 4-11: epilogue — two warps per TMEM lane quarter, each owning 32 of a chunk's 64 channels, so every
+//   scheduler has two epilogue warps to hide each other's latencies (with one, the HBM-bound layers were
+//   bound by the epilogue's dependent-issue latency, not by memory)
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // Epilogue (bf16 outputs): most ResNet layers here are HBM-bound (1x1 convs with a residual), so the
@@ -34,7 +37,9 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                      // bf16 elements = 128 B = swizzle span
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
-constexpr int kNumThreads = 224;
+constexpr int kNumThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kEpiChunk = 64;                    // channels per epilogue chunk (128-byte rows)
 constexpr int kEpiBytes = kBlockM * kEpiChunk * 2;  // 16 KB
 constexpr int kMaxStages = 8;
@@ -72,6 +77,16 @@ struct Cfg {
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
 };
+
+// (x0, x1) = (x0, x1) * (s0, s1) + (b0, b1) in one packed FFMA2 (sm_100 fma.rn.f32x2)
+__device__ __forceinline__ void ffma2(float& x0, float& x1, float s0, float s1, float b0, float b1) {
+  unsigned long long x, sc, bi;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(s0), "f"(s1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bi) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x) : "l"(sc), "l"(bi));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
 
 __device__ __forceinline__ uint32_t swz128(int row, int chunk16) {  // byte offset inside a 128B-swizzled tile
   return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4));
@@ -131,11 +146,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
     for (int i = 0; i < kMaxEpiBufs; ++i) {
       mbar_init(&epi_full_bar[i], 1);
-      mbar_init(&epi_empty_bar[i], 4);
+      mbar_init(&epi_empty_bar[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -201,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ===================== TMA producer of the epilogue operands (residual / mask tiles) =====================
     if (lane == 0 && epi_loads) {
       int buf = 0;
@@ -232,12 +247,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (4..11) =====================
+    const int q = warp & 3;              // TMEM lane quarter this warp may touch
+    const int colhalf = (warp - 4) >> 2;  // which 32 of a chunk's 64 channels
     const int row = q * 32 + lane;
     const int hl = row >> a.tw_shift, wl = row & (a.tw - 1);
-    const bool leader = (threadIdx.x == 64);
+    const bool leader = (threadIdx.x == 128);
     // residual row of this thread inside the TMA-loaded tile (res_mode 2: the (TH/2 x TW/2) coarse tile)
     const int rrow = (a.res_mode == 2) ? ((hl >> 1) * (a.tw >> 1) + (wl >> 1)) : row;
     int it = 0;
@@ -264,63 +280,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c0 = 0; c0 < BLOCK_N; c0 += kEpiChunk) {
           const int cbase = n_tile * BLOCK_N + c0;
           if (cbase >= a.cout_store) break;
-          uint32_t raw0[32], raw1[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
-          tmem_ld_32x32(taddr, raw0);
-          tmem_ld_32x32(taddr + 32, raw1);
+          const int cw = cbase + colhalf * 32;  // first channel of this warp's half
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0 + colhalf * 32), raw);
           tmem_ld_wait();
-          float v[64];
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw0[j]); v[32 + j] = __uint_as_float(raw1[j]); }
-          if (a.scale) {
-            const float4* sp = reinterpret_cast<const float4*>(a.scale + cbase);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (a.scale && a.bias) {  // FrozenBN: v = v * scale + shift, two channels per FFMA2
+            const float4* sp = reinterpret_cast<const float4*>(a.scale + cw);
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + cw);
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
-              const float4 t = __ldg(sp + g);
-              v[4 * g] *= t.x; v[4 * g + 1] *= t.y; v[4 * g + 2] *= t.z; v[4 * g + 3] *= t.w;
+            for (int g = 0; g < 8; ++g) {
+              const float4 s4 = __ldg(sp + g), b4 = __ldg(bp + g);
+              ffma2(v[4 * g], v[4 * g + 1], s4.x, s4.y, b4.x, b4.y);
+              ffma2(v[4 * g + 2], v[4 * g + 3], s4.z, s4.w, b4.z, b4.w);
             }
-          }
-          if (a.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(a.bias + cbase);
+          } else if (a.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + cw);
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
+            for (int g = 0; g < 8; ++g) {
               const float4 t = __ldg(bp + g);
               v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+            }
+          } else if (a.scale) {
+            const float4* sp = reinterpret_cast<const float4*>(a.scale + cw);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = __ldg(sp + g);
+              v[4 * g] *= t.x; v[4 * g + 1] *= t.y; v[4 * g + 2] *= t.z; v[4 * g + 3] *= t.w;
             }
           }
           if (epi_loads) mbar_wait(&epi_full_bar[ebuf], ephase);
           if (a.epi_res && !a.accumulate) {
             const uint8_t* rb = s_res + ebuf * kEpiBytes;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               float f[8];
-              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(rrow, g)), f);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(rrow, colhalf * 4 + g)), f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
             }
           }
-          if (a.relu) {
+          uint4 packed[4];
+          if (!a.accumulate) {
+            // ReLU and the ReLU-backward mask commute with the bf16 rounding: do them two channels at a time
+            __nv_bfloat162* pk = reinterpret_cast<__nv_bfloat162*>(packed);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (a.epi_mask) {
-            const uint8_t* mb = s_mask + ebuf * kEpiBytes;
+            for (int j = 0; j < 16; ++j) pk[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            if (a.relu) {
+              const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float f[8];
-              unpack_bf16x8(*reinterpret_cast<const uint4*>(mb + swz128(row, g)), f);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] = (f[j] > 0.f) ? v[g * 8 + j] : 0.f;
+              for (int j = 0; j < 16; ++j) pk[j] = __hmax2(pk[j], z);
             }
-          }
-          if (a.epi_res && a.accumulate) {  // out += v: the old output tile arrived as the "residual"
+            if (a.epi_mask) {
+              const uint8_t* mb = s_mask + ebuf * kEpiBytes;
+              const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+              uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 m4 = *reinterpret_cast<const uint4*>(mb + swz128(row, colhalf * 4 + g));
+                const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pw[g * 4 + j] &= __hgt2_mask(mh[j], z);
+              }
+            }
+          } else {
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (a.epi_mask) {
+              const uint8_t* mb = s_mask + ebuf * kEpiBytes;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+                unpack_bf16x8(*reinterpret_cast<const uint4*>(mb + swz128(row, colhalf * 4 + g)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] = (f[j] > 0.f) ? v[g * 8 + j] : 0.f;
+              }
+            }
+            // out += v: the old output tile arrived as the "residual"
             const uint8_t* rb = s_res + ebuf * kEpiBytes;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               float f[8];
-              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(row, g)), f);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(row, colhalf * 4 + g)), f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+              packed[g] = pack_bf16x8(v + g * 8);
             }
           }
           if (epi_loads) {
@@ -330,12 +378,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // the store that last read s_out[obuf] (two chunks ago) must have finished reading it
           if (leader) bulk_wait_group_read<1>();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
           uint8_t* ob = s_out + obuf * kEpiBytes;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(ob + swz128(row, g)) = pack_bf16x8(v + g * 8);
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(ob + swz128(row, colhalf * 4 + g)) = packed[g];
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
           if (leader) {
             tma_store_4d(&tmO, ob, cbase, w0, h0, img);
             bulk_commit_group();
@@ -353,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           res_off = (long long)img * a.res_sn + (long long)(h >> 1) * a.res_sh + (long long)(w >> 1) * a.res_sw;
         if (a.mask) mask_off = (long long)img * a.mask_sn + (long long)h * a.mask_sh + (long long)w * a.mask_sw;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = colhalf * 32; c0 < BLOCK_N; c0 += 64) {
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), raw);
           tmem_ld_wait();
