@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(1024)
 roi_sample_kernel(const float* __restrict__ prop_box, const int* __restrict__ prop_count, int prop_stride,
                   const float* __restrict__ gt_boxes, const int* __restrict__ gt_classes,
                   const int* __restrict__ gt_counts, int gmax, float iou_thr, int num_classes, int num_samples,
-                  float pos_fraction, uint32_t seed, const uint32_t* __restrict__ salts, int append_gt,
+                  float pos_fraction, const uint32_t* __restrict__ seed_ptr, const uint32_t* __restrict__ salts, int append_gt,
                   float* __restrict__ out_box, int* __restrict__ out_batch, int* __restrict__ out_class,
                   float* __restrict__ out_gtbox, int* __restrict__ out_src, int* __restrict__ out_count,
                   int* __restrict__ stats) {
@@ -244,6 +244,7 @@ roi_sample_kernel(const float* __restrict__ prop_box, const int* __restrict__ pr
   __shared__ int s_scan[40];
   __shared__ int s_cnt[2];
   const int img = blockIdx.x;
+  const uint32_t seed = *seed_ptr;
   const int np = min(prop_count[img], prop_stride);
   const int g = min(gt_counts[img], gmax);
   const int n = np + (append_gt ? g : 0);
@@ -465,7 +466,8 @@ extern "C" int aldi_nms_sorted(const float* cand_box, const float* cand_score, c
 // multi-block subsample_labels (select_mb.cu)
 size_t aldi_subsample_workspace_bytes(int n_images);
 int aldi_subsample_labels(signed char* labels, int n_images, int n, int num_samples, float pos_fraction,
-                          unsigned int seed, const unsigned int* salts, int* stats, void* workspace, cudaStream_t stream);
+                          const unsigned int* d_seed, const unsigned int* salts, int* stats, void* workspace,
+                          cudaStream_t stream);
 
 extern "C" size_t aldi_rpn_label_workspace_bytes(int n_images, int gmax) {
   return (((size_t)n_images * gmax * sizeof(int) + 255) & ~size_t(255)) + aldi_subsample_workspace_bytes(n_images) + 256;
@@ -473,11 +475,11 @@ extern "C" size_t aldi_rpn_label_workspace_bytes(int n_images, int gmax) {
 
 extern "C" int aldi_rpn_label_anchors(const aldi_rpn_levels* L, int n_images, const float* gt_boxes,
                                       const int* gt_counts, int gmax, float iou_lo, float iou_hi, int num_samples,
-                                      float pos_fraction, unsigned int seed, const unsigned int* salts,
+                                      float pos_fraction, const unsigned int* d_seed, const unsigned int* salts,
                                       void* workspace, size_t workspace_bytes, signed char* labels, int* matched,
                                       int* stats, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ALDI_CHECK_ARG(L && gt_boxes && gt_counts && salts && workspace && labels && matched,
+  ALDI_CHECK_ARG(L && gt_boxes && gt_counts && d_seed && salts && workspace && labels && matched,
                  "aldi_rpn_label_anchors: null pointer");
   ALDI_CHECK_ARG(gmax > 0 && gmax <= 2048, "aldi_rpn_label_anchors: gmax must be in (0, 2048]");
   ALDI_CHECK_ARG(workspace_bytes >= aldi_rpn_label_workspace_bytes(n_images, gmax),
@@ -499,22 +501,22 @@ extern "C" int aldi_rpn_label_anchors(const aldi_rpn_levels* L, int n_images, co
     ALDI_CUDA_LAUNCH_CHECK("aldi_rpn_label_anchors(match)");
   }
   if (num_samples > 0)
-    return aldi_subsample_labels(labels, n_images, total, num_samples, pos_fraction, seed, salts, stats, sub_ws, stream);
+    return aldi_subsample_labels(labels, n_images, total, num_samples, pos_fraction, d_seed, salts, stats, sub_ws, stream);
   return ALDI_OK;
 }
 
 extern "C" int aldi_roi_label_sample(const float* prop_box, const int* prop_count, int prop_stride, int n_images,
                                      const float* gt_boxes, const int* gt_classes, const int* gt_counts, int gmax,
                                      float iou_thresh, int num_classes, int num_samples, float pos_fraction,
-                                     unsigned int seed, const unsigned int* salts, int append_gt, float* out_box,
+                                     const unsigned int* d_seed, const unsigned int* salts, int append_gt, float* out_box,
                                      int* out_batch, int* out_class, float* out_gtbox, int* out_src, int* out_count,
                                      int* stats, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ALDI_CHECK_ARG(prop_box && prop_count && gt_boxes && gt_classes && gt_counts && salts && out_box && out_batch &&
+  ALDI_CHECK_ARG(prop_box && prop_count && gt_boxes && gt_classes && gt_counts && d_seed && salts && out_box && out_batch &&
                      out_class && out_gtbox && out_src && out_count, "aldi_roi_label_sample: null pointer");
   ALDI_CHECK_ARG(prop_stride + gmax <= 4096, "aldi_roi_label_sample: proposals + gt must be <= 4096 per image");
   roi_sample_kernel<<<n_images, 1024, 0, stream>>>(prop_box, prop_count, prop_stride, gt_boxes, gt_classes, gt_counts,
-                                                   gmax, iou_thresh, num_classes, num_samples, pos_fraction, seed,
+                                                   gmax, iou_thresh, num_classes, num_samples, pos_fraction, d_seed,
                                                    salts, append_gt, out_box, out_batch, out_class, out_gtbox,
                                                    out_src, out_count, stats);
   ALDI_COUNT_LAUNCH();

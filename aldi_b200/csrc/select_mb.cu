@@ -283,12 +283,13 @@ __device__ __forceinline__ uint32_t sub_key(uint32_t seed, uint32_t salt, int cl
 }
 
 __global__ void __launch_bounds__(kThreads)
-subsample_hist_kernel(const signed char* __restrict__ labels, int n, int pass, uint32_t seed,
+subsample_hist_kernel(const signed char* __restrict__ labels, int n, int pass, const uint32_t* __restrict__ seed_ptr,
                       const uint32_t* __restrict__ salts, int num_samples, float pos_fraction,
                       uint32_t* __restrict__ hist, SelState* __restrict__ states) {
   __shared__ uint32_t s_hist[2][4096];
   __shared__ int s_warp[33], s_res[3], s_flag;
   const int img = blockIdx.y;
+  const uint32_t seed = *seed_ptr;
   const signed char* lab = labels + (size_t)img * n;
   const uint32_t salt = salts[img];
   SelState* st = states + 2 * img;  // [pos, neg]
@@ -349,9 +350,10 @@ subsample_hist_kernel(const signed char* __restrict__ labels, int n, int pass, u
 // final labels: selected positives stay 1, selected negatives stay 0, everything else -1; ties that straddle the cut
 // are parked as -2 (pos) / -3 (neg) for subsample_tie_kernel
 __global__ void __launch_bounds__(kThreads)
-subsample_apply_kernel(signed char* __restrict__ labels, int n, uint32_t seed, const uint32_t* __restrict__ salts,
-                       const SelState* __restrict__ states, int* __restrict__ stats) {
+subsample_apply_kernel(signed char* __restrict__ labels, int n, const uint32_t* __restrict__ seed_ptr,
+                       const uint32_t* __restrict__ salts, const SelState* __restrict__ states, int* __restrict__ stats) {
   const int img = blockIdx.y;
+  const uint32_t seed = *seed_ptr;
   signed char* lab = labels + (size_t)img * n;
   const uint32_t salt = salts[img];
   const SelState s0 = states[2 * img], s1 = states[2 * img + 1];
@@ -451,7 +453,8 @@ size_t aldi_subsample_workspace_bytes(int n_images) {
 }
 
 int aldi_subsample_labels(signed char* labels, int n_images, int n, int num_samples, float pos_fraction,
-                          unsigned int seed, const unsigned int* salts, int* stats, void* workspace, cudaStream_t stream) {
+                          const unsigned int* d_seed, const unsigned int* salts, int* stats, void* workspace,
+                          cudaStream_t stream) {
   const size_t segs = (size_t)n_images * 2;
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
@@ -462,12 +465,12 @@ int aldi_subsample_labels(signed char* labels, int n_images, int n, int num_samp
   bx = bx < 1 ? 1 : bx > 64 ? 64 : bx;
   const dim3 grid(bx, n_images);
   for (int pass = 0; pass < 3; ++pass) {
-    subsample_hist_kernel<<<grid, kThreads, 0, stream>>>(labels, n, pass, seed, salts, num_samples, pos_fraction, hist,
+    subsample_hist_kernel<<<grid, kThreads, 0, stream>>>(labels, n, pass, d_seed, salts, num_samples, pos_fraction, hist,
                                                          states);
     ALDI_COUNT_LAUNCH();
     ALDI_CUDA_LAUNCH_CHECK("aldi_rpn_label_anchors(subsample hist)");
   }
-  subsample_apply_kernel<<<grid, kThreads, 0, stream>>>(labels, n, seed, salts, states, stats);
+  subsample_apply_kernel<<<grid, kThreads, 0, stream>>>(labels, n, d_seed, salts, states, stats);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_rpn_label_anchors(subsample apply)");
   subsample_tie_kernel<<<n_images, 32, 0, stream>>>(labels, n, states);

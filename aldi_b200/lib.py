@@ -107,8 +107,8 @@ SIGNATURES = {
     "aldi_nms_sorted": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_int, P, c_size_t, P, P, P, P, P, P]),
     "aldi_rpn_label_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aldi_rpn_label_anchors": (c_int, [ctypes.POINTER(RpnLevels), c_int, P, P, c_int, c_float, c_float, c_int, c_float,
-                                       c_uint, P, P, c_size_t, P, P, P, P]),
-    "aldi_roi_label_sample": (c_int, [P, P, c_int, c_int, P, P, P, c_int, c_float, c_int, c_int, c_float, c_uint, P,
+                                       P, P, P, c_size_t, P, P, P, P]),
+    "aldi_roi_label_sample": (c_int, [P, P, c_int, c_int, P, P, P, c_int, c_float, c_int, c_int, c_float, P, P,
                                       c_int, P, P, P, P, P, P, P, P]),
     "aldi_roi_inference_candidates": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, c_float, P, c_float, P, P, P, P,
                                               P, c_int, P]),

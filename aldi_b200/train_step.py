@@ -61,6 +61,7 @@ class StepConfig:
         self.test_nms_thresh = 0.5
         self.test_topk = 100
         self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": parity path
+        self.cuda_graph = False                  # replay each micro-batch as a captured CUDA graph (2nd use onwards)
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError("unknown StepConfig field %s" % k)
@@ -72,26 +73,87 @@ class StepConfig:
                     self.do_obj_dst, self.do_rpn_reg_dst, self.do_roih_reg_dst])
 
 
-class Batch:
-    """A micro-batch staged on the device: uint8 canvas, valid sizes, padded GT."""
+class MicroBatch:
+    """Persistent staging buffers of one micro-batch shape: uint8 canvas, valid sizes, padded GT, the sampling seed
+    and salts.  The buffers keep their addresses, so a CUDA graph captured over them can be replayed after `load`
+    has refreshed their contents; per load there are n image copies plus TWO small H2D copies (int metadata, boxes)
+    from pinned mirrors."""
 
-    def __init__(self, data, device, with_gt):
-        n = len(data)
+    SITES = 3  # sampling.SITE_RPN, SITE_ROI, SITE_RPN_DISTILL
+
+    def __init__(self, n, hp, wp, gmax, device):
+        self.n, self.hp, self.wp, self.gmax = n, hp, wp, gmax
+        self.images = torch.zeros(n, 3, hp, wp, dtype=torch.uint8, device=device)
+        ni = 1 + self.SITES * n + 2 * n + n + n * gmax
+        self.h_meta = torch.zeros(ni, dtype=torch.int32).pin_memory() if device.type == "cuda" else torch.zeros(ni, dtype=torch.int32)
+        self.h_boxes = torch.zeros(n, gmax, 4).pin_memory() if device.type == "cuda" else torch.zeros(n, gmax, 4)
+        self.meta = torch.zeros(ni, dtype=torch.int32, device=device)
+        self.boxes = torch.zeros(n, gmax, 4, device=device)
+        o = 1
+        self.seed = self.meta[0:1]
+        self.salts = self.meta[o:o + self.SITES * n].view(self.SITES, n); o += self.SITES * n
+        self.sizes = self.meta[o:o + 2 * n].view(n, 2); o += 2 * n
+        counts = self.meta[o:o + n]; o += n
+        classes = self.meta[o:o + n * gmax].view(n, gmax)
+        self.gt = GroundTruth(self.boxes, classes, counts, gmax)
+        self._full_canvas = True
+        self._copied = None
+
+    @staticmethod
+    def shape_key(data, with_gt):
         hs = [int(d["image"].shape[1]) for d in data]
         ws = [int(d["image"].shape[2]) for d in data]
         hp = (max(hs) + 31) // 32 * 32
         wp = (max(ws) + 31) // 32 * 32
-        same = all(h == hp and w == wp for h, w in zip(hs, ws))
-        # per-image async copies straight from the (pinned) host tensors into the device canvas
-        self.images = (torch.empty if same else torch.zeros)(n, 3, hp, wp, dtype=torch.uint8, device=device)
+        g = max([len(d["boxes"]) for d in data] + [1]) if with_gt else 1
+        gmax = max(128, (g + 31) // 32 * 32)
+        return len(data), hp, wp, gmax
+
+    def load(self, data, seed, pass_id, with_gt):
+        """Stage one micro-batch; returns the host->device bytes moved."""
+        n, gmax = self.n, self.gmax
+        if self._copied is not None:
+            self._copied.synchronize()   # the pinned mirrors are free again once the previous load's copies ran
+        hs = [int(d["image"].shape[1]) for d in data]
+        ws = [int(d["image"].shape[2]) for d in data]
+        same = all(h == self.hp and w == self.wp for h, w in zip(hs, ws))
+        if not (same and self._full_canvas):
+            self.images.zero_()
+        self._full_canvas = same
+        nbytes = 0
         for i, d in enumerate(data):
             self.images[i, :, :hs[i], :ws[i]].copy_(d["image"], non_blocking=True)
-        self.h2d_bytes = sum(d["image"].numel() for d in data if not d["image"].is_cuda)
-        self.n, self.hp, self.wp = n, hp, wp
-        self.sizes = torch.tensor([[h, w] for h, w in zip(hs, ws)], dtype=torch.int32).to(device, non_blocking=True)
-        self.gt = None
+            if not d["image"].is_cuda:
+                nbytes += d["image"].numel()
+        m = self.h_meta
+        m.zero_()
+        m[0] = seed - (1 << 32) if seed >= (1 << 31) else seed
+        o = 1
+        for site in range(self.SITES):
+            for i in range(n):
+                v = sampling.make_salt(pass_id, site, i)
+                m[o + site * n + i] = v - (1 << 32) if v >= (1 << 31) else v
+        o += self.SITES * n
+        for i in range(n):
+            m[o + 2 * i], m[o + 2 * i + 1] = hs[i], ws[i]
+        o += 2 * n
         if with_gt:
-            self.gt = GroundTruth.from_host([d["boxes"] for d in data], [d["classes"] for d in data], device)
+            self.h_boxes.zero_()
+            for i, d in enumerate(data):
+                k = len(d["boxes"])
+                assert k <= gmax
+                m[o + i] = k
+                if k:
+                    self.h_boxes[i, :k] = d["boxes"].float()
+                    m[o + n + i * gmax:o + n + i * gmax + k] = d["classes"].to(torch.int32)
+            self.boxes.copy_(self.h_boxes, non_blocking=True)
+            nbytes += self.h_boxes.numel() * 4
+        self.meta.copy_(m, non_blocking=True)
+        nbytes += m.numel() * 4
+        if self.images.is_cuda:
+            self._copied = torch.cuda.Event()
+            self._copied.record()
+        return nbytes
 
 
 class GroundTruth:
@@ -140,6 +202,11 @@ class B200TrainStep:
         self.pg = process_group
         self.reducer = GradReducer(self.layout, self.grad, process_group)
         self._last_backward = False
+        self._mb_cache = {}        # (kind, n, hp, wp, gmax) -> MicroBatch staging buffers
+        self._graphs = {}          # key -> None (seen once, ran eagerly) | torch.cuda.CUDAGraph
+        self._graph_pool = None
+        self._graph_reduced = False
+        self.graph_replays = 0
         self.iter = 0
         self.h2d_bytes = 0
         self.last_pseudo = None
@@ -205,10 +272,44 @@ class B200TrainStep:
         return {k: float(vals[j]) for k, j in (out_keys or self._out_keys)}
 
     # ---- one source micro-batch: student forward + backward with hard losses --------------------------
+    def _stage(self, kind, data, pass_id, with_gt):
+        key = (kind,) + MicroBatch.shape_key(data, with_gt)
+        mb = self._mb_cache.get(key)
+        if mb is None:
+            mb = self._mb_cache[key] = MicroBatch(*key[1:], self.device)
+        self.h2d_bytes += mb.load(data, self.seed, pass_id, with_gt)
+        return key, mb
+
+    def _run(self, key, fn):
+        """Run one micro-batch body: eagerly the first time a (shape, schedule) key is seen, from then on as a
+        captured CUDA graph (cfg.cuda_graph).  All inputs live in MicroBatch buffers with fixed addresses, the
+        sampling seed and salts included, so a replay sees the new step's data."""
+        if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override:
+            return fn()
+        g = self._graphs.get(key, False)
+        if g is False:
+            self._graphs[key] = None
+            return fn()
+        if g is None:
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                fn()
+                if self._last_backward and self.reducer.active:
+                    self.reducer.finish()   # join the bucket all-reduces inside the capture
+            self._graphs[key] = g
+        g.replay()
+        self.graph_replays += 1
+        if self._last_backward and self.reducer.active:
+            self._graph_reduced = True
+
     def _source_microbatch(self, data, gscale, pass_id):
+        key, b = self._stage("source", data, pass_id, with_gt=True)
+        self._run(key + (gscale, self._last_backward), lambda: self._source_body(b, gscale, pass_id))
+
+    def _source_body(self, b, gscale, pass_id):
         cfg, det, W = self.cfg, self.det, self.student
-        b = Batch(data, self.device, with_gt=True)
-        self.h2d_bytes += b.h2d_bytes
         fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=True)
         n = b.n
         d_rpn = torch.zeros(n, fw["lv"].total_locs, 64, device=self.device, dtype=self.dtype)
@@ -230,7 +331,7 @@ class B200TrainStep:
         rpn_out, rpn_ts = det.rpn_head(W, feats, lv, save=True)
         out = {"feats": feats, "saved": saved, "lv": lv, "rpn_out": rpn_out, "rpn_ts": rpn_ts}
         if want_rpn_labels:
-            out["labels"], out["matched"], out["rpn_stats"] = self._label_anchors(lv, n, gt, pass_id, sampling.SITE_RPN)
+            out["labels"], out["matched"], out["rpn_stats"] = self._label_anchors(lv, b, gt, sampling.SITE_RPN)
         props = det.proposals(rpn_out, lv, b.sizes, cfg.rpn_pre_topk[0], cfg.rpn_post_topk[0], cfg.rpn_nms_thresh,
                               self.err_flag)
         out["props"] = props
@@ -242,21 +343,16 @@ class B200TrainStep:
         roi_src = torch.empty(m, dtype=torch.int32, device=self.device)
         roi_count = torch.zeros(n, dtype=torch.int32, device=self.device)
         roi_stats = torch.zeros(n, 2, dtype=torch.int32, device=self.device)
-        salts = self._salts(n, pass_id, sampling.SITE_ROI)
         ops.call("aldi_roi_label_sample", props["boxes"], props["count"], props["boxes"].shape[1], n, gt.boxes,
                  gt.classes, gt.counts, gt.gmax, cfg.roi_iou, cfg.num_classes, cfg.roi_batch, cfg.roi_pos_fraction,
-                 self.seed, salts, 1, rois, roi_batch, roi_class, roi_gt, roi_src, roi_count, roi_stats)
+                 b.seed, b.salts[sampling.SITE_ROI], 1, rois, roi_batch, roi_class, roi_gt, roi_src, roi_count, roi_stats)
         pred, head_saved = det.box_head(W, feats, rois, roi_batch, save=True)
         out.update(rois=rois, roi_gt=roi_gt, roi_batch=roi_batch, roi_class=roi_class, roi_src=roi_src,
                    roi_count=roi_count, roi_stats=roi_stats, pred=pred, head_saved=head_saved)
         return out
 
-    def _salts(self, n, pass_id, site):
-        return torch.tensor([sampling.make_salt(pass_id, site, i) for i in range(n)],
-                            dtype=torch.int32).to(self.device)
-
-    def _label_anchors(self, lv, n, gt, pass_id, site):
-        cfg = self.cfg
+    def _label_anchors(self, lv, b, gt, site):
+        cfg, n = self.cfg, b.n
         total = lv.total_locs * lv.num_anchors
         labels = torch.empty(n, total, dtype=torch.int8, device=self.device)
         matched = torch.empty(n, total, dtype=torch.int32, device=self.device)
@@ -264,8 +360,7 @@ class B200TrainStep:
         wsb = int(_l.load().aldi_rpn_label_workspace_bytes(n, gt.gmax))
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
         ops.call("aldi_rpn_label_anchors", _l.ctypes.byref(lv), n, gt.boxes, gt.counts, gt.gmax, cfg.rpn_iou[0],
-                 cfg.rpn_iou[1], cfg.rpn_batch, cfg.rpn_pos_fraction, self.seed, self._salts(n, pass_id, site), ws, wsb,
-                 labels, matched, stats)
+                 cfg.rpn_iou[1], cfg.rpn_batch, cfg.rpn_pos_fraction, b.seed, b.salts[site], ws, wsb, labels, matched, stats)
         return labels, matched, stats
 
     # ---- teacher: trunk + RPN once, eval-mode detections -> pseudo labels --------------------------------
@@ -299,10 +394,12 @@ class B200TrainStep:
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
     def _distill_microbatch(self, weak, strong, gscale, pass_id):
+        kw, bw = self._stage("weak", weak, pass_id, with_gt=False)
+        ks, bs = self._stage("strong", strong, pass_id, with_gt=False)
+        self._run(kw + ks + (gscale, self._last_backward), lambda: self._distill_body(bw, bs, gscale, pass_id))
+
+    def _distill_body(self, bw, bs, gscale, pass_id):
         cfg, det = self.cfg, self.det
-        bw = Batch(weak, self.device, with_gt=False)
-        bs = Batch(strong, self.device, with_gt=False)
-        self.h2d_bytes += bw.h2d_bytes + bs.h2d_bytes
         n = bw.n
         t_feats, t_lv, t_rpn_out = self.teacher_forward(bw)
         pseudo, _ = self.pseudo_label(bw, t_feats, t_lv, t_rpn_out)
@@ -316,7 +413,7 @@ class B200TrainStep:
         # teacher RoI head on the student's sampled proposals (ReplaceProposalsOnce + shared seed)
         t_pred, _ = det.box_head(self.teacher, t_feats, fw["rois"], fw["roi_batch"], save=False)
         # fresh anchor sampling by the TEACHER's RPN on the pseudo labels (T2)
-        labels, _, stats = self._label_anchors(t_lv, n, pseudo, pass_id, sampling.SITE_RPN_DISTILL)
+        labels, _, stats = self._label_anchors(t_lv, bs, pseudo, sampling.SITE_RPN_DISTILL)
         lv = fw["lv"]
         d_rpn = torch.zeros(n, lv.total_locs, 64, device=self.device, dtype=self.dtype)
         acc = 0
@@ -362,6 +459,9 @@ class B200TrainStep:
     def allreduce_grads(self):
         """One sum-all-reduce of the flat gradient buffer per step, started bucket by bucket during the last
         backward (data_parallel.GradReducer); DDP in the reference averages inside every micro-batch backward."""
+        if self._graph_reduced:          # the captured last backward already reduced and joined every bucket
+            self._graph_reduced = False
+            return 1.0 / self.reducer.world
         return self.reducer.finish()
 
     def optimizer_step(self, lr=None):

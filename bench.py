@@ -209,7 +209,8 @@ def run_ours(args):
 
     # SOLVER.BASE_LR: the reference's 0.06 makes the synthetic random-init detector diverge within ~10 steps (box-head
     # losses overflow -> the step's Inf/NaN check fires); the benchmark runs the identical optimizer work at 1/100 of it
-    cfg = StepConfig(dtype="bf16", ims_per_gpu=IMS_PER_GPU, base_lr=BENCH_BASE_LR if args.base_lr is None else args.base_lr)
+    cfg = StepConfig(dtype="bf16", ims_per_gpu=IMS_PER_GPU, base_lr=BENCH_BASE_LR if args.base_lr is None else args.base_lr,
+                     cuda_graph=not args.no_graph)
     step = B200TrainStep(cfg, arch.synthetic_state_dict(0), device=device, process_group=pg)
     step.debug = None
     host = make_data(1234 + rank, pinned=True)
@@ -276,10 +277,16 @@ def run_ours(args):
     d2h = step.loss_acc.numel() * 4 + 4
 
     # per-launch device timing of the dominant kernel family (tcgen05 implicit-GEMM conv fwd/dgrad)
+    # (eager issue for this one step: a graph replay bypasses the host-side launch hooks; the kernels are the same)
     prof = ops.KernelProfiler()
     ops.set_profiler(prof)
+    graph_mode, step.cfg.cuda_graph = step.cfg.cuda_graph, False
+    torch.cuda.synchronize()
+    lib.reset_launch_count()
     one_step(dev, False)
     torch.cuda.synchronize()
+    launches_per_step = lib.launch_count()
+    step.cfg.cuda_graph = graph_mode
     ops.set_profiler(None)
     summ = prof.summary()
     if args.profile_out and rank == 0:
@@ -327,8 +334,10 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "parallelism": "dp%d" % world,
                            "global_batch": imgs_per_step,
                            "l2": "inputs larger than L2: 75 MB of uint8 views + >4 GB of activations per micro-batch vs 126 MB L2",
-                           "algorithmic_tflop_per_step_per_gpu": 24.0, "base_lr": cfg.base_lr},
-                "clocks": clocks, "gpu_launches": int(launches // args.steps), "host_issue_ms_per_step": host_ms,
+                           "algorithmic_tflop_per_step_per_gpu": 24.0, "base_lr": cfg.base_lr,
+                           "cuda_graph": bool(cfg.cuda_graph), "graph_replays": step.graph_replays,
+                           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)},
+                "clocks": clocks, "gpu_launches": int(launches_per_step), "host_issue_ms_per_step": host_ms,
                 "host_floor_ms_per_step": host_floor_ms,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
@@ -345,6 +354,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--profile-out", default="", help="write the per-layer-shape kernel table (markdown) here")
     ap.add_argument("--trace-losses", type=int, default=0, help="debug: run this many steps printing the loss dict, then exit")
     ap.add_argument("--base-lr", type=float, default=None, help="override SOLVER.BASE_LR (default: the reference's 0.06)")

@@ -200,17 +200,19 @@ int aldi_nms_sorted(const float* cand_box, const float* cand_score, const int* c
                     const unsigned char* cand_valid, const int* cand_count, int n_images, int cand_stride,
                     float iou_thresh, int post_topk, void* workspace, size_t workspace_bytes, float* out_box,
                     float* out_score, int* out_cat, int* out_src, int* out_count, void* stream);
+/* Sampling seed: `d_seed` is a DEVICE pointer to one uint32 (the value aldi/helpers.py:17-26 ManualSeed would
+ * feed torch.manual_seed) so that a captured CUDA graph of the step can be replayed with a new seed.       */
 /* RPN.label_and_sample_anchors: Matcher([lo,hi],[0,-1,1], low-quality) + subsample_labels; labels (N,R) int8 */
 size_t aldi_rpn_label_workspace_bytes(int n_images, int gmax);
 int aldi_rpn_label_anchors(const aldi_rpn_levels* levels, int n_images, const float* gt_boxes, const int* gt_counts,
                            int gmax, float iou_lo, float iou_hi, int num_samples, float pos_fraction,
-                           unsigned int seed, const unsigned int* salts, void* workspace, size_t workspace_bytes,
+                           const unsigned int* d_seed, const unsigned int* salts, void* workspace, size_t workspace_bytes,
                            signed char* labels, int* matched, int* stats, void* stream);
 /* StandardROIHeads.label_and_sample_proposals: append GT, Matcher([thr],[0,1]), subsample; (N*num_samples) rows */
 int aldi_roi_label_sample(const float* prop_box, const int* prop_count, int prop_stride, int n_images,
                           const float* gt_boxes, const int* gt_classes, const int* gt_counts, int gmax,
-                          float iou_thresh, int num_classes, int num_samples, float pos_fraction, unsigned int seed,
-                          const unsigned int* salts, int append_gt, float* out_box, int* out_batch, int* out_class,
+                          float iou_thresh, int num_classes, int num_samples, float pos_fraction,
+                          const unsigned int* d_seed, const unsigned int* salts, int append_gt, float* out_box, int* out_batch, int* out_class,
                           float* out_gtbox, int* out_src, int* out_count, int* stats, void* stream);
 /* FastRCNNOutputLayers.inference front half: softmax, per-class decode + clip, score filter */
 int aldi_roi_inference_candidates(const float* pred, int pred_stride, const float* prop_box, const int* prop_count,

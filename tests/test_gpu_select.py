@@ -64,7 +64,8 @@ def test_rpn_label_and_sample_exact(count):
     wsb = int(_l.load().aldi_rpn_label_workspace_bytes(n, gmax))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     salts = torch.tensor([sampling.make_salt(pass_id, sampling.SITE_RPN, i) for i in range(n)], dtype=torch.int32, device=dev)
-    ops.call("aldi_rpn_label_anchors", ctypes.byref(lv), n, gb.to(dev), cnt.to(dev), gmax, 0.3, 0.7, 256, 0.5, seed, salts,
+    seed_t = torch.tensor([seed], dtype=torch.int32, device=dev)   # device-resident seed (graph-replayable)
+    ops.call("aldi_rpn_label_anchors", ctypes.byref(lv), n, gb.to(dev), cnt.to(dev), gmax, 0.3, 0.7, 256, 0.5, seed_t, salts,
              ws, wsb, labels, matched, stats)
     torch.cuda.synchronize()
     for i in range(n):
@@ -108,7 +109,8 @@ def test_roi_label_sample_exact():
     rb = torch.empty(m, dtype=torch.int32, device=dev); rc = torch.empty(m, dtype=torch.int32, device=dev)
     rs = torch.empty(m, dtype=torch.int32, device=dev); rcount = torch.zeros(n, dtype=torch.int32, device=dev)
     salts = torch.tensor([sampling.make_salt(pass_id, sampling.SITE_ROI, i) for i in range(n)], dtype=torch.int32, device=dev)
-    ops.call("aldi_roi_label_sample", pb, pc, P, n, gb.to(dev), gc.to(dev), cnt.to(dev), gmax, 0.5, 8, S, 0.25, seed, salts, 1,
+    seed_t = torch.tensor([seed], dtype=torch.int32, device=dev)
+    ops.call("aldi_roi_label_sample", pb, pc, P, n, gb.to(dev), gc.to(dev), cnt.to(dev), gmax, 0.5, 8, S, 0.25, seed_t, salts, 1,
              rois, rb, rc, rgt, rs, rcount, None)
     torch.cuda.synchronize()
     for i in range(n):
