@@ -98,6 +98,12 @@ class MicroBatch:
         self.gt = GroundTruth(self.boxes, classes, counts, gmax)
         self._full_canvas = True
         self._copied = None
+        # recorded on the compute stream after the last consumer of these buffers (initially: after the zero-fills
+        # above, which a prefetch on the copy stream must not overtake)
+        self.free_event = None
+        if device.type == "cuda":
+            self.free_event = torch.cuda.Event()
+            self.free_event.record()
 
     @staticmethod
     def shape_key(data, with_gt):
@@ -206,6 +212,7 @@ class B200TrainStep:
         self._graphs = {}          # key -> None (seen once, ran eagerly) | torch.cuda.CUDAGraph
         self._graph_pool = None
         self._graph_reduced = False
+        self._h2d_stream = None
         self.graph_replays = 0
         self.iter = 0
         self.h2d_bytes = 0
@@ -239,29 +246,41 @@ class B200TrainStep:
         self.seed_log = {}
         self.pseudo_log = []
         out_keys = []
-        pass_id = 0
-        n_backward = sum(-(-len(d) // mb) for d in (labeled_weak, labeled_strong) if d is not None) + \
-            (-(-len(unlabeled_weak) // mb) if do_distill else 0)
+        # ---- plan the micro-batches (same order and seed draws as the reference loops), then run them with the
+        # NEXT micro-batch's host->device staging overlapped on a copy stream whenever it uses other buffers
+        plan = []
         for tag, d in (("source_weak", labeled_weak), ("source_strong", labeled_strong)):
             if d is None:
                 continue
             for i in range(0, len(d), mb):
-                self.seed_log[pass_id] = self.seed
-                self._last_backward = pass_id == n_backward - 1
-                self._source_microbatch(d[i:i + mb], gscale, pass_id)
-                pass_id += 1
+                plan.append({"kind": "source", "parts": [("source", d[i:i + mb], True)], "seed": self.seed})
             out_keys += [(k + "_" + tag, j) for j, k in enumerate(SRC_KEYS)]
         if do_distill:
             assert len(unlabeled_weak) == len(unlabeled_strong), "Teacher and student data must be the same length."
             for i in range(0, len(unlabeled_weak), mb):
-                self.seed = random.randint(0, 2 ** 32 - 1)  # seeder.reset_seed(), aldi/distill.py:150
-                self.seed_log[100 + pass_id] = self.seed
-                self._last_backward = pass_id == n_backward - 1
-                self._distill_microbatch(unlabeled_weak[i:i + mb], unlabeled_strong[i:i + mb], gscale, 100 + pass_id)
-                pass_id += 1
+                seed = random.randint(0, 2 ** 32 - 1)       # seeder.reset_seed(), aldi/distill.py:150
+                plan.append({"kind": "distill", "seed": seed,
+                             "parts": [("weak", unlabeled_weak[i:i + mb], False), ("strong", unlabeled_strong[i:i + mb], False)]})
             out_keys += [(k + "_distill", 4 + j) for j, k in enumerate(SRC_KEYS)]
             soft_on = (cfg.do_obj_dst, cfg.do_rpn_reg_dst, cfg.do_cls_dst, cfg.do_roih_reg_dst)
             out_keys += [(k + "_distill", 8 + j) for j, (k, on) in enumerate(zip(SOFT_KEYS, soft_on)) if on]
+        for i, item in enumerate(plan):
+            item["pass_id"] = i if item["kind"] == "source" else 100 + i
+            item["keys"] = [(kind,) + MicroBatch.shape_key(d, gt) for kind, d, gt in item["parts"]]
+            self.seed_log[item["pass_id"]] = item["seed"]
+        for i, item in enumerate(plan):
+            self.seed = item["seed"]
+            self._last_backward = i == len(plan) - 1
+            mbs = item.get("staged") or self._stage(item, None)
+            body = self._source_body if item["kind"] == "source" else self._distill_body
+            self._run(tuple(item["keys"]) + (gscale, self._last_backward), lambda: body(*mbs, gscale, item["pass_id"]))
+            if self.device.type == "cuda":
+                for m in mbs:
+                    m.free_event = torch.cuda.Event()
+                    m.free_event.record()
+                nxt = plan[i + 1] if i + 1 < len(plan) else None
+                if nxt is not None and not (set(nxt["keys"]) & set(item["keys"])):
+                    nxt["staged"] = self._stage(nxt, self._copy_stream())
         self._out_keys = out_keys
         return LossDict(self, out_keys)
 
@@ -272,13 +291,32 @@ class B200TrainStep:
         return {k: float(vals[j]) for k, j in (out_keys or self._out_keys)}
 
     # ---- one source micro-batch: student forward + backward with hard losses --------------------------
-    def _stage(self, kind, data, pass_id, with_gt):
-        key = (kind,) + MicroBatch.shape_key(data, with_gt)
-        mb = self._mb_cache.get(key)
-        if mb is None:
-            mb = self._mb_cache[key] = MicroBatch(*key[1:], self.device)
-        self.h2d_bytes += mb.load(data, self.seed, pass_id, with_gt)
-        return key, mb
+    def _copy_stream(self):
+        if self._h2d_stream is None:
+            self._h2d_stream = torch.cuda.Stream(device=self.device)
+        return self._h2d_stream
+
+    def _stage(self, item, stream):
+        """Stage the inputs of one planned micro-batch into their MicroBatch buffers; `stream` = the copy stream for a
+        prefetch (ordered after the buffers' last consumer, the compute stream then waits for the copies) or None
+        for plain in-order staging on the compute stream."""
+        out = []
+        for key, (kind, data, with_gt) in zip(item["keys"], item["parts"]):
+            mb = self._mb_cache.get(key)
+            if mb is None:
+                mb = self._mb_cache[key] = MicroBatch(*key[1:], self.device)
+            if stream is None:
+                self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt)
+            else:
+                with torch.cuda.stream(stream):
+                    if mb.free_event is not None:
+                        stream.wait_event(mb.free_event)
+                    self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt)
+                    ready = torch.cuda.Event()
+                    ready.record(stream)
+                torch.cuda.current_stream().wait_event(ready)
+            out.append(mb)
+        return out
 
     def _run(self, key, fn):
         """Run one micro-batch body: eagerly the first time a (shape, schedule) key is seen, from then on as a
@@ -303,10 +341,6 @@ class B200TrainStep:
         self.graph_replays += 1
         if self._last_backward and self.reducer.active:
             self._graph_reduced = True
-
-    def _source_microbatch(self, data, gscale, pass_id):
-        key, b = self._stage("source", data, pass_id, with_gt=True)
-        self._run(key + (gscale, self._last_backward), lambda: self._source_body(b, gscale, pass_id))
 
     def _source_body(self, b, gscale, pass_id):
         cfg, det, W = self.cfg, self.det, self.student
@@ -393,11 +427,6 @@ class B200TrainStep:
         return GroundTruth(gb, gc, cnt, gmax, gs), dets
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
-    def _distill_microbatch(self, weak, strong, gscale, pass_id):
-        kw, bw = self._stage("weak", weak, pass_id, with_gt=False)
-        ks, bs = self._stage("strong", strong, pass_id, with_gt=False)
-        self._run(kw + ks + (gscale, self._last_backward), lambda: self._distill_body(bw, bs, gscale, pass_id))
-
     def _distill_body(self, bw, bs, gscale, pass_id):
         cfg, det = self.cfg, self.det
         n = bw.n
