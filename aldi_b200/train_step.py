@@ -17,6 +17,7 @@ micro-batches accumulate into one flat buffer that is all-reduced once per step 
 per micro-batch backward; averaging is linear).
 """
 import math
+import os
 import random
 
 import torch
@@ -211,7 +212,7 @@ class B200TrainStep:
         self._mb_cache = {}        # (kind, n, hp, wp, gmax) -> MicroBatch staging buffers
         self._graphs = {}          # key -> None (seen once, ran eagerly) | torch.cuda.CUDAGraph
         self._graph_pool = None
-        self._graph_reduced = False
+        self._capture_hook = None
         self._h2d_stream = None
         self.graph_replays = 0
         self.iter = 0
@@ -319,28 +320,58 @@ class B200TrainStep:
         return out
 
     def _run(self, key, fn):
-        """Run one micro-batch body: eagerly the first time a (shape, schedule) key is seen, from then on as a
-        captured CUDA graph (cfg.cuda_graph).  All inputs live in MicroBatch buffers with fixed addresses, the
-        sampling seed and salts included, so a replay sees the new step's data."""
+        """Run one micro-batch body: eagerly the first time a (shape, schedule) key is seen, from then on as
+        captured CUDA graphs (cfg.cuda_graph).  All inputs live in MicroBatch buffers with fixed addresses, the
+        sampling seed and salts included, so a replay sees the new step's data.  The step's LAST backward under
+        data parallelism is captured as a CHAIN of graphs cut where a gradient bucket becomes final: the NCCL
+        all-reduce of that bucket is issued eagerly between two replays and overlaps the next segment."""
         if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override:
             return fn()
-        g = self._graphs.get(key, False)
-        if g is False:
+        chain = self._graphs.get(key, False)
+        if chain is False:
             self._graphs[key] = None
             return fn()
-        if g is None:
-            if self._graph_pool is None:
-                self._graph_pool = torch.cuda.graph_pool_handle()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self._graph_pool):
+        if chain is None:
+            chain = self._graphs[key] = self._capture(fn)
+        for seg in chain:
+            if isinstance(seg, str):
+                self.reducer.ready(seg)
+            else:
+                seg.replay()
+                self.graph_replays += 1
+
+    def _capture(self, fn):
+        import gc
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+            self._capture_stream = torch.cuda.Stream(device=self.device)
+        chain = []
+        # ALDI_GRAPH_SPLIT=1: cut the chain even on one GPU (test knob for the segmented capture)
+        split = self._last_backward and (self.reducer.active or os.environ.get("ALDI_GRAPH_SPLIT") == "1")
+        torch.cuda.synchronize()
+        gc.collect()
+        cs = self._capture_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            seg = torch.cuda.CUDAGraph()
+            seg.capture_begin(pool=self._graph_pool)
+            state = {"seg": seg}
+
+            def cut(tag):
+                state["seg"].capture_end()
+                chain.extend([state["seg"], tag])
+                state["seg"] = torch.cuda.CUDAGraph()
+                state["seg"].capture_begin(pool=self._graph_pool)
+
+            self._capture_hook = cut if split else None
+            try:
                 fn()
-                if self._last_backward and self.reducer.active:
-                    self.reducer.finish()   # join the bucket all-reduces inside the capture
-            self._graphs[key] = g
-        g.replay()
-        self.graph_replays += 1
-        if self._last_backward and self.reducer.active:
-            self._graph_reduced = True
+            finally:
+                self._capture_hook = None
+                state["seg"].capture_end()
+            chain.append(state["seg"])
+        torch.cuda.current_stream().wait_stream(cs)
+        return chain
 
     def _source_body(self, b, gscale, pass_id):
         cfg, det, W = self.cfg, self.det, self.student
@@ -483,14 +514,15 @@ class B200TrainStep:
 
     def _bucket_ready(self):
         """Gradient buckets become final only in the step's LAST backward; earlier micro-batches just accumulate."""
-        return self.reducer.ready if (self._last_backward and self.reducer.active) else None
+        if self._capture_hook is not None:
+            return self._capture_hook
+        if not (self._last_backward and self.reducer.active):
+            return None
+        return self.reducer.ready
 
     def allreduce_grads(self):
         """One sum-all-reduce of the flat gradient buffer per step, started bucket by bucket during the last
         backward (data_parallel.GradReducer); DDP in the reference averages inside every micro-batch backward."""
-        if self._graph_reduced:          # the captured last backward already reduced and joined every bucket
-            self._graph_reduced = False
-            return 1.0 / self.reducer.world
         return self.reducer.finish()
 
     def optimizer_step(self, lr=None):

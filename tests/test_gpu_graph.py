@@ -27,12 +27,17 @@ def _steps(cuda_graph, n_steps, dtype):
     return step, out
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_graph_replay_matches_eager(dtype):
+@pytest.mark.parametrize("dtype,split", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_graph_replay_matches_eager(dtype, split, monkeypatch):
+    """split: the last backward captured as a chain of graphs cut at the gradient-bucket boundaries (what a
+    data-parallel run does so that each bucket's all-reduce can start between two replays)."""
+    if split:
+        monkeypatch.setenv("ALDI_GRAPH_SPLIT", "1")
     eager_step, eager = _steps(False, 4, dtype)
     graph_step, graph = _steps(True, 4, dtype)
     assert eager_step.graph_replays == 0
-    assert graph_step.graph_replays == 2 * 3      # (source, distill) x steps 2..4; step 1 runs eagerly
+    # (source, distill) x steps 2..4, step 1 runs eagerly; split: the distill backward is 6 segments
+    assert graph_step.graph_replays == (1 + 6 if split else 2) * 3
     for i, (a, b) in enumerate(zip(eager, graph)):
         assert set(a) == set(b)
         for k in a:
