@@ -342,6 +342,8 @@ class B200TrainStep:
 
     def _capture(self, fn):
         import gc
+        import warnings
+        warnings.filterwarnings("ignore", message="The CUDA Graph is empty")  # the tail after the last bucket cut
         if self._graph_pool is None:
             self._graph_pool = torch.cuda.graph_pool_handle()
             self._capture_stream = torch.cuda.Stream(device=self.device)
