@@ -10,9 +10,11 @@
 // K-major UMMA operand layout.  Warp roles (persistent CTA, one per SM):
 //   warp 0: TMA producer (A/B stages)      warp 1: TMEM alloc + tcgen05.mma issuer
 //   warp 2: TMA producer of the epilogue operands (residual / mask tiles)       warp 3: idle
-//   warps 4-11: epilogue — two warps per TMEM lane quarter, each owning 32 of a chunk's 64 channels, so every
-//   scheduler has two epilogue warps to hide each other's latencies (with one, the HBM-bound layers were
-//   bound by the epilogue's dependent-issue latency, not by memory)
+//   warps 4-11: epilogue — two warps per TMEM lane quarter (= per scheduler).  They take ALTERNATE 64-channel
+//   chunks and never synchronise with each other: each warp reads its 32 pixel rows from TMEM (tcgen05.ld is
+//   ~64 B/clk/SM plus a ~100-cycle wait::ld, the real floor of the K-small layers), stages a 32 x 64 bf16 slab
+//   in its own 4 KB of swizzled shared memory and stores it with its own TMA store, while its sibling on the
+//   same scheduler covers the latencies with the neighbouring chunk
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // Epilogue (bf16 outputs): most ResNet layers here are HBM-bound (1x1 convs with a residual), so the
@@ -39,7 +41,7 @@ constexpr int kBlockK = 64;                      // bf16 elements = 128 B = swiz
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
+
 constexpr int kEpiChunk = 64;                    // channels per epilogue chunk (128-byte rows)
 constexpr int kEpiBytes = kBlockM * kEpiChunk * 2;  // 16 KB
 constexpr int kMaxStages = 8;
@@ -68,6 +70,7 @@ struct ConvArgs {
   int tma_epi;       // bf16 output through shared memory + TMA store
   int epi_res, epi_mask;  // residual / mask tiles arrive by TMA (tma_epi only)
   int epi_bufs;      // depth of the residual / mask tile ring (2..4): bytes in flight for the HBM-bound layers
+  int debug;         // ALDI_CONV_DEBUG (perf bisection only): 1 no TMA store, 2 also no smem staging, 3 empty epilogue
 };
 
 template <int BLOCK_N>
@@ -146,11 +149,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+      // one arrive per epilogue warp that reads the tile (N = 64 TMA path: one chunk per tile -> one warp per quarter)
+      mbar_init(&tmem_empty_bar[i], (a.tma_epi && BLOCK_N == 64) ? 4 : kEpiWarps);
     }
     for (int i = 0; i < kMaxEpiBufs; ++i) {
       mbar_init(&epi_full_bar[i], 1);
-      mbar_init(&epi_empty_bar[i], kEpiWarps);
+      mbar_init(&epi_empty_bar[i], 4);  // a chunk is consumed by one warp per lane quarter
     }
     fence_barrier_init();
   }
@@ -233,7 +237,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h0 = thi * a.th, w0 = twi * a.tw;
         for (int c0 = 0; c0 < BLOCK_N; c0 += kEpiChunk) {
           const int cbase = n_tile * BLOCK_N + c0;
-          if (cbase >= a.cout_store) break;
           mbar_wait(&epi_empty_bar[buf], phase ^ 1);
           mbar_expect_tx(&epi_full_bar[buf], bytes);
           if (a.epi_res) {
@@ -249,16 +252,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps (4..11) =====================
-    const int q = warp & 3;              // TMEM lane quarter this warp may touch
-    const int colhalf = (warp - 4) >> 2;  // which 32 of a chunk's 64 channels
+    const int q = warp & 3;              // TMEM lane quarter this warp may touch (== its scheduler)
+    const int par = (warp - 4) >> 2;     // which of the quarter's two warps: takes chunks with (global index & 1) == par
+    const int colhalf = par;             // fp32 direct path: alternate 32-column groups
     const int row = q * 32 + lane;
     const int hl = row >> a.tw_shift, wl = row & (a.tw - 1);
-    const bool leader = (threadIdx.x == 128);
     // residual row of this thread inside the TMA-loaded tile (res_mode 2: the (TH/2 x TW/2) coarse tile)
     const int rrow = (a.res_mode == 2) ? ((hl >> 1) * (a.tw >> 1) + (wl >> 1)) : row;
+    // this warp's 32-row slab inside the tile and its private 4 KB staging buffer
+    const int slab_h = (q * 32) >> a.tw_shift, slab_w = (q * 32) & (a.tw - 1);
+    uint8_t* my_out = s_out + (warp - 4) * 4096;
+    constexpr int kChunks = BLOCK_N / kEpiChunk;
     int it = 0;
-    int ebuf = 0, obuf = 0;
-    uint32_t ephase = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -271,127 +276,151 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int h0 = thi * a.th, w0 = twi * a.tw;
       const int h = h0 + hl, w = w0 + wl;
 
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-
       if (a.tma_epi) {
-        // ---------- bf16 output: 64-channel chunks through swizzled shared memory, TMA in / TMA out ----------
+        // ---------- bf16 output: per-warp 32 x 64 slabs through swizzled shared memory, TMA in / TMA out ----------
+        bool waited = false;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += kEpiChunk) {
-          const int cbase = n_tile * BLOCK_N + c0;
-          if (cbase >= a.cout_store) break;
-          const int cw = cbase + colhalf * 32;  // first channel of this warp's half
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0 + colhalf * 32), raw);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (a.scale && a.bias) {  // FrozenBN: v = v * scale + shift, two channels per FFMA2
-            const float4* sp = reinterpret_cast<const float4*>(a.scale + cw);
-            const float4* bp = reinterpret_cast<const float4*>(a.bias + cw);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 s4 = __ldg(sp + g), b4 = __ldg(bp + g);
-              ffma2(v[4 * g], v[4 * g + 1], s4.x, s4.y, b4.x, b4.y);
-              ffma2(v[4 * g + 2], v[4 * g + 3], s4.z, s4.w, b4.z, b4.w);
-            }
-          } else if (a.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(a.bias + cw);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 t = __ldg(bp + g);
-              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-            }
-          } else if (a.scale) {
-            const float4* sp = reinterpret_cast<const float4*>(a.scale + cw);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 t = __ldg(sp + g);
-              v[4 * g] *= t.x; v[4 * g + 1] *= t.y; v[4 * g + 2] *= t.z; v[4 * g + 3] *= t.w;
-            }
+        for (int c = 0; c < kChunks; ++c) {
+          const int g = it * kChunks + c;  // global chunk index: residual/mask ring slot and warp assignment
+          if ((g & 1) != par) continue;
+          if (!waited) {
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            waited = true;
           }
-          if (epi_loads) mbar_wait(&epi_full_bar[ebuf], ephase);
-          if (a.epi_res && !a.accumulate) {
-            const uint8_t* rb = s_res + ebuf * kEpiBytes;
+          const int cbase = n_tile * BLOCK_N + c * kEpiChunk;
+          const int slot = g % a.epi_bufs;
+          const uint32_t ephase = (uint32_t)(g / a.epi_bufs) & 1u;
+          if (a.debug == 3) continue;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(rrow, colhalf * 4 + g)), f);
+          for (int half = 0; half < 2; ++half) {
+            const int cw = cbase + half * 32;  // first channel of this half
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * kEpiChunk + half * 32),
+                          raw);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
-            }
-          }
-          uint4 packed[4];
-          if (!a.accumulate) {
-            // ReLU and the ReLU-backward mask commute with the bf16 rounding: do them two channels at a time
-            __nv_bfloat162* pk = reinterpret_cast<__nv_bfloat162*>(packed);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            if (a.scale && a.bias) {  // FrozenBN: v = v * scale + shift, two channels per FFMA2
+              const float4* sp = reinterpret_cast<const float4*>(a.scale + cw);
+              const float4* bp = reinterpret_cast<const float4*>(a.bias + cw);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            if (a.relu) {
-              const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+              for (int gq = 0; gq < 8; ++gq) {
+                const float4 s4 = __ldg(sp + gq), b4 = __ldg(bp + gq);
+                ffma2(v[4 * gq], v[4 * gq + 1], s4.x, s4.y, b4.x, b4.y);
+                ffma2(v[4 * gq + 2], v[4 * gq + 3], s4.z, s4.w, b4.z, b4.w);
+              }
+            } else if (a.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(a.bias + cw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = __hmax2(pk[j], z);
-            }
-            if (a.epi_mask) {
-              const uint8_t* mb = s_mask + ebuf * kEpiBytes;
-              const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
-              uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+              for (int gq = 0; gq < 8; ++gq) {
+                const float4 t = __ldg(bp + gq);
+                v[4 * gq] += t.x; v[4 * gq + 1] += t.y; v[4 * gq + 2] += t.z; v[4 * gq + 3] += t.w;
+              }
+            } else if (a.scale) {
+              const float4* sp = reinterpret_cast<const float4*>(a.scale + cw);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 m4 = *reinterpret_cast<const uint4*>(mb + swz128(row, colhalf * 4 + g));
-                const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pw[g * 4 + j] &= __hgt2_mask(mh[j], z);
+              for (int gq = 0; gq < 8; ++gq) {
+                const float4 t = __ldg(sp + gq);
+                v[4 * gq] *= t.x; v[4 * gq + 1] *= t.y; v[4 * gq + 2] *= t.z; v[4 * gq + 3] *= t.w;
               }
             }
-          } else {
-            if (a.relu) {
+            if (half == 0 && epi_loads) mbar_wait(&epi_full_bar[slot], ephase);
+            if (a.epi_res && !a.accumulate) {
+              const uint8_t* rb = s_res + slot * kEpiBytes;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (a.epi_mask) {
-              const uint8_t* mb = s_mask + ebuf * kEpiBytes;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
+              for (int gq = 0; gq < 4; ++gq) {
                 float f[8];
-                unpack_bf16x8(*reinterpret_cast<const uint4*>(mb + swz128(row, colhalf * 4 + g)), f);
+                unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(rrow, half * 4 + gq)), f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[g * 8 + j] = (f[j] > 0.f) ? v[g * 8 + j] : 0.f;
+                for (int j = 0; j < 8; ++j) v[gq * 8 + j] += f[j];
               }
             }
-            // out += v: the old output tile arrived as the "residual"
-            const uint8_t* rb = s_res + ebuf * kEpiBytes;
+            uint4 packed[4];
+            if (!a.accumulate) {
+              // ReLU and the ReLU-backward mask commute with the bf16 rounding: do them two channels at a time
+              __nv_bfloat162* pk = reinterpret_cast<__nv_bfloat162*>(packed);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-              unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(row, colhalf * 4 + g)), f);
+              for (int j = 0; j < 16; ++j) pk[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              if (a.relu) {
+                const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
-              packed[g] = pack_bf16x8(v + g * 8);
+                for (int j = 0; j < 16; ++j) pk[j] = __hmax2(pk[j], z);
+              }
+              if (a.epi_mask) {
+                const uint8_t* mb = s_mask + slot * kEpiBytes;
+                const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+                uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                  const uint4 m4 = *reinterpret_cast<const uint4*>(mb + swz128(row, half * 4 + gq));
+                  const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m4);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) pw[gq * 4 + j] &= __hgt2_mask(mh[j], z);
+                }
+              }
+            } else {
+              if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (a.epi_mask) {
+                const uint8_t* mb = s_mask + slot * kEpiBytes;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                  float f[8];
+                  unpack_bf16x8(*reinterpret_cast<const uint4*>(mb + swz128(row, half * 4 + gq)), f);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[gq * 8 + j] = (f[j] > 0.f) ? v[gq * 8 + j] : 0.f;
+                }
+              }
+              // out += v: the old output tile arrived as the "residual"
+              const uint8_t* rb = s_res + slot * kEpiBytes;
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                float f[8];
+                unpack_bf16x8(*reinterpret_cast<const uint4*>(rb + swz128(row, half * 4 + gq)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[gq * 8 + j] += f[j];
+                packed[gq] = pack_bf16x8(v + gq * 8);
+              }
             }
+            if (a.debug == 2) {
+              if (packed[0].x == 0x12345678u && packed[3].w == 0x9abcdef0u) atomicAdd(reinterpret_cast<int*>(a.out), 1);
+              continue;
+            }
+            if (half == 0) {
+              // this warp's previous TMA store must have finished reading the slab buffer
+              if (lane == 0) bulk_wait_group_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq)
+              *reinterpret_cast<uint4*>(my_out + swz128(lane, half * 4 + gq)) = packed[gq];
           }
           if (epi_loads) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&epi_empty_bar[ebuf]);
-            if (++ebuf == a.epi_bufs) { ebuf = 0; ephase ^= 1; }
+            if (lane == 0) mbar_arrive(&epi_empty_bar[slot]);
           }
-          // the store that last read s_out[obuf] (two chunks ago) must have finished reading it
-          if (leader) bulk_wait_group_read<1>();
-          named_bar_sync(1, kEpiThreads);
-          uint8_t* ob = s_out + obuf * kEpiBytes;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(ob + swz128(row, colhalf * 4 + g)) = packed[g];
+          if (a.debug == 2) continue;
           fence_proxy_async();
-          named_bar_sync(1, kEpiThreads);
-          if (leader) {
-            tma_store_4d(&tmO, ob, cbase, w0, h0, img);
+          __syncwarp();
+          if (lane == 0 && a.debug != 1) {
+            tma_store_4d(&tmO, my_out, cbase, w0 + slab_w, h0 + slab_h, img);
             bulk_commit_group();
           }
-          obuf ^= 1;
         }
+        if (waited) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        continue;
       } else {
         // ---------- fp32 (or unaligned) output: direct per-thread row-segment stores ----------
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
         const bool valid = (h < a.ho) && (w < a.wo);
         const long long out_off = (long long)img * a.out_sn + (long long)h * a.out_sh + (long long)w * a.out_sw;
         long long res_off = 0, mask_off = 0;
@@ -488,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-    if (a.tma_epi && leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires
+    if (a.tma_epi && lane == 0) bulk_wait_group<0>();  // all output slabs written before the CTA retires
   }
 
   tc_fence_before();
@@ -574,7 +603,7 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
 
   // bf16 outputs whose channel extent is a whole number of 64-channel chunks leave through TMA; `accumulate`
   // becomes "residual = the output tile itself" (never combined with another residual by the callers)
-  const bool tma_epi = p->out_dtype == ALDI_DTYPE_BF16 && p->cout_store % 64 == 0 && !(p->accumulate && p->res_mode);
+  const bool tma_epi = p->out_dtype == ALDI_DTYPE_BF16 && p->cout_store == p->cout_p && !(p->accumulate && p->res_mode);
   const bool epi_res = tma_epi && (p->res_mode || p->accumulate);
   const bool epi_mask = tma_epi && p->mask;
   const int res_mode = (tma_epi && p->accumulate) ? 1 : p->res_mode;
@@ -629,6 +658,8 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   a.stages = stages;
   a.tma_epi = tma_epi; a.epi_res = epi_res; a.epi_mask = epi_mask;
   a.epi_bufs = epi_bufs;
+  static const char* dbg = getenv("ALDI_CONV_DEBUG");
+  a.debug = dbg ? atoi(dbg) : 0;
 
   CUtensorMap tm[5];
   int rc = make_cl_tmap(&tm[0], p->x, p->x_c, p->x_w, p->x_h, p->x_n, p->x_sw, p->x_sh, p->x_sn, tw, th);
@@ -643,7 +674,9 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   }
   tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];  // placeholders when unused
   if (tma_epi) {
-    rc = make_cl_tmap(&tm[2], p->out, p->cout_store, p->wo, p->ho, p->n, p->out_sw, p->out_sh, p->out_sn, tw, th);
+    // output leaves as per-warp 32-pixel slabs: box {64 ch, min(TW,32), 32 / min(TW,32), 1}
+    const int bw = tw < 32 ? tw : 32;
+    rc = make_cl_tmap(&tm[2], p->out, p->cout_store, p->wo, p->ho, p->n, p->out_sw, p->out_sh, p->out_sn, bw, 32 / bw);
     if (rc) return rc;
     if (epi_res) {
       if (p->accumulate)
