@@ -213,6 +213,7 @@ class B200TrainStep:
         self._graphs = {}          # key -> None (seen once, ran eagerly) | torch.cuda.CUDAGraph
         self._graph_pool = None
         self._capture_hook = None
+        self.profile_spin_cycles = 0
         self._h2d_stream = None
         self.graph_replays = 0
         self.iter = 0
@@ -326,6 +327,10 @@ class B200TrainStep:
         data parallelism is captured as a CHAIN of graphs cut where a gradient bucket becomes final: the NCCL
         all-reduce of that bucket is issued eagerly between two replays and overlaps the next segment."""
         if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override:
+            if self.profile_spin_cycles:
+                # profiling aid: park the GPU on a spin kernel while the host queues this micro-batch, so the kernels
+                # then run back to back (warm L2, no launch gaps) and per-launch CUDA events time exactly their durations
+                torch.cuda._sleep(int(self.profile_spin_cycles))
             return fn()
         chain = self._graphs.get(key, False)
         if chain is False:

@@ -116,7 +116,8 @@ def cpu_reference_step_factory(threads):
     student = aldi_ref.ALDI(num_classes=8)
     student.load_state_dict(sd)
     trainer = aldi_ref.OracleTrainer(student, distill_kwargs=dict(do_cls_dst=True, do_obj_dst=True, do_rpn_reg_dst=True,
-                                                                  do_roih_reg_dst=True), ims_per_gpu=1)
+                                                                  do_roih_reg_dst=True), ims_per_gpu=1,
+                                    lr=BENCH_BASE_LR * 0.01)   # same warm-up start LR as the GPU arm (see BENCH_BASE_LR)
     ls, uw, us = synth_data.synthetic_batch(1234, 1, 1, H, W, num_boxes=12)
 
     def conv(b, labeled):
@@ -262,6 +263,29 @@ def run_ours(args):
         return
     for _ in range(max(args.warmup, 3)):
         one_step(dev, False)
+    if args.kineto_out:
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as kprof:
+            for _ in range(3):
+                one_step(dev, False)
+            torch.cuda.synchronize()
+        evs = [e for e in kprof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        agg = {}
+        for e in evs:
+            d = agg.setdefault(e.name, [0, 0.0])
+            d[0] += 1
+            d[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+        t0 = min(e.time_range.start for e in evs)
+        t1 = max(e.time_range.end for e in evs)
+        busy = sum(v for _, v in agg.values())
+        with open(args.kineto_out, "w") as fh:
+            fh.write("# in-situ kernel times (torch.profiler / CUPTI), 3 steps, graph=%s\n\n" % (not args.no_graph))
+            fh.write("span %.3f ms/step, sum of kernel+memcpy durations %.3f ms/step\n\n" % ((t1 - t0) / 3e3, busy / 3e3))
+            fh.write("| kernel | launches/step | ms/step | share |\n|---|---:|---:|---:|\n")
+            for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+                fh.write("| `%s` | %.1f | %.3f | %.1f%% |\n" % (name[:90].replace("|", "/"), n / 3, us / 3e3, 100 * us / busy))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches = timed(dev, args.steps, False)
     host_ms = host_issue["ms_per_step"]
@@ -281,12 +305,14 @@ def run_ours(args):
     prof = ops.KernelProfiler()
     ops.set_profiler(prof)
     graph_mode, step.cfg.cuda_graph = step.cfg.cuda_graph, False
+    step.profile_spin_cycles = 60e6   # ~30 ms spin before each micro-batch: the host gets ahead, kernels run back to back
     torch.cuda.synchronize()
     lib.reset_launch_count()
     one_step(dev, False)
     torch.cuda.synchronize()
     launches_per_step = lib.launch_count()
     step.cfg.cuda_graph = graph_mode
+    step.profile_spin_cycles = 0
     ops.set_profiler(None)
     summ = prof.summary()
     if args.profile_out and rank == 0:
@@ -356,6 +382,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--profile-out", default="", help="write the per-layer-shape kernel table (markdown) here")
+    ap.add_argument("--kineto-out", default="", help="debug: profile 3 steps with torch.profiler (CUPTI) and write per-kernel "
+                    "in-situ device times here")
     ap.add_argument("--trace-losses", type=int, default=0, help="debug: run this many steps printing the loss dict, then exit")
     ap.add_argument("--base-lr", type=float, default=None, help="override SOLVER.BASE_LR (default: the reference's 0.06)")
     args = ap.parse_args()
