@@ -209,6 +209,10 @@ def step_config_from_cfg(cfg, dtype=None):
     if (cfg.SOLVER.OPTIMIZER or "SGD").upper() != "SGD":
         raise ValueError("Unsupported optimizer/backbone combination {} {}.".format(cfg.SOLVER.OPTIMIZER,
                                                                                      cfg.MODEL.BACKBONE.NAME))
+    if max(cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST) > 2048:
+        raise NotImplementedError("MODEL.RPN.PRE_NMS_TOPK_TRAIN/TEST up to 2048 per level are supported (the ALDI configs "
+                                  "use 2000 / 1000, configs/detectron2/Base-RCNN-FPN.yaml:14-15); got %d / %d"
+                                  % (cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST))
     return StepConfig(
         num_classes=cfg.MODEL.ROI_HEADS.NUM_CLASSES, ims_per_gpu=cfg.SOLVER.IMS_PER_GPU, ema_alpha=cfg.EMA.ALPHA,
         ema_start_iter=cfg.EMA.START_ITER, pseudo_threshold=cfg.DOMAIN_ADAPT.TEACHER.THRESHOLD,

@@ -626,6 +626,8 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   const int epi_bytes = out_bytes + (set_bytes ? epi_bufs * set_bytes : 0);
   int stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  static const char* force_stages = getenv("ALDI_CONV_STAGES");  // perf bisection only
+  if (force_stages && atoi(force_stages) >= 1 && atoi(force_stages) < stages) stages = atoi(force_stages);
   const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
 
   int th, tw;

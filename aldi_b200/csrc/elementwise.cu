@@ -247,25 +247,41 @@ __global__ void __launch_bounds__(256) add_f32_kernel(T* __restrict__ dst, const
 
 // ---- out[c] += scale * sum_rows x[row, c]   (bias gradients) ----------------------------------------
 // grid (chunks of rows, channel groups of 32); block 32 x 8: lanes over channels (coalesced), 8 row lanes.
+// out[ch] += scale * sum over (image, row) of x[img*img_stride + row*row_stride + ch]: 16-byte loads, one thread
+// per 16 bytes of a row, 256 / (threads per row) rows per pass, register accumulation, one shared-memory reduction
+// and one atomicAdd per channel per block.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, long long row_stride, long long rows, int c, float scale,
-              float* __restrict__ out) {
-  __shared__ float part[8][33];
-  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int ch = blockIdx.y * 32 + lane;
-  float s = 0.f;
-  if (ch < c) {
-    for (long long r = (long long)blockIdx.x * 8 + ry; r < rows; r += (long long)gridDim.x * 8)
-      s += to_f32<T>(x[r * row_stride + ch]);
-  }
-  part[ry][lane] = s;
-  __syncthreads();
-  if (ry == 0 && ch < c) {
-    float t = 0.f;
+colsum_kernel(const T* __restrict__ x, int n_img, long long rows, long long img_stride, long long row_stride, int c,
+              float scale, float* __restrict__ out) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float part[256][V + 1];
+  const int tpr = (c + V - 1) / V;            // threads per row
+  const int rpp = 256 / tpr;                  // rows per pass
+  const int rg = threadIdx.x / tpr, tc = threadIdx.x - rg * tpr;
+  float acc[V];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][lane];
-    atomicAdd(out + ch, t * scale);
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  if (rg < rpp) {
+    const long long total = (long long)n_img * rows;
+    for (long long r = (long long)blockIdx.x * rpp + rg; r < total; r += (long long)gridDim.x * rpp) {
+      const long long img = r / rows, rr = r - img * rows;
+      float f[V];
+      Vec16<T>::load(x + img * img_stride + rr * row_stride + (long long)tc * V, f);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += f[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) part[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (rg == 0 && tc < tpr) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = 0.f;
+      for (int g = 0; g < rpp; ++g) t += part[g * tpr + tc][k];
+      if (tc * V + k < c) atomicAdd(out + tc * V + k, t * scale);
+    }
   }
 }
 
@@ -366,20 +382,26 @@ extern "C" int aldi_add_f32(void* dst, int dtype, const float* src, size_t n, vo
   return ALDI_OK;
 }
 
-extern "C" int aldi_colsum(const void* x, int dtype, long long rows, long long row_stride, int c, float scale,
-                           float* out, void* stream_) {
+extern "C" int aldi_colsum(const void* x, int dtype, int n_img, long long rows, long long img_stride,
+                           long long row_stride, int c, float scale, float* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ALDI_CHECK_ARG(x && out && c > 0, "aldi_colsum: bad args");
+  ALDI_CHECK_ARG(x && out && c > 0 && n_img > 0, "aldi_colsum: bad args");
+  const int v = dtype == ALDI_DTYPE_BF16 ? 8 : 4;
+  ALDI_CHECK_ARG((c + v - 1) / v <= 256, "aldi_colsum: at most %d channels", 256 * v);
+  ALDI_CHECK_ARG(row_stride % v == 0 && img_stride % v == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                 "aldi_colsum: rows must be 16-byte aligned (and hold ceil(c/%d)*%d readable channels)", v, v);
   if (rows <= 0) return ALDI_OK;
-  long long gx = (rows + 8 * 64 - 1) / (8 * 64);
-  long long cap = (long long)aldi_num_sms() * 8;
+  const int rpp = 256 / ((c + v - 1) / v);
+  long long gx = ((long long)n_img * rows + (long long)rpp * 16 - 1) / ((long long)rpp * 16);
+  long long cap = (long long)aldi_num_sms() * 4;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)((c + 31) / 32));
   if (dtype == ALDI_DTYPE_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, row_stride, rows, c, scale, out);
+    colsum_kernel<__nv_bfloat16><<<(unsigned)gx, 256, 0, stream>>>((const __nv_bfloat16*)x, n_img, rows, img_stride,
+                                                                  row_stride, c, scale, out);
   else
-    colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, row_stride, rows, c, scale, out);
+    colsum_kernel<float><<<(unsigned)gx, 256, 0, stream>>>((const float*)x, n_img, rows, img_stride, row_stride, c, scale,
+                                                           out);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_colsum");
   return ALDI_OK;

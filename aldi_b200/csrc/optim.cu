@@ -111,6 +111,7 @@ __device__ __forceinline__ float bn_scale(const aldi_refresh_desc& d, int co) {
   return __fmul_rn(__ldg(d.bn_w + co), __frsqrt_rn(__fadd_rn(__ldg(d.bn_var + co), d.eps)));
 }
 
+// kind 0, scalar fallback (cin_p != cin) and kind 1 in fp32: one output element per thread step
 template <typename T>
 __device__ void refresh_pack(const aldi_refresh_desc& d, size_t begin, size_t end) {
   T* out = reinterpret_cast<T*>(d.out);
@@ -136,6 +137,66 @@ __device__ void refresh_pack(const aldi_refresh_desc& d, size_t begin, size_t en
   }
 }
 
+// kind 0 with cin_p == cin: the operand is the master weight itself (rows >= cout are zero) -> straight convert
+__device__ void refresh_pack_fwd_bf16(const aldi_refresh_desc& d, size_t begin, size_t end) {
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  const size_t valid = (size_t)d.cout * d.taps * d.cin;
+  for (size_t i = begin + (size_t)threadIdx.x * 8; i < end; i += (size_t)blockDim.x * 8) {
+    float f[8];
+    if (i + 8 <= valid) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(d.w + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(d.w + i + 4));
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = (i + k < valid) ? __ldg(d.w + i + k) : 0.f;
+    }
+    uint4 q;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<uint4*>(out + i) = q;
+  }
+}
+
+// kind 1 in bf16: a block transposes one 64 (cout) x 32 (cin) tile of one tap through shared memory, so both the
+// fp32 reads (32 consecutive cin of a cout row) and the bf16 writes (64 consecutive cout of a cin row) are coalesced
+__device__ void refresh_pack_dgrad_bf16(const aldi_refresh_desc& d, int blk) {
+  __shared__ float tile[64][33];
+  const int nco = d.cout_p / 64, nci = d.cin_p / 32;
+  const int cob = blk % nco;
+  int r = blk / nco;
+  const int cib = r % nci;
+  const int t = r / nci;
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int co = cob * 64 + p * 8 + ry, ci = cib * 32 + lane;
+    float v = 0.f;
+    if (co < d.cout && ci < d.cin) {
+      v = __ldg(d.w + ((size_t)co * d.taps + t) * d.cin + ci);
+      if (d.bn_w) v *= bn_scale(d, co);
+    }
+    tile[p * 8 + ry][lane] = v;
+  }
+  __syncthreads();
+  const int row = threadIdx.x >> 3, cg = threadIdx.x & 7;  // 32 cin rows x 8 groups of 8 cout
+  uint4 q;
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(tile[cg * 8 + 2 * k][row], tile[cg * 8 + 2 * k + 1][row]);
+  const size_t ci = (size_t)cib * 32 + row;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  *reinterpret_cast<uint4*>(out + (ci * d.taps + (d.taps - 1 - t)) * d.cout_p + cob * 64 + cg * 8) = q;
+}
+
+__device__ __forceinline__ bool refresh_fast_fwd(const aldi_refresh_desc& d) {
+  return d.kind == 0 && d.out_dtype == ALDI_DTYPE_BF16 && d.cin_p == d.cin && (d.cin % 8) == 0;
+}
+__device__ __forceinline__ bool refresh_fast_dgrad(const aldi_refresh_desc& d) {
+  return d.kind == 1 && d.out_dtype == ALDI_DTYPE_BF16;
+}
+
 __global__ void __launch_bounds__(256)
 refresh_kernel(const aldi_refresh_desc* __restrict__ descs, const int* __restrict__ block_start, int n_desc) {
   // binary search: last descriptor whose first block <= blockIdx.x
@@ -145,11 +206,17 @@ refresh_kernel(const aldi_refresh_desc* __restrict__ descs, const int* __restric
     if (block_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const aldi_refresh_desc d = descs[lo];
-  const size_t begin = (size_t)(blockIdx.x - block_start[lo]) * kRefreshChunk;
+  const int blk = blockIdx.x - block_start[lo];
+  if (refresh_fast_dgrad(d)) {
+    refresh_pack_dgrad_bf16(d, blk);
+    return;
+  }
+  const size_t begin = (size_t)blk * kRefreshChunk;
   if (d.kind <= 1) {
     const size_t total = (d.kind == 0 ? (size_t)d.cout_p * d.taps * d.cin_p : (size_t)d.cin_p * d.taps * d.cout_p);
     const size_t end = begin + kRefreshChunk < total ? begin + kRefreshChunk : total;
-    if (d.out_dtype == ALDI_DTYPE_BF16) refresh_pack<__nv_bfloat16>(d, begin, end);
+    if (refresh_fast_fwd(d)) refresh_pack_fwd_bf16(d, begin, end);
+    else if (d.out_dtype == ALDI_DTYPE_BF16) refresh_pack<__nv_bfloat16>(d, begin, end);
     else refresh_pack<float>(d, begin, end);
   } else if (d.kind == 4) {  // stem 7x7x3 -> 4x4 taps over the 2x2 space-to-depth map: out[co][a][b][dy][dx][c4], bf16
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
@@ -216,6 +283,8 @@ extern "C" int aldi_sgd_momentum_step(float* params, float* momentum_buf, const 
 
 extern "C" int aldi_refresh_blocks(const aldi_refresh_desc* d) {
   size_t total;
+  if (d->kind == 1 && d->out_dtype == ALDI_DTYPE_BF16)  // one block per (tap, 32-cin, 64-cout) transpose tile
+    return d->taps * (d->cin_p / 32) * (d->cout_p / 64);
   if (d->kind == 0) total = (size_t)d->cout_p * d->taps * d->cin_p;
   else if (d->kind == 1) total = (size_t)d->cin_p * d->taps * d->cout_p;
   else if (d->kind == 4) total = (size_t)d->cout_p * 256;

@@ -417,7 +417,7 @@ class Detector:
         if not g.norm:
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             assert dy.is_contiguous()
-            ops.call("aldi_colsum", dy, _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32, rows, dy.shape[3], g.cout,
+            ops.call("aldi_colsum", dy, _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32, 1, rows, 0, dy.shape[3], g.cout,
                      1.0, W.view(name, "bias", G))
 
     def _dgrad(self, W, name, dy, out, *, mask=None, residual=None, accumulate=False):
@@ -535,5 +535,5 @@ class Detector:
                   cout_store=g.cout, cin_store=g.cin)
         n, h, w, c = dy.shape
         dtc = _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32
-        for i in range(n):  # rows of one image's level slab are contiguous
-            ops.call("aldi_colsum", dy[i], dtc, h * w, c, g.cout, 1.0, W.view(name, "bias", G))
+        # rows of one image's level slab are contiguous; images are total_locs * c apart
+        ops.call("aldi_colsum", dy, dtc, n, h * w, dy.stride(0), c, g.cout, 1.0, W.view(name, "bias", G))

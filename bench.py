@@ -279,12 +279,45 @@ def run_ours(args):
         t0 = min(e.time_range.start for e in evs)
         t1 = max(e.time_range.end for e in evs)
         busy = sum(v for _, v in agg.values())
+        # label the tensor-core launches with their layer shapes: an eager step records the shape keys in launch order
+        rec = ops.KeyRecorder()
+        ops.set_profiler(rec)
+        graph_mode, step.cfg.cuda_graph = step.cfg.cuda_graph, False
+        one_step(dev, False)
+        torch.cuda.synchronize()
+        step.cfg.cuda_graph = graph_mode
+        ops.set_profiler(None)
+        tf, bw = float(peaks.get("bf16_tflops_sustained", 1400.0)), float(peaks.get("hbm_gbs", 6650.0))
+        layer_rows = []
+        for entry, kname in (("aldi_conv_tc", "conv_tc_kernel"), ("aldi_wgrad_tc", "wgrad_tc_kernel")):
+            keys = [r for r in rec.records if r[0] == entry]
+            kev = sorted([e for e in evs if kname in e.name], key=lambda e: e.time_range.start)
+            if len(kev) != 3 * len(keys):
+                print("kineto: %s launches %d != 3 x %d recorded keys" % (kname, len(kev), len(keys)), file=sys.stderr)
+                continue
+            per = {}
+            for i, e in enumerate(kev):
+                _, fl, by, key = keys[i % len(keys)]
+                d = per.setdefault(key, [0, 0.0, 0.0, 0.0])
+                d[0] += 1
+                d[1] += (e.device_time if hasattr(e, "device_time") else e.cuda_time) / 3e3
+                d[2] += fl / 3
+                d[3] += by / 3
+            for key, (n, ms, fl, by) in per.items():
+                layer_rows.append((ms, entry, key, n / 3, fl, by, max(fl / (tf * 1e12), by / (bw * 1e9)) * 1e3))
+        layer_rows.sort(reverse=True)
         with open(args.kineto_out, "w") as fh:
             fh.write("# in-situ kernel times (torch.profiler / CUPTI), 3 steps, graph=%s\n\n" % (not args.no_graph))
             fh.write("span %.3f ms/step, sum of kernel+memcpy durations %.3f ms/step\n\n" % ((t1 - t0) / 3e3, busy / 3e3))
             fh.write("| kernel | launches/step | ms/step | share |\n|---|---:|---:|---:|\n")
             for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
                 fh.write("| `%s` | %.1f | %.3f | %.1f%% |\n" % (name[:90].replace("|", "/"), n / 3, us / 3e3, 100 * us / busy))
+            fh.write("\n## tensor-core launches by layer shape (floor = max(flops / %.0f TFLOP/s, bytes / %.0f GB/s))\n\n" % (tf, bw))
+            fh.write("| entry point | shape | launches | ms/step | TFLOP/s | GB/s | floor ms | floor/actual |\n|---|---|---:|---:|---:|---:|---:|---:|\n")
+            for ms, entry, key, n, fl, by, floor in layer_rows:
+                fh.write("| %s | %s | %d | %.3f | %.0f | %.0f | %.3f | %.2f |\n" % (entry, key, n, ms, fl / ms / 1e9, by / ms / 1e6,
+                                                                                 floor, floor / ms))
+            fh.write("\nsum of floors %.3f ms, sum of actual %.3f ms\n" % (sum(r[6] for r in layer_rows), sum(r[0] for r in layer_rows)))
         return
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches = timed(dev, args.steps, False)

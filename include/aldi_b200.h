@@ -152,9 +152,10 @@ int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, int h, int w,
 /* coarse[n,h,w,c] += sum of the 2x2 block of fine (backward of nearest-2x upsample + add in FPN top-down) */
 int aldi_sum2x2_accum(const void* fine, void* coarse, int dtype, int n, int h, int w, int c, void* stream);
 int aldi_add_f32(void* dst, int dtype, const float* src, size_t n, void* stream);
-/* out[c] += scale * sum_rows x[row*row_stride + c]  (bias gradients) */
-int aldi_colsum(const void* x, int dtype, long long rows, long long row_stride, int c, float scale, float* out,
-                void* stream);
+/* out[ch] += scale * sum over images and rows of x[img*img_stride + row*row_stride + ch]  (bias gradients;
+ * strides in elements, rows 16-byte aligned) */
+int aldi_colsum(const void* x, int dtype, int n_img, long long rows, long long img_stride, long long row_stride, int c,
+                float scale, float* out, void* stream);
 /* FrozenBatchNorm2d -> per-channel (scale, shift): scale = w*rsqrt(var+eps), shift = b - mean*scale */
 int aldi_frozenbn_fold(const float* weight, const float* bias, const float* mean, const float* var, float eps,
                        float* scale, float* shift, int n, void* stream);

@@ -150,3 +150,26 @@ def test_empty_pseudo_labels():
     check_losses(dev_losses, ora)
     assert dev_losses["loss_rpn_l1_distill"] == 0.0
     check_grads(step, student)
+
+
+def test_ragged_batch_and_empty_gt_match_oracle():
+    """Edge cases of the batch format: images of different sizes share a zero-padded canvas (detectron2 ImageList),
+    and one labelled image carries no ground-truth box at all."""
+    from aldi_b200 import arch, synth_data
+    gen = torch.Generator().manual_seed(314)
+    sd_s = arch.synthetic_state_dict(seed=61)
+    sd_t = arch.synthetic_state_dict(seed=61)
+    ls = []
+    for (h, w, nb) in ((96, 160, 5), (128, 96, 0), (64, 64, 3)):
+        img, boxes, classes = synth_data.synth_image(h, w, gen, num_boxes=nb, max_side=48)
+        ls.append({"image": img, "boxes": boxes.reshape(-1, 4), "classes": classes.reshape(-1).long(), "height": h, "width": w})
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, None, None), ims_per_gpu=3)
+    pu.install_device_sampler(step.seed_log)
+    student, _ = pu.oracle_models(sd_s, sd_t)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, aldi_ref.NullDistiller(), (None, pu.to_d2(ls, True), None, None),
+                                                   3, False, lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    check_losses(dev_losses, ora)
+    worst = check_grads(step, student)
+    print("ragged/empty-gt: losses", dev_losses, "worst grad rel err", worst)

@@ -1,0 +1,128 @@
+"""Host-side mirror of the reference's cfg / dataloader / trainer surface (no GPU needed except where marked)."""
+import pytest
+import torch
+
+from aldi_b200.config import add_aldi_config, get_cfg, step_config_from_cfg
+from aldi_b200.trainer import ALDITrainer, SyntheticWeakStrongLoader, unpack_data_weak_strong
+
+ALDI_BEST = """
+_BASE_: "./base.yaml"
+DATASETS:
+  BATCH_CONTENTS: ("labeled_strong", "unlabeled_strong")
+  BATCH_RATIOS: (1, 1)
+EMA:
+  ENABLED: True
+DOMAIN_ADAPT:
+  TEACHER:
+    ENABLED: True
+  DISTILL:
+    HARD_ROIH_CLS_ENABLED: False
+    ROIH_CLS_ENABLED: True
+    OBJ_ENABLED: True
+    ROIH_REG_ENABLED: True
+    RPN_REG_ENABLED: True
+SOLVER:
+  BACKWARD_AT_END: False
+"""
+BASE = """
+MODEL:
+  ROI_HEADS:
+    NUM_CLASSES: 8
+  RPN:
+    PRE_NMS_TOPK_TRAIN: 2000
+    PRE_NMS_TOPK_TEST: 1000
+    POST_NMS_TOPK_TRAIN: 1000
+    POST_NMS_TOPK_TEST: 1000
+SOLVER:
+  IMS_PER_BATCH: 8
+  IMS_PER_GPU: 2
+  BASE_LR: 0.02
+  AMP:
+    ENABLED: True
+"""
+
+
+def _cfg(tmp_path, opts=()):
+    (tmp_path / "base.yaml").write_text(BASE)
+    (tmp_path / "aldi.yaml").write_text(ALDI_BEST)
+    cfg = get_cfg()
+    add_aldi_config(cfg)
+    cfg.merge_from_file(str(tmp_path / "aldi.yaml"))
+    cfg.merge_from_list(list(opts))
+    return cfg
+
+
+def test_yaml_base_chain_and_overrides(tmp_path):
+    cfg = _cfg(tmp_path, ["SOLVER.IMS_PER_GPU", "4", "DOMAIN_ADAPT.TEACHER.THRESHOLD", "0.7"])
+    assert cfg.SOLVER.IMS_PER_BATCH == 8 and cfg.SOLVER.IMS_PER_GPU == 4            # base value, override
+    assert cfg.DATASETS.BATCH_CONTENTS == ("labeled_strong", "unlabeled_strong")
+    assert cfg.EMA.ALPHA == 0.9996 and cfg.EMA.START_ITER == 0                       # aldi/config.py defaults
+    sc = step_config_from_cfg(cfg)
+    assert (sc.ims_per_gpu, sc.num_classes, sc.dtype, sc.base_lr) == (4, 8, "bf16", 0.02)
+    assert sc.do_cls_dst and sc.do_obj_dst and sc.do_rpn_reg_dst and sc.do_roih_reg_dst and not sc.do_hard_cls
+    assert sc.pseudo_threshold == 0.7 and sc.rpn_pre_topk == (2000, 1000) and sc.distill_enabled
+    cfg.freeze()
+    with pytest.raises(AttributeError):
+        cfg.SOLVER.BASE_LR = 1.0
+    with pytest.raises(KeyError):
+        _cfg(tmp_path, ["SOLVER.NO_SUCH_KEY", "1"])
+
+
+def test_unsupported_combinations_fail_with_reference_errors(tmp_path):
+    cfg = _cfg(tmp_path, ["SOLVER.OPTIMIZER", "ADAMW"])
+    with pytest.raises(ValueError, match="Unsupported optimizer/backbone combination"):
+        step_config_from_cfg(cfg)
+    cfg = _cfg(tmp_path, ["MODEL.BACKBONE.NAME", "build_vitdet_b_backbone"])
+    with pytest.raises(NotImplementedError):
+        step_config_from_cfg(cfg)
+    cfg = _cfg(tmp_path, ["MODEL.RPN.PRE_NMS_TOPK_TRAIN", "12000"])       # detectron2's own default, not the ALDI configs'
+    with pytest.raises(NotImplementedError, match="PRE_NMS_TOPK"):
+        step_config_from_cfg(cfg)
+    cfg = _cfg(tmp_path, ["MODEL.DEVICE", "cpu"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ALDITrainer(cfg)
+
+
+def test_unpack_weak_strong_semantics():
+    lab = [{"image": torch.ones(1), "img_weak": torch.zeros(1), "id": i} for i in range(2)]
+    unl = [{"image": torch.ones(1) * 2, "img_weak": torch.zeros(1), "id": 10 + i} for i in range(2)]
+    lw, ls, uw, us = unpack_data_weak_strong(lab, unl, ("labeled_strong", "unlabeled_strong"))
+    assert lw is None and ls is lab and us is unl
+    assert uw is not None and all(float(d["image"]) == 0.0 for d in uw)         # weak view returned for pseudo-labelling
+    assert all(float(d["image"]) == 2.0 for d in us)                             # strong batch untouched
+    lw, ls, uw, us = unpack_data_weak_strong(lab, None, ("labeled_weak",))
+    assert ls is None and uw is None and us is None and all(float(d["image"]) == 0.0 for d in lw)
+    assert all(float(d["image"]) == 1.0 for d in lab)                            # the weak copy does not alias the input
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_synthetic_loader_batch_sizes(tmp_path, world):
+    cfg = _cfg(tmp_path)
+    loader = SyntheticWeakStrongLoader(cfg, 64, 96, rank=world - 1, world=world)
+    lw, ls, uw, us = next(iter(loader))
+    per = 4 // world                                                             # IMS_PER_BATCH 8, ratios (1, 1)
+    assert lw is None and len(ls) == per and len(uw) == per and len(us) == per
+    assert ls[0]["image"].shape == (3, 64, 96) and ls[0]["image"].dtype == torch.uint8 and "boxes" in ls[0]
+    assert not torch.equal(uw[0]["image"], us[0]["image"])                       # weak vs strong view of the same image
+    a = next(iter(SyntheticWeakStrongLoader(cfg, 64, 96, rank=0, world=2)))
+    b = next(iter(SyntheticWeakStrongLoader(cfg, 64, 96, rank=1, world=2)))
+    assert not torch.equal(a[1][0]["image"], b[1][0]["image"])                   # ranks draw different images
+    bad = _cfg(tmp_path, ["DATASETS.BATCH_RATIOS", "(1, 1, 1)"])
+    with pytest.raises(AssertionError):
+        SyntheticWeakStrongLoader(bad, 64, 96)
+
+
+@pytest.mark.gpu
+def test_trainer_runs_aldi_best_config(tmp_path):
+    cfg = _cfg(tmp_path, ["SOLVER.BASE_LR", "0.0005", "SOLVER.WARMUP_ITERS", "10"])
+    trainer = ALDITrainer(cfg, image_size=(128, 160))
+    hist = trainer.train(0, 4)
+    assert len(hist) == 4 and trainer.iter == 4
+    keys = {k for k in hist[-1] if k.startswith("loss_")}
+    assert {"loss_cls_source_strong", "loss_obj_bce_distill", "loss_cls_ce_distill", "loss_cls_distill"} <= keys
+    assert all(v == v for h in hist for v in h.values())
+    assert hist[1]["lr"] > hist[0]["lr"]                                         # linear warm-up
+    sd = trainer.state_dict()
+    assert set(sd) == {"model", "ema", "iteration"}
+    assert "backbone.bottom_up.res2.0.conv1.weight" in sd["model"] and "roi_heads.box_predictor.cls_score.bias" in sd["ema"]
+    assert trainer.step_impl.graph_replays == 0 or trainer.step_impl.cfg.cuda_graph

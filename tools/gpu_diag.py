@@ -426,6 +426,31 @@ def case_perf_mem():
     return True
 
 
+def case_perf_small():
+    """the layers whose time is not explained by flops or HBM bytes (3x3 with few channels, small maps)."""
+    import torch
+    from aldi_b200 import ops
+    shapes = [("3x3 64->64 4x256x512", 4, 256, 512, 64, 64, 3), ("3x3 128->128 4x128x256", 4, 128, 256, 128, 128, 3),
+              ("3x3 256->256 4x64x128", 4, 64, 128, 256, 256, 3), ("1x1 256->1024 4x64x128", 4, 64, 128, 256, 1024, 1)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, n, h, w, cin, cout, k in shapes:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(cout, k * k * cin, device="cuda", generator=g) / (k * k * cin) ** 0.5).bfloat16()
+        out = torch.empty(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.conv(x, wt, out, taps_h=k, taps_w=k, pad_h=k // 2, pad_w=k // 2)
+        e0.record()
+        for _ in range(10):
+            ops.conv(x, wt, out, taps_h=k, taps_w=k, pad_h=k // 2, pad_w=k // 2)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        tiles = n * h * w / 128 * max(1, cout // 256)
+        print("[perf_small] %s: %.1f us  %.0f TFLOP/s  %.2f us/tile/SM" % (
+            name, ms * 1e3, 2.0 * n * h * w * cin * cout * k * k / ms / 1e9, ms * 1e3 / (tiles / 148)), flush=True)
+    return True
+
+
 CASES = [
     "optim", "fwd_f32", "bwd_f32",
     "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "fwd_epilogue2",
