@@ -11,9 +11,9 @@ import torch
 class ConvSpec:
     """One conv / linear layer: Detectron2 key prefix and geometry."""
 
-    def __init__(self, key, cin, cout, k=1, stride=1, pad=0, bias=False, norm=False, trainable=True):
+    def __init__(self, key, cin, cout, k=1, stride=1, pad=0, bias=False, norm=False, trainable=True, linear=False):
         self.key, self.cin, self.cout, self.k, self.stride, self.pad = key, cin, cout, k, stride, pad
-        self.bias, self.norm, self.trainable = bias, norm, trainable
+        self.bias, self.norm, self.trainable, self.linear = bias, norm, trainable, linear
 
 
 RES_DEPTHS = (3, 4, 6, 3)
@@ -42,7 +42,29 @@ def resnet_specs(freeze_at=2):
     return specs
 
 
-def rcnn_specs(num_classes=8, freeze_at=2):
+def align_specs(align):
+    """Discriminators of the AlignMixin (aldi/align.py:40-41,103-136) with their nn.Sequential state_dict keys.
+    align: {"img": (input_dim, hidden_dims) | None, "ins": (input_dim, hidden_dims) | None}."""
+    specs = OrderedDict()
+    if not align:
+        return specs
+    if align.get("img"):
+        cin, hidden = align["img"]
+        for i, dim in enumerate(hidden):       # Conv2d(prev, dim, 3) [valid], ReLU
+            specs["img_align.conv%d" % i] = ConvSpec("img_align.model.%d" % (2 * i), cin, dim, 3, 1, 0, bias=True)
+            cin = dim
+        # ..., AdaptiveAvgPool2d(1), Flatten, Linear(prev, 1)
+        specs["img_align.out"] = ConvSpec("img_align.model.%d" % (2 * len(hidden) + 2), cin, 1, bias=True, linear=True)
+    if align.get("ins"):
+        cin, hidden = align["ins"]
+        for i, dim in enumerate(hidden):       # Flatten, then Linear(prev, dim), ReLU
+            specs["ins_align.fc%d" % i] = ConvSpec("ins_align.model.%d" % (1 + 2 * i), cin, dim, bias=True, linear=True)
+            cin = dim
+        specs["ins_align.out"] = ConvSpec("ins_align.model.%d" % (1 + 2 * len(hidden)), cin, 1, bias=True, linear=True)
+    return specs
+
+
+def rcnn_specs(num_classes=8, freeze_at=2, align=None):
     specs = resnet_specs(freeze_at)
     for lvl, c in zip((2, 3, 4, 5), (256, 512, 1024, 2048)):
         specs["fpn_lateral%d" % lvl] = ConvSpec("backbone.fpn_lateral%d" % lvl, c, 256, 1, 1, 0, bias=True)
@@ -55,6 +77,7 @@ def rcnn_specs(num_classes=8, freeze_at=2):
     specs["fc2"] = ConvSpec("roi_heads.box_head.fc2", 1024, 1024, bias=True)
     specs["cls_score"] = ConvSpec("roi_heads.box_predictor.cls_score", 1024, num_classes + 1, bias=True)
     specs["bbox_pred"] = ConvSpec("roi_heads.box_predictor.bbox_pred", 1024, num_classes * 4, bias=True)
+    specs.update(align_specs(align))
     return specs
 
 
@@ -64,15 +87,15 @@ NORM_FIELDS = ("weight", "bias", "running_mean", "running_var")
 
 def d2_shape(name, s):
     """Shape of `<key>.weight` in the Detectron2 state_dict."""
-    if name in LINEAR_LAYERS:
+    if name in LINEAR_LAYERS or s.linear:
         return (s.cout, s.cin)
     return (s.cout, s.cin, s.k, s.k)
 
 
-def state_dict_entries(num_classes=8, freeze_at=2):
+def state_dict_entries(num_classes=8, freeze_at=2, align=None):
     """[(d2_key, shape, layer_name, field)] in a fixed order; field in {weight,bias,norm.<f>}."""
     out = []
-    for name, s in rcnn_specs(num_classes, freeze_at).items():
+    for name, s in rcnn_specs(num_classes, freeze_at, align).items():
         out.append((s.key + ".weight", d2_shape(name, s), name, "weight"))
         if s.bias:
             out.append((s.key + ".bias", (s.cout,), name, "bias"))
@@ -82,14 +105,14 @@ def state_dict_entries(num_classes=8, freeze_at=2):
     return out
 
 
-def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2):
+def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None):
     """Deterministic CPU-generated weights with O(1) activations (stands in for a burn-in checkpoint).
 
     Scales are chosen so that a bf16 trunk stays in range, RPN logits are well separated and the
     box classifier is confident enough (>0.8) on some RoIs for the pseudo-label path to be non-empty.
     """
     sd = OrderedDict()
-    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at)):
+    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at, align)):
         g = torch.Generator().manual_seed(seed * 100003 + idx)
         if field == "weight":
             fan_in = 1
@@ -98,7 +121,7 @@ def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2):
             fan_out = shape[0] * (shape[2] * shape[3] if len(shape) == 4 else 1)
             if name == "stem" or name.startswith("res"):
                 t = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
-            elif name.startswith("fpn") or name in ("fc1", "fc2"):
+            elif name.startswith("fpn") or name in ("fc1", "fc2") or "_align." in name:
                 bound = (3.0 / fan_in) ** 0.5
                 t = (torch.rand(shape, generator=g) * 2 - 1) * bound
             elif name.startswith("rpn"):

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 unsigned long long g_aldi_launch_count = 0;
@@ -24,6 +25,15 @@ int aldi_num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+bool aldi_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ALDI_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 extern "C" const char* aldi_last_error(void) { return g_err; }

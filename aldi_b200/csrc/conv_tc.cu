@@ -163,6 +163,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above overlapped the previous kernel's tail (programmatic dependent launch); its results are
+  // visible after this wait, and the next kernel may begin ITS prologue as soon as our CTAs retire
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -541,8 +545,13 @@ int launch_conv(const CUtensorMap* tm, const ConvArgs& a, int smem_bytes, cudaSt
     attr_set = true;
   }
   int grid = a.num_tiles < aldi_num_sms() ? a.num_tiles : aldi_num_sms();
-  conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], a);
+  cudaError_t le = aldi_launch_pdl(conv_tc_kernel<BLOCK_N>, dim3(grid), dim3(kNumThreads), (size_t)smem_bytes, stream,
+                                   tm[0], tm[1], tm[2], tm[3], tm[4], a);
   ALDI_COUNT_LAUNCH();
+  if (le != cudaSuccess) {
+    aldi_set_error("aldi_conv_tc: launch failed: %s", cudaGetErrorString(le));
+    return ALDI_ERR_CUDA;
+  }
   ALDI_CUDA_LAUNCH_CHECK("aldi_conv_tc");
   return ALDI_OK;
 }

@@ -228,21 +228,23 @@ sum2x2_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int h, int 
 }
 
 // ---- dst += src (fp32 source, e.g. RoIAlign's atomic gradient buffer); n multiple of 8 --------------
-template <typename T>
+template <typename T, bool ASSIGN>
 __global__ void __launch_bounds__(256) add_f32_kernel(T* __restrict__ dst, const float* __restrict__ src, size_t n) {
   constexpr int V = Vec16<T>::N;
   const size_t nv = n / V;
+  pdl_wait();
+  pdl_launch_dependents();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
     float d[V], s[V];
-    Vec16<T>::load(dst + i * V, d);
+    if (!ASSIGN) Vec16<T>::load(dst + i * V, d);
 #pragma unroll
     for (int k = 0; k < V; k += 4) Vec16<float>::load(src + i * V + k, s + k);
 #pragma unroll
-    for (int k = 0; k < V; ++k) d[k] += s[k];
+    for (int k = 0; k < V; ++k) d[k] = ASSIGN ? s[k] : d[k] + s[k];
     Vec16<T>::store(dst + i * V, d);
   }
   for (size_t i = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = from_f32<T>(to_f32<T>(dst[i]) + src[i]);
+    dst[i] = from_f32<T>(ASSIGN ? src[i] : to_f32<T>(dst[i]) + src[i]);
 }
 
 // ---- out[c] += scale * sum_rows x[row, c]   (bias gradients) ----------------------------------------
@@ -250,24 +252,43 @@ __global__ void __launch_bounds__(256) add_f32_kernel(T* __restrict__ dst, const
 // out[ch] += scale * sum over (image, row) of x[img*img_stride + row*row_stride + ch]: 16-byte loads, one thread
 // per 16 bytes of a row, 256 / (threads per row) rows per pass, register accumulation, one shared-memory reduction
 // and one atomicAdd per channel per block.
+constexpr int kColsumThreads = 512;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kColsumThreads, 2)
 colsum_kernel(const T* __restrict__ x, int n_img, long long rows, long long img_stride, long long row_stride, int c,
               float scale, float* __restrict__ out) {
   constexpr int V = Vec16<T>::N;
-  __shared__ float part[256][V + 1];
+  __shared__ float part[kColsumThreads][V + 1];
   const int tpr = (c + V - 1) / V;            // threads per row
-  const int rpp = 256 / tpr;                  // rows per pass
+  const int rpp = kColsumThreads / tpr;       // rows per pass
   const int rg = threadIdx.x / tpr, tc = threadIdx.x - rg * tpr;
   float acc[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  pdl_wait();
+  pdl_launch_dependents();
   if (rg < rpp) {
     const long long total = (long long)n_img * rows;
-    for (long long r = (long long)blockIdx.x * rpp + rg; r < total; r += (long long)gridDim.x * rpp) {
-      const long long img = r / rows, rr = r - img * rows;
+    const long long step = (long long)gridDim.x * rpp;
+    const T* base = x + (long long)tc * V;
+    long long r = (long long)blockIdx.x * rpp + rg;
+    // four independent 16-byte loads in flight per thread, 1024 threads per SM: a pure HBM stream.  Few, fat blocks:
+    // the per-block atomics below all land on the same handful of cache lines and serialise in the L2.
+    for (; r + 3 * step < total; r += 4 * step) {
+      float f[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long ru = r + u * step;
+        const long long img = (n_img == 1) ? 0 : ru / rows;
+        Vec16<T>::load(base + img * img_stride + (ru - img * rows) * row_stride, f[u]);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += (f[0][k] + f[1][k]) + (f[2][k] + f[3][k]);
+    }
+    for (; r < total; r += step) {
+      const long long img = (n_img == 1) ? 0 : r / rows;
       float f[V];
-      Vec16<T>::load(x + img * img_stride + rr * row_stride + (long long)tc * V, f);
+      Vec16<T>::load(base + img * img_stride + (r - img * rows) * row_stride, f);
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] += f[k];
     }
@@ -275,13 +296,48 @@ colsum_kernel(const T* __restrict__ x, int n_img, long long rows, long long img_
 #pragma unroll
   for (int k = 0; k < V; ++k) part[threadIdx.x][k] = acc[k];
   __syncthreads();
-  if (rg == 0 && tc < tpr) {
+  // thread (q, tc) of the first 4*tpr threads sums channel quad q of column group tc over the row groups
+  constexpr int Q = V / 4;
+  if (threadIdx.x < Q * tpr) {
+    const int q = threadIdx.x / tpr, t2 = threadIdx.x - q * tpr;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int g = 0; g < rpp; ++g) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += part[g * tpr + t2][q * 4 + k];
+    }
+    const int ch = t2 * V + q * 4;
+    if (ch + 4 <= c && ((reinterpret_cast<uintptr_t>(out + ch) & 15) == 0)) {
+      atomicAdd(reinterpret_cast<float4*>(out + ch), make_float4(t[0] * scale, t[1] * scale, t[2] * scale, t[3] * scale));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ch + k < c) atomicAdd(out + ch + k, t[k] * scale);
+    }
+  }
+}
+
+// ---- backward of AdaptiveAvgPool2d(1) behind a ReLU (aldi/align.py:103-118 ConvDiscriminator) ---------------------
+// dh[n, p, ch] = h[n, p, ch] > 0 ? dgap[n, ch] * scale : 0 and ndh = -dh (operand of the gradient-reversed dgrad)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gap_backward_kernel(const T* __restrict__ h, const float* __restrict__ dgap, int n, long long pix, int c_p, int c,
+                    float scale, T* __restrict__ dh, T* __restrict__ ndh) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = c_p / V;
+  const size_t total = (size_t)n * pix * cv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cv) * V;
+    const int img = (int)(i / ((size_t)pix * cv));
+    float f[V], d[V], nd[V];
+    Vec16<T>::load(h + i * V, f);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      float t = 0.f;
-      for (int g = 0; g < rpp; ++g) t += part[g * tpr + tc][k];
-      if (tc * V + k < c) atomicAdd(out + tc * V + k, t * scale);
+      const float g = (ch + k < c && f[k] > 0.f) ? __ldg(dgap + (size_t)img * c + ch + k) * scale : 0.f;
+      d[k] = g;
+      nd[k] = -g;
     }
+    Vec16<T>::store(dh + i * V, d);
+    Vec16<T>::store(ndh + i * V, nd);
   }
 }
 
@@ -374,11 +430,25 @@ extern "C" int aldi_add_f32(void* dst, int dtype, const float* src, size_t n, vo
   if (n == 0) return ALDI_OK;
   const int grid = grid_for(n / 4 + 1, 256);
   if (dtype == ALDI_DTYPE_BF16)
-    add_f32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((__nv_bfloat16*)dst, src, n);
+    aldi_launch_pdl(add_f32_kernel<__nv_bfloat16, false>, dim3(grid), dim3(256), 0, stream, (__nv_bfloat16*)dst, src, n);
   else
-    add_f32_kernel<float><<<grid, 256, 0, stream>>>((float*)dst, src, n);
+    aldi_launch_pdl(add_f32_kernel<float, false>, dim3(grid), dim3(256), 0, stream, (float*)dst, src, n);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_add_f32");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_cast_f32(void* dst, int dtype, const float* src, size_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(dst && src, "aldi_cast_f32: null pointer");
+  if (n == 0) return ALDI_OK;
+  const int grid = grid_for(n / 4 + 1, 256);
+  if (dtype == ALDI_DTYPE_BF16)
+    aldi_launch_pdl(add_f32_kernel<__nv_bfloat16, true>, dim3(grid), dim3(256), 0, stream, (__nv_bfloat16*)dst, src, n);
+  else
+    aldi_launch_pdl(add_f32_kernel<float, true>, dim3(grid), dim3(256), 0, stream, (float*)dst, src, n);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_cast_f32");
   return ALDI_OK;
 }
 
@@ -387,21 +457,21 @@ extern "C" int aldi_colsum(const void* x, int dtype, int n_img, long long rows, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(x && out && c > 0 && n_img > 0, "aldi_colsum: bad args");
   const int v = dtype == ALDI_DTYPE_BF16 ? 8 : 4;
-  ALDI_CHECK_ARG((c + v - 1) / v <= 256, "aldi_colsum: at most %d channels", 256 * v);
+  ALDI_CHECK_ARG((c + v - 1) / v <= kColsumThreads, "aldi_colsum: at most %d channels", kColsumThreads * v);
   ALDI_CHECK_ARG(row_stride % v == 0 && img_stride % v == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                  "aldi_colsum: rows must be 16-byte aligned (and hold ceil(c/%d)*%d readable channels)", v, v);
   if (rows <= 0) return ALDI_OK;
-  const int rpp = 256 / ((c + v - 1) / v);
+  const int rpp = kColsumThreads / ((c + v - 1) / v);
   long long gx = ((long long)n_img * rows + (long long)rpp * 16 - 1) / ((long long)rpp * 16);
-  long long cap = (long long)aldi_num_sms() * 4;
+  long long cap = (long long)aldi_num_sms() * 2;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   if (dtype == ALDI_DTYPE_BF16)
-    colsum_kernel<__nv_bfloat16><<<(unsigned)gx, 256, 0, stream>>>((const __nv_bfloat16*)x, n_img, rows, img_stride,
-                                                                  row_stride, c, scale, out);
+    aldi_launch_pdl(colsum_kernel<__nv_bfloat16>, dim3((unsigned)gx), dim3(kColsumThreads), 0, stream, (const __nv_bfloat16*)x, n_img,
+                    rows, img_stride, row_stride, c, scale, out);
   else
-    colsum_kernel<float><<<(unsigned)gx, 256, 0, stream>>>((const float*)x, n_img, rows, img_stride, row_stride, c, scale,
-                                                           out);
+    aldi_launch_pdl(colsum_kernel<float>, dim3((unsigned)gx), dim3(kColsumThreads), 0, stream, (const float*)x, n_img, rows,
+                    img_stride, row_stride, c, scale, out);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_colsum");
   return ALDI_OK;
@@ -414,5 +484,23 @@ extern "C" int aldi_frozenbn_fold(const float* weight, const float* bias, const 
   frozenbn_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(weight, bias, mean, var, eps, scale, shift, n);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_frozenbn_fold");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_gap_backward(const void* h, const float* dgap, int dtype, int n, long long pix, int c_p, int c,
+                                 float scale, void* dh, void* ndh, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(h && dgap && dh && ndh && n > 0 && pix > 0 && c > 0 && c <= c_p, "aldi_gap_backward: bad args");
+  const int v = dtype == ALDI_DTYPE_BF16 ? 8 : 4;
+  ALDI_CHECK_ARG(c_p % v == 0, "aldi_gap_backward: padded channels must be a multiple of %d", v);
+  const int grid = grid_for((size_t)n * pix * (c_p / v), 256);
+  if (dtype == ALDI_DTYPE_BF16)
+    gap_backward_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)h, dgap, n, pix, c_p, c, scale,
+                                                                  (__nv_bfloat16*)dh, (__nv_bfloat16*)ndh);
+  else
+    gap_backward_kernel<float><<<grid, 256, 0, stream>>>((const float*)h, dgap, n, pix, c_p, c, scale, (float*)dh,
+                                                         (float*)ndh);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_gap_backward");
   return ALDI_OK;
 }

@@ -293,6 +293,78 @@ domain_bce_kernel(const float* __restrict__ pred, int n, int stride, float label
   if (threadIdx.x == 0) atomicAdd(loss_out, l * (weight * gscale * inv));
 }
 
+// aldi/align.py:81-90 + the discriminator's final Linear(C, 1): logits = feat . w + b for every row, BCE-with-logits
+// (mean over the valid rows) against the constant domain label, and in the same pass the gradients of that layer:
+// dw += sum_r dl[r] * feat[r], db += sum_r dl[r], dfeat[r] = dl[r] * w (optionally gated by feat > 0, i.e. already
+// the gradient w.r.t. the PRE-activation of the ReLU that produced feat) and its negation (the operand of the
+// gradient-reversed data gradient, aldi/helpers.py:51-63).
+template <typename T>
+__global__ void __launch_bounds__(256)
+domain_head_kernel(const T* __restrict__ feat, int n, int c, long long feat_stride, const int* __restrict__ counts,
+                   int rows_per_image, const float* __restrict__ w, const float* __restrict__ b, float label,
+                   float weight, float gscale, int relu_mask, T* __restrict__ dfeat, T* __restrict__ ndfeat,
+                   long long d_stride, float* __restrict__ dw, float* __restrict__ db, float* __restrict__ loss_out) {
+  constexpr int R = 32;
+  __shared__ float s_dl[R];
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float denom = (float)n;
+  if (counts) {
+    int tot = 0;
+    const int n_img = (n + rows_per_image - 1) / rows_per_image;
+    for (int i = 0; i < n_img; ++i) tot += min(counts[i], rows_per_image);
+    denom = (float)max(tot, 1);
+  }
+  const float k = weight * gscale / denom;
+  const float bias = b[0];
+  float loss = 0.f, dsum = 0.f;
+  for (int r0 = blockIdx.x * R; r0 < n; r0 += gridDim.x * R) {
+    __syncthreads();
+    for (int rr = warp; rr < R; rr += 8) {
+      const int r = r0 + rr;
+      float dl = 0.f;
+      if (r < n) {
+        const bool valid = !counts || (r % rows_per_image) < counts[r / rows_per_image];
+        float dot = 0.f;
+        if (valid) {
+          const T* f = feat + (long long)r * feat_stride;
+          for (int ch = lane; ch < c; ch += 32) dot += to_f32<T>(f[ch]) * w[ch];
+        }
+        dot = warp_sum(dot);
+        if (valid) {
+          const float x = dot + bias;
+          dl = (sigmoidf_(x) - label) * k;
+          if (lane == 0) { loss += bce_with_logits(x, label); dsum += dl; }
+        }
+      }
+      if (lane == 0) s_dl[rr] = dl;
+    }
+    __syncthreads();
+    const int rmax = min(R, n - r0);
+    for (int ch = threadIdx.x; ch < c; ch += 256) {
+      const float wv = w[ch];
+      float acc = 0.f;
+      for (int rr = 0; rr < rmax; ++rr) {
+        const long long r = r0 + rr;
+        const float f = to_f32<T>(feat[r * feat_stride + ch]);
+        const float dl = s_dl[rr];
+        acc += dl * f;
+        float g = dl * wv;
+        if (relu_mask && !(f > 0.f)) g = 0.f;
+        dfeat[r * d_stride + ch] = from_f32<T>(g);
+        if (ndfeat) ndfeat[r * d_stride + ch] = from_f32<T>(-g);
+      }
+      atomicAdd(dw + ch, acc);
+    }
+  }
+  loss = block_sum(loss, red);
+  dsum = block_sum(dsum, red);
+  if (threadIdx.x == 0) {
+    if (loss != 0.f) atomicAdd(loss_out, loss * k);
+    if (dsum != 0.f) atomicAdd(db, dsum);
+  }
+}
+
 int blocks_for(long long work) {
   long long b = (work + 255) / 256;
   long long cap = (long long)aldi_num_sms() * 8;
@@ -410,5 +482,28 @@ extern "C" int aldi_domain_bce_loss(const float* pred, int n, int stride, float 
                                                        dstride, loss_out);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_domain_bce_loss");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_domain_head_loss(const void* feat, int dtype, int n, int c, long long feat_stride, const int* counts,
+                                     int rows_per_image, const float* w, const float* b, float domain_label,
+                                     float weight, float gscale, int relu_mask, void* dfeat, void* ndfeat,
+                                     long long d_stride, float* dw, float* db, float* loss_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(feat && w && b && dfeat && dw && db && loss_out && n > 0 && c > 0, "aldi_domain_head_loss: bad args");
+  ALDI_CHECK_ARG(!counts || rows_per_image > 0, "aldi_domain_head_loss: counts need rows_per_image");
+  int grid = (n + 31) / 32;
+  const int cap = aldi_num_sms() * 4;
+  if (grid > cap) grid = cap;
+  if (dtype == ALDI_DTYPE_BF16)
+    domain_head_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        (const __nv_bfloat16*)feat, n, c, feat_stride, counts, rows_per_image, w, b, domain_label, weight, gscale,
+        relu_mask, (__nv_bfloat16*)dfeat, (__nv_bfloat16*)ndfeat, d_stride, dw, db, loss_out);
+  else
+    domain_head_kernel<float><<<grid, 256, 0, stream>>>((const float*)feat, n, c, feat_stride, counts, rows_per_image, w,
+                                                        b, domain_label, weight, gscale, relu_mask, (float*)dfeat,
+                                                        (float*)ndfeat, d_stride, dw, db, loss_out);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_domain_head_loss");
   return ALDI_OK;
 }

@@ -94,6 +94,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();               // prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -228,8 +230,13 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, const WgradArgs
     attr_set = true;
   }
   int grid = a.num_items < aldi_num_sms() ? a.num_items : aldi_num_sms();
-  wgrad_tc_kernel<BLOCK_N, MH><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmY, tmX, a);
+  cudaError_t le = aldi_launch_pdl(wgrad_tc_kernel<BLOCK_N, MH>, dim3(grid), dim3(kNumThreads), (size_t)C::kSmemBytes,
+                                   stream, tmY, tmX, a);
   ALDI_COUNT_LAUNCH();
+  if (le != cudaSuccess) {
+    aldi_set_error("aldi_wgrad_tc: launch failed: %s", cudaGetErrorString(le));
+    return ALDI_ERR_CUDA;
+  }
   ALDI_CUDA_LAUNCH_CHECK("aldi_wgrad_tc");
   return ALDI_OK;
 }

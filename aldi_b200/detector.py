@@ -30,9 +30,10 @@ def _pad64(c):
 class FlatLayout:
     """Detectron2 state_dict keys <-> ranges of one flat fp32 buffer (trainable range first)."""
 
-    def __init__(self, num_classes=8, freeze_at=2):
+    def __init__(self, num_classes=8, freeze_at=2, align=None):
         self.num_classes = num_classes
-        self.specs = arch.rcnn_specs(num_classes, freeze_at)
+        self.align = align
+        self.specs = arch.rcnn_specs(num_classes, freeze_at, align)
         member_of = {m: g for g, ms in FUSED.items() for m in ms}
         train, frozen, buffers = [], [], []
         done = set()
@@ -148,7 +149,7 @@ class DetectorWeights:
             if g.norm:
                 self.scale[name] = torch.zeros(g.cout_p, device=self.dev)
             self.shift[name] = torch.zeros(g.cout_p, device=self.dev)
-        self.no_dgrad = {"stem", "res3.0.conv1", "res3.0.shortcut", "fpn_lateral2"}
+        self.no_dgrad = {"stem", "res3.0.conv1", "res3.0.shortcut", "fpn_lateral2", "img_align.out", "ins_align.out"}
         self._tables = {}
 
     # ---- flat views -------------------------------------------------------------------------------
@@ -267,7 +268,8 @@ class Detector:
         xv = x[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else x
         n, h, w, _ = xv.shape
         if out is None:
-            out = torch.empty(n, h, w, g.cout_p, device=x.device, dtype=out_dtype or x.dtype)
+            ho, wo = h + 2 * g.pad - g.k + 1, w + 2 * g.pad - g.k + 1   # stride-2 1x1 convs were turned into views
+            out = torch.empty(n, ho, wo, g.cout_p, device=x.device, dtype=out_dtype or x.dtype)
         ops.conv(xv, W.fwd[name], out, taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad, scale=W.scale.get(name),
                  bias=W.shift[name], residual=residual, res_mode=res_mode, relu=relu, cout_store=cout_store)
         return out
@@ -408,6 +410,62 @@ class Detector:
                  score_thresh, ops.host_floats((10.0, 10.0, 5.0, 5.0)), SCALE_CLAMP, cb, cs, cc, csrc, cnt, cstride)
         return self.nms(cb, cs, cc, None, cnt, nms_thresh, topk)
 
+    # ---- domain-alignment discriminators (aldi/align.py:71-136; off in the shipped ALDI++ configs) -----------
+    def align_forward(self, W, G, feats, f2, roi_count, roi_batch_size, cfg, labeled, gscale, loss_out):
+        """`AlignMixin.forward(do_align=True)` after the detector forward: image-level ConvDiscriminator on
+        feats[cfg.img_da_layer] and instance-level FCDiscriminator on the box-head output, each behind a gradient
+        reversal, BCE-with-logits against the domain label (1 = source, 0 = target).  The last Linear + loss + that
+        layer's gradients are one kernel; the returned dict feeds `backward(align=...)`.
+        loss_out: 2 floats (loss_da_img, loss_da_ins), accumulated."""
+        label = 1.0 if labeled else 0.0
+        dtc = _l.BF16 if W.dtype == torch.bfloat16 else _l.F32
+        dev = f2.device if f2 is not None else feats["p2"].device
+        saved = {}
+        if cfg.img_da_enabled:
+            if len(cfg.img_da_hidden_dims) != 1:
+                raise NotImplementedError("image-level discriminator: exactly one hidden conv layer is implemented "
+                                          "(DOMAIN_ADAPT.ALIGN.IMG_DA_HIDDEN_DIMS default [256])")
+            x = feats[cfg.img_da_layer]
+            h = self.conv(W, "img_align.conv0", x, relu=True)        # 3x3 VALID conv + bias + ReLU
+            n, ho, wo, cp = h.shape
+            c = W.geom["img_align.conv0"].cout
+            gap = torch.zeros(n, c, device=dev)
+            for i in range(n):                                        # AdaptiveAvgPool2d(1)
+                ops.call("aldi_colsum", h[i], dtc, 1, ho * wo, 0, cp, c, 1.0 / (ho * wo), gap[i])
+            dgap = torch.empty(n, c, device=dev)
+            ops.call("aldi_domain_head_loss", gap, _l.F32, n, c, c, None, 0, W.view("img_align.out", "weight"),
+                     W.view("img_align.out", "bias"), label, cfg.img_da_weight, gscale, 0, dgap, None, c,
+                     W.view("img_align.out", "weight", G), W.view("img_align.out", "bias", G), loss_out[0:1])
+            saved["img"] = (x, h, dgap)
+        if cfg.ins_da_enabled:
+            if len(cfg.ins_da_hidden_dims) != 1:
+                raise NotImplementedError("instance-level discriminator: exactly one hidden layer is implemented "
+                                          "(DOMAIN_ADAPT.ALIGN.INS_DA_HIDDEN_DIMS default [1024])")
+            hf = self.conv(W, "ins_align.fc0", f2, relu=True)        # f2: (1, 1, M, 1024) box-head output
+            m, cp = hf.shape[2], hf.shape[3]
+            c = W.geom["ins_align.fc0"].cout
+            dh = torch.empty_like(hf)
+            ndh = torch.empty_like(hf)
+            if cp > c:
+                dh.zero_(); ndh.zero_()
+            ops.call("aldi_domain_head_loss", hf, dtc, m, c, cp, roi_count, roi_batch_size,
+                     W.view("ins_align.out", "weight"), W.view("ins_align.out", "bias"), label, cfg.ins_da_weight, gscale,
+                     1, dh, ndh, cp, W.view("ins_align.out", "weight", G), W.view("ins_align.out", "bias", G),
+                     loss_out[1:2])
+            saved["ins"] = (f2, dh, ndh)
+        return saved
+
+    def _align_img_backward(self, W, G, saved, dP_layer):
+        """grad_reverse(features) -> Conv2d(valid) -> ReLU -> GAP: the conv's own gradients use dh, the features
+        receive the data gradient of -dh (aldi/helpers.py:51-63 multiplies by -1)."""
+        x, h, dgap = saved
+        dtc = _l.BF16 if W.dtype == torch.bfloat16 else _l.F32
+        n, ho, wo, cp = h.shape
+        dh, ndh = torch.empty_like(h), torch.empty_like(h)
+        ops.call("aldi_gap_backward", h, dgap, dtc, n, ho * wo, cp, W.geom["img_align.conv0"].cout, 1.0 / (ho * wo), dh, ndh)
+        self._wgrad(W, G, "img_align.conv0", x, dh)
+        self._dgrad(W, "img_align.conv0", ndh, dP_layer, accumulate=True)
+
     # ---- backward -------------------------------------------------------------------------------------
     def _wgrad(self, W, G, name, x, dy):
         g = W.geom[name]
@@ -429,7 +487,8 @@ class Detector:
                  cout_store=g.cin)
         return out
 
-    def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch, on_ready=None):
+    def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch, on_ready=None,
+                 align=None):
         """Accumulate d(loss)/d(params) into the flat gradient buffer G.
         d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64).
         on_ready(tag): called when a bucket of G ("heads", "fpn", "res5", "res4", "res3") has received its last
@@ -437,19 +496,27 @@ class Detector:
         on_ready = on_ready or (lambda tag: None)
         dt = W.dtype
         dtc = _l.BF16 if dt == torch.bfloat16 else _l.F32
-        dev = d_rpn.device
-        n = d_rpn.shape[0]
+        dev = feats["p2"].device
+        n = feats["p2"].shape[0]
         # ---- box head: predictor -> fc2 -> fc1 -> RoIAlign scatter
         dP = {}
-        for l in (2, 3, 4, 5):
-            dP[l] = torch.zeros_like(feats["p%d" % l])
-        if dpred is not None:
+        ins = (align or {}).get("ins")
+        if dpred is None and ins is None:
+            for l in (2, 3, 4, 5):
+                dP[l] = torch.zeros_like(feats["p%d" % l])
+        else:
             x, f1, f2 = head_saved
-            m = dpred.shape[0]
-            dy = dpred.view(1, 1, m, dpred.shape[1])
-            self._wgrad(W, G, "predictor", f2, dy)
+            m = f2.shape[2]
             df2 = torch.empty_like(f2)
-            self._dgrad(W, "predictor", dy, df2, mask=f2)
+            if dpred is not None:
+                dy = dpred.view(1, 1, m, dpred.shape[1])
+                self._wgrad(W, G, "predictor", f2, dy)
+                self._dgrad(W, "predictor", dy, df2, mask=f2)
+            if ins is not None:
+                # instance-level discriminator: its hidden layer learns from dh, the box head receives -dh
+                _, dh, ndh = ins
+                self._wgrad(W, G, "ins_align.fc0", f2, dh)
+                self._dgrad(W, "ins_align.fc0", ndh, df2, mask=f2, accumulate=dpred is not None)
             self._wgrad(W, G, "fc2", f1, df2)
             df1 = torch.empty_like(f1)
             self._dgrad(W, "fc2", df2, df1, mask=f1)
@@ -461,7 +528,9 @@ class Detector:
             ops.roi_align(plv, rois, roi_batch, dout=dx.view(m, 7, 7, 256), dfeats=dfeat,
                           scales=[1.0 / s for s in FPN_STRIDES[:4]])
             for l, d in zip((2, 3, 4, 5), dfeat):
-                ops.call("aldi_add_f32", dP[l], dtc, d, d.numel())
+                # first writer of dP[l]: the fp32 scatter map becomes the activation-dtype gradient (no memset + add)
+                dP[l] = torch.empty_like(feats["p%d" % l])
+                ops.call("aldi_cast_f32", dP[l], dtc, d, d.numel())
             del dfeat, dx, df1, df2
         # ---- RPN head (weights shared over the 5 levels)
         if d_rpn is not None:
@@ -477,6 +546,10 @@ class Detector:
                 tgt = dP[l] if l < 6 else dP[5][:, ::2, ::2, :]
                 self._dgrad(W, "rpn_conv", dt_, tgt, accumulate=True)
                 del dt_
+        if align and "img" in align:
+            lname = align["img_layer"]
+            tgt = dP[int(lname[1])] if lname != "p6" else dP[5][:, ::2, ::2, :]
+            self._align_img_backward(W, G, align["img"], tgt)
         on_ready("heads")
         # ---- FPN: p_l = output_l(prev_l); prev_l = lateral_l(res_l) + up2(prev_{l+1})
         dprev, dres = {}, {}

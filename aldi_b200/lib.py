@@ -96,6 +96,10 @@ SIGNATURES = {
     "aldi_maxpool3x3s2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_sum2x2_accum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_add_f32": (c_int, [P, c_int, P, c_size_t, P]),
+    "aldi_cast_f32": (c_int, [P, c_int, P, c_size_t, P]),
+    "aldi_gap_backward": (c_int, [P, P, c_int, c_int, c_ll, c_int, c_int, c_float, P, P, P]),
+    "aldi_domain_head_loss": (c_int, [P, c_int, c_int, c_int, c_ll, P, c_int, P, P, c_float, c_float, c_float, c_int, P, P,
+                                      c_ll, P, P, P, P]),
     "aldi_colsum": (c_int, [P, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_float, P, P]),
     "aldi_frozenbn_fold": (c_int, [P, P, P, P, c_float, P, P, c_int, P]),
     "aldi_roi_align_forward": (c_int, [ctypes.POINTER(RoiAlignParams), P]),

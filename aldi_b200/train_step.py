@@ -30,6 +30,13 @@ from .detector import Detector, DetectorWeights, FlatLayout
 
 SRC_KEYS = ("loss_cls", "loss_box_reg", "loss_rpn_cls", "loss_rpn_loc")
 SOFT_KEYS = ("loss_obj_bce", "loss_rpn_l1", "loss_cls_ce", "loss_roih_l1")
+DA_KEYS = ("loss_da_img", "loss_da_ins")
+# slots of the device-side loss vector (one D2H read per step): per source tag 4 hard + 2 alignment losses, the
+# target_weak alignment pass, then the distillation pass (4 hard + 4 soft); the last slot stays 0 (the reference's
+# `_da` placeholder, aldi/align.py:91-100)
+LOSS_SLOTS = 32
+SLOT_BASE = {"source_weak": 0, "source_strong": 6, "target_weak": 12, "distill": 14}
+SLOT_ZERO = LOSS_SLOTS - 1
 
 
 class StepConfig:
@@ -61,12 +68,32 @@ class StepConfig:
         self.test_score_thresh = 0.05
         self.test_nms_thresh = 0.5
         self.test_topk = 100
+        # DOMAIN_ADAPT.ALIGN.* (aldi/config.py:38-49); both off in every shipped ALDI++ config
+        self.img_da_enabled = False
+        self.img_da_layer = "p2"
+        self.img_da_weight = 0.01
+        self.img_da_input_dim = 256
+        self.img_da_hidden_dims = (256,)
+        self.ins_da_enabled = False
+        self.ins_da_weight = 0.01
+        self.ins_da_input_dim = 1024
+        self.ins_da_hidden_dims = (1024,)
         self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": parity path
         self.cuda_graph = False                  # replay each micro-batch as a captured CUDA graph (2nd use onwards)
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError("unknown StepConfig field %s" % k)
             setattr(self, k, v)
+
+    @property
+    def do_align(self):                          # aldi/trainer.py:48
+        return bool(self.img_da_enabled or self.ins_da_enabled)
+
+    def align_spec(self):
+        if not self.do_align:
+            return None
+        return {"img": (self.img_da_input_dim, tuple(self.img_da_hidden_dims)) if self.img_da_enabled else None,
+                "ins": (self.ins_da_input_dim, tuple(self.ins_da_hidden_dims)) if self.ins_da_enabled else None}
 
     @property
     def distill_enabled(self):                   # aldi/distill.py:140-142
@@ -191,7 +218,7 @@ class B200TrainStep:
         self.dtype = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
         self.dtc = _l.BF16 if cfg.dtype == "bf16" else _l.F32
         _l.load()  # fail loudly if the CUDA library is missing
-        self.layout = FlatLayout(cfg.num_classes)
+        self.layout = FlatLayout(cfg.num_classes, align=cfg.align_spec())
         self.det = Detector(cfg.num_classes)
         flat = self.layout.pack_state_dict(state_dict).to(self.device)
         tflat = flat.clone() if teacher_state_dict is None else \
@@ -204,7 +231,7 @@ class B200TrainStep:
         self.momentum_buf = torch.zeros(self.nt, device=self.device)
         self.student.refresh()
         self.teacher.refresh()
-        self.loss_acc = torch.zeros(16, device=self.device)
+        self.loss_acc = torch.zeros(LOSS_SLOTS, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pg = process_group
         self.reducer = GradReducer(self.layout, self.grad, process_group)
@@ -251,31 +278,49 @@ class B200TrainStep:
         # ---- plan the micro-batches (same order and seed draws as the reference loops), then run them with the
         # NEXT micro-batch's host->device staging overlapped on a copy stream whenever it uses other buffers
         plan = []
+        do_align = cfg.do_align
+        da_on = (cfg.img_da_enabled, cfg.ins_da_enabled)
         for tag, d in (("source_weak", labeled_weak), ("source_strong", labeled_strong)):
             if d is None:
                 continue
+            base = SLOT_BASE[tag]
             for i in range(0, len(d), mb):
-                plan.append({"kind": "source", "parts": [("source", d[i:i + mb], True)], "seed": self.seed})
-            out_keys += [(k + "_" + tag, j) for j, k in enumerate(SRC_KEYS)]
+                plan.append({"kind": "source", "parts": [("source", d[i:i + mb], True)], "seed": self.seed, "base": base})
+            out_keys += [(k + "_" + tag, base + j) for j, k in enumerate(SRC_KEYS)]
+            out_keys += [(k + "_" + tag, base + 4 + j) for j, (k, on) in enumerate(zip(DA_KEYS, da_on)) if on]
+        if do_align:
+            # weakly-augmented target imagery, domain label 0, alignment losses only (aldi/trainer.py:107-109)
+            assert unlabeled_weak is not None, "domain alignment needs unlabeled (target) data"
+            base = SLOT_BASE["target_weak"]
+            for i in range(0, len(unlabeled_weak), mb):
+                plan.append({"kind": "align_target", "parts": [("target", unlabeled_weak[i:i + mb], False)],
+                             "seed": self.seed, "base": base})
+            out_keys += [(k + "_target_weak", base + j) for j, (k, on) in enumerate(zip(DA_KEYS, da_on)) if on]
         if do_distill:
             assert len(unlabeled_weak) == len(unlabeled_strong), "Teacher and student data must be the same length."
+            base = SLOT_BASE["distill"]
             for i in range(0, len(unlabeled_weak), mb):
                 seed = random.randint(0, 2 ** 32 - 1)       # seeder.reset_seed(), aldi/distill.py:150
-                plan.append({"kind": "distill", "seed": seed,
+                plan.append({"kind": "distill", "seed": seed, "base": base,
                              "parts": [("weak", unlabeled_weak[i:i + mb], False), ("strong", unlabeled_strong[i:i + mb], False)]})
-            out_keys += [(k + "_distill", 4 + j) for j, k in enumerate(SRC_KEYS)]
+            out_keys += [(k + "_distill", base + j) for j, k in enumerate(SRC_KEYS)]
             soft_on = (cfg.do_obj_dst, cfg.do_rpn_reg_dst, cfg.do_cls_dst, cfg.do_roih_reg_dst)
-            out_keys += [(k + "_distill", 8 + j) for j, (k, on) in enumerate(zip(SOFT_KEYS, soft_on)) if on]
+            out_keys += [(k + "_distill", base + 4 + j) for j, (k, on) in enumerate(zip(SOFT_KEYS, soft_on)) if on]
+            if do_align:
+                # the student's forward inside the distiller returns the `_da` placeholder (aldi/align.py:91-100),
+                # which passes the distill key filter `k != "_"` (aldi/trainer.py:113) as a zero
+                out_keys.append(("_da_distill", SLOT_ZERO))
         for i, item in enumerate(plan):
-            item["pass_id"] = i if item["kind"] == "source" else 100 + i
+            item["pass_id"] = 100 + i if item["kind"] == "distill" else i
             item["keys"] = [(kind,) + MicroBatch.shape_key(d, gt) for kind, d, gt in item["parts"]]
             self.seed_log[item["pass_id"]] = item["seed"]
         for i, item in enumerate(plan):
             self.seed = item["seed"]
             self._last_backward = i == len(plan) - 1
             mbs = item.get("staged") or self._stage(item, None)
-            body = self._source_body if item["kind"] == "source" else self._distill_body
-            self._run(tuple(item["keys"]) + (gscale, self._last_backward), lambda: body(*mbs, gscale, item["pass_id"]))
+            body = {"source": self._source_body, "distill": self._distill_body, "align_target": self._align_target_body}[item["kind"]]
+            self._run(tuple(item["keys"]) + (gscale, self._last_backward, item["base"]),
+                      lambda: body(*mbs, gscale, item["pass_id"], item["base"]))
             if self.device.type == "cuda":
                 for m in mbs:
                     m.free_event = torch.cuda.Event()
@@ -380,20 +425,41 @@ class B200TrainStep:
         torch.cuda.current_stream().wait_stream(cs)
         return chain
 
-    def _source_body(self, b, gscale, pass_id):
+    def _source_body(self, b, gscale, pass_id, base=SLOT_BASE["source_strong"]):
         cfg, det, W = self.cfg, self.det, self.student
         fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=True)
         n = b.n
         d_rpn = torch.zeros(n, fw["lv"].total_locs, 64, device=self.device, dtype=self.dtype)
         ops.call("aldi_rpn_loss", fw["rpn_out"], _l.ctypes.byref(fw["lv"]), n, fw["labels"], fw["matched"], b.gt.boxes,
-                 b.gt.counts, b.gt.gmax, cfg.rpn_batch, 1.0, 1.0, gscale, d_rpn, self.dtc, 64, 0, self.loss_acc[2:4])
+                 b.gt.counts, b.gt.gmax, cfg.rpn_batch, 1.0, 1.0, gscale, d_rpn, self.dtc, 64, 0,
+                 self.loss_acc[base + 2:base + 4])
         m = n * cfg.roi_batch
         dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
         ops.call("aldi_roi_loss", fw["pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"], fw["rois"], fw["roi_gt"],
                  fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)), 1.0, 1.0, gscale, dpred, self.dtc, 64,
-                 self.loss_acc[0:2])
+                 self.loss_acc[base:base + 2])
+        align = self._align(fw, True, gscale, self.loss_acc[base + 4:base + 6])
         det.backward(W, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"], dpred,
-                     fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready())
+                     fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), align=align)
+
+    def _align(self, fw, labeled, gscale, loss_out):
+        """AlignMixin.forward(do_align=True) on a finished student forward (aldi/align.py:74-90)."""
+        if not self.cfg.do_align:
+            return None
+        saved = self.det.align_forward(self.student, self.grad, fw["feats"], fw["head_saved"][2], fw["roi_count"],
+                                       self.cfg.roi_batch, self.cfg, labeled, gscale, loss_out)
+        saved["img_layer"] = self.cfg.img_da_layer
+        return saved
+
+    def _align_target_body(self, b, gscale, pass_id, base=SLOT_BASE["target_weak"]):
+        """aldi/trainer.py:107-109: model(unlabeled_weak, labeled=False, do_align=True) — a training-mode student
+        forward on target images with EMPTY ground truth (aldi/dataloader.py:21-30), of which only the `_da_` losses
+        are kept and back-propagated (the detection losses are multiplied by 0, aldi/trainer.py:75-77)."""
+        det, W = self.det, self.student
+        fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=False)
+        align = self._align(fw, False, gscale, self.loss_acc[base:base + 2])
+        det.backward(W, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], None, fw["lv"], fw["head_saved"], None,
+                     fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), align=align)
 
     def _student_forward(self, b, gt, pass_id, want_rpn_labels):
         cfg, det, W = self.cfg, self.det, self.student
@@ -465,7 +531,7 @@ class B200TrainStep:
         return GroundTruth(gb, gc, cnt, gmax, gs), dets
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
-    def _distill_body(self, bw, bs, gscale, pass_id):
+    def _distill_body(self, bw, bs, gscale, pass_id, base=SLOT_BASE["distill"]):
         cfg, det = self.cfg, self.det
         n = bw.n
         t_feats, t_lv, t_rpn_out = self.teacher_forward(bw)
@@ -487,11 +553,11 @@ class B200TrainStep:
         if hard_rpn:
             ops.call("aldi_rpn_loss", fw["rpn_out"], _l.ctypes.byref(lv), n, fw["labels"], fw["matched"], pseudo.boxes,
                      pseudo.counts, pseudo.gmax, cfg.rpn_batch, 1.0 if cfg.do_hard_obj else 0.0,
-                     1.0 if cfg.do_hard_rpn_reg else 0.0, gscale, d_rpn, self.dtc, 64, 0, self.loss_acc[6:8])
+                     1.0 if cfg.do_hard_rpn_reg else 0.0, gscale, d_rpn, self.dtc, 64, 0, self.loss_acc[base + 2:base + 4])
             acc = 1
         ops.call("aldi_distill_rpn_loss", fw["rpn_out"], t_rpn_out, _l.ctypes.byref(lv), n, labels, stats,
                  cfg.obj_temperature, 1.0 if cfg.do_obj_dst else 0.0, 1.0 if cfg.do_rpn_reg_dst else 0.0, gscale, d_rpn,
-                 self.dtc, 64, acc, self.loss_acc[8:10])
+                 self.dtc, 64, acc, self.loss_acc[base + 4:base + 6])
         m = n * cfg.roi_batch
         dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
         acc = 0
@@ -499,12 +565,12 @@ class B200TrainStep:
             ops.call("aldi_roi_loss", fw["pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"], fw["rois"],
                      fw["roi_gt"], fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)),
                      1.0 if cfg.do_hard_cls else 0.0, 1.0 if cfg.do_hard_roi_reg else 0.0, gscale, dpred, self.dtc, 64,
-                     self.loss_acc[4:6])
+                     self.loss_acc[base:base + 2])
             acc = 1
         ops.call("aldi_distill_roi_loss", fw["pred"], t_pred, det.PRED_CH, m, cfg.num_classes, fw["roi_class"],
                  fw["roi_count"], n, cfg.cls_temperature, 1 if cfg.cls_loss_type == "KL" else 0,
                  1.0 if cfg.do_cls_dst else 0.0, 1.0 if cfg.do_roih_reg_dst else 0.0, gscale, dpred, self.dtc, 64, acc,
-                 self.loss_acc[10:12])
+                 self.loss_acc[base + 6:base + 8])
         self.debug = {"fw": fw, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": labels, "stats": stats,
                       "pseudo": pseudo} if self.debug is not None else None
         det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, lv, fw["head_saved"],

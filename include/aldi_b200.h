@@ -152,6 +152,8 @@ int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, int h, int w,
 /* coarse[n,h,w,c] += sum of the 2x2 block of fine (backward of nearest-2x upsample + add in FPN top-down) */
 int aldi_sum2x2_accum(const void* fine, void* coarse, int dtype, int n, int h, int w, int c, void* stream);
 int aldi_add_f32(void* dst, int dtype, const float* src, size_t n, void* stream);
+/* dst = (dtype) src: the fp32 RoIAlign gradient map becomes the activation-dtype gradient of p2..p5 (first writer) */
+int aldi_cast_f32(void* dst, int dtype, const float* src, size_t n, void* stream);
 /* out[ch] += scale * sum over images and rows of x[img*img_stride + row*row_stride + ch]  (bias gradients;
  * strides in elements, rows 16-byte aligned) */
 int aldi_colsum(const void* x, int dtype, int n_img, long long rows, long long img_stride, long long row_stride, int c,
@@ -250,6 +252,18 @@ int aldi_distill_roi_loss(const float* student_pred, const float* teacher_pred, 
 /* aldi/align.py:81-90: loss_out[0] += weight * mean BCE-with-logits(pred, domain_label) */
 int aldi_domain_bce_loss(const float* pred, int n, int stride, float domain_label, float weight, float gscale,
                          void* dpred, int dtype, int dstride, float* loss_out, void* stream);
+/* aldi/align.py:81-90,103-136: the discriminator's last Linear(C,1) + BCE-with-logits (mean over valid rows) against
+ * the constant domain label, fused with that layer's gradients: loss_out[0] += weight*gscale*mean BCE;
+ * dw[C] += sum_r dl[r]*feat[r]; db[0] += sum_r dl[r]; dfeat[r] = dl[r]*w (gated by feat>0 when relu_mask) and
+ * ndfeat = -dfeat (nullable; operand of the gradient-reversed data gradient, aldi/helpers.py:51-63).
+ * counts (nullable): row r is valid iff (r % rows_per_image) < counts[r / rows_per_image]. */
+int aldi_domain_head_loss(const void* feat, int dtype, int n, int c, long long feat_stride, const int* counts,
+                          int rows_per_image, const float* w, const float* b, float domain_label, float weight,
+                          float gscale, int relu_mask, void* dfeat, void* ndfeat, long long d_stride, float* dw,
+                          float* db, float* loss_out, void* stream);
+/* backward of ReLU -> AdaptiveAvgPool2d(1) (aldi/align.py:113): dh[n,p,ch] = h>0 ? dgap[n,ch]*scale : 0, ndh = -dh */
+int aldi_gap_backward(const void* h, const float* dgap, int dtype, int n, long long pix, int c_p, int c, float scale,
+                      void* dh, void* ndh, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,27 +22,35 @@ def install_device_sampler(seed_log):
     d2.set_sample_chooser(chooser)
 
 
-def make_inputs(seed, n_l, n_u, h, w, teacher_mix=0.05):
-    s = arch.synthetic_state_dict(seed=seed)
-    o = arch.synthetic_state_dict(seed=seed + 1000)
+ALIGN = {"img": (256, (256,)), "ins": (1024, (1024,))}
+
+
+def make_inputs(seed, n_l, n_u, h, w, teacher_mix=0.05, align=None):
+    s = arch.synthetic_state_dict(seed=seed, align=align)
+    o = arch.synthetic_state_dict(seed=seed + 1000, align=align)
     t = {k: (1 - teacher_mix) * s[k] + teacher_mix * o[k] for k in s}
     ls, uw, us = synth_data.synthetic_batch(seed, n_l, n_u, h, w)
     return s, t, ls, uw, us
 
 
-def to_d2(batch, labeled):
+def to_d2(batch, labeled, empty_instances=False):
+    """empty_instances: what the reference's UnlabeledDatasetMapper attaches to target images
+    (aldi/dataloader.py:21-30) — needed whenever the student runs in training mode on them before pseudo-labelling."""
     out = []
     for d in batch:
         e = {"image": d["image"].clone(), "height": d["height"], "width": d["width"]}
         if labeled:
             e["instances"] = d2.Instances((d["height"], d["width"]), gt_boxes=d2.Boxes(d["boxes"].clone()),
                                           gt_classes=d["classes"].clone())
+        elif empty_instances:
+            e["instances"] = d2.Instances((d["height"], d["width"]), gt_boxes=d2.Boxes(torch.zeros(0, 4)),
+                                          gt_classes=torch.zeros(0, dtype=torch.int64))
         out.append(e)
     return out
 
 
-def oracle_models(sd_s, sd_t):
-    student, teacher = aldi_ref.ALDI(num_classes=8), aldi_ref.ALDI(num_classes=8)
+def oracle_models(sd_s, sd_t, **kw):
+    student, teacher = aldi_ref.ALDI(num_classes=8, **kw), aldi_ref.ALDI(num_classes=8, **kw)
     student.load_state_dict(sd_s)
     teacher.load_state_dict(sd_t)
     return student.train(), teacher.train()
@@ -77,13 +85,13 @@ def oracle_grads_internal(layout, model):
     return out
 
 
-def predict_seed_log(py_seed, n_source_mb, n_distill_mb):
+def predict_seed_log(py_seed, n_source_mb, n_distill_mb, n_align_mb=0):
     """The sampling seeds B200TrainStep.run_model will draw after random.seed(py_seed)."""
     rng = random.Random(py_seed)
     log = {}
     s0 = rng.randint(0, 2 ** 32 - 1)
     p = 0
-    for _ in range(n_source_mb):
+    for _ in range(n_source_mb + n_align_mb):
         log[p] = s0
         p += 1
     for _ in range(n_distill_mb):

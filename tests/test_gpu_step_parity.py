@@ -173,3 +173,31 @@ def test_ragged_batch_and_empty_gt_match_oracle():
     check_losses(dev_losses, ora)
     worst = check_grads(step, student)
     print("ragged/empty-gt: losses", dev_losses, "worst grad rel err", worst)
+
+
+def test_domain_alignment_step_matches_oracle():
+    """image- and instance-level discriminators behind gradient reversal (aldi/align.py:71-136) on
+    source (label 1) and target_weak (label 0, empty GT) passes, together with the distillation pass; the
+    `_da_distill` placeholder key of the reference (aldi/align.py:91-100) must be present and zero."""
+    n_l = n_u = mb = 2
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(53, n_l, n_u, 128, 160, align=pu.ALIGN)
+    kw = dict(img_da_enabled=True, ins_da_enabled=True, img_da_weight=0.5, ins_da_weight=0.25)
+    pu.install_device_sampler(pu.predict_seed_log(1234, 1, 1, n_align_mb=1))
+    student, teacher = pu.oracle_models(sd_s, sd_t, **kw)
+    dist = aldi_ref.ALDIDistiller(teacher, student, **pu.SOFT)
+    uw_o, us_o = pu.to_d2(uw, False, empty_instances=True), pu.to_d2(us, False, empty_instances=True)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, pu.to_d2(ls, True), uw_o, us_o), mb, False,
+                                                   lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    override = [pu.pseudo_to_device([d["instances"] for d in uw_o], "cuda")]
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, uw, us), pseudo_override=override, ims_per_gpu=mb, **kw)
+    assert step.seed_log == pu.predict_seed_log(1234, 1, 1, n_align_mb=1)
+    for k in ("loss_da_img_source_strong", "loss_da_ins_source_strong", "loss_da_img_target_weak",
+              "loss_da_ins_target_weak", "_da_distill"):
+        assert k in dev_losses, (k, sorted(dev_losses))
+    assert dev_losses["_da_distill"] == 0.0
+    assert dev_losses["loss_da_img_source_strong"] > 0 and dev_losses["loss_da_ins_target_weak"] > 0
+    check_losses(dev_losses, ora)
+    worst = check_grads(step, student)
+    print("alignment step: losses", dev_losses, "worst grad rel err", worst)
