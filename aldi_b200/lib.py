@@ -60,6 +60,17 @@ class RoiAlignParams(ctypes.Structure):
     ]
 
 
+class MsdaParams(ctypes.Structure):
+    _fields_ = [
+        ("value", c_void_p), ("sampling_loc", c_void_p), ("attn_weight", c_void_p),
+        ("spatial_h", ctypes.POINTER(c_int)), ("spatial_w", ctypes.POINTER(c_int)), ("level_start", ctypes.POINTER(c_int)),
+        ("n", c_int), ("s", c_int), ("m", c_int), ("d", c_int), ("lq", c_int), ("l", c_int), ("p", c_int),
+        ("dtype", c_int),
+        ("out", c_void_p), ("grad_out", c_void_p), ("grad_value", c_void_p), ("grad_loc", c_void_p),
+        ("grad_attn", c_void_p),
+    ]
+
+
 class RpnLevels(ctypes.Structure):
     _fields_ = [
         ("num_levels", c_int), ("num_anchors", c_int),
@@ -126,6 +137,8 @@ SIGNATURES = {
     "aldi_distill_roi_loss": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_float, c_int, c_float, c_float,
                                       c_float, P, c_int, c_int, c_int, P, P]),
     "aldi_domain_bce_loss": (c_int, [P, c_int, c_int, c_float, c_float, c_float, P, c_int, c_int, P, P]),
+    "aldi_msda_forward": (c_int, [ctypes.POINTER(MsdaParams), P]),
+    "aldi_msda_backward": (c_int, [ctypes.POINTER(MsdaParams), P]),
 }
 
 

@@ -28,6 +28,7 @@ extern "C" {
 
 #define ALDI_DTYPE_F32 0
 #define ALDI_DTYPE_BF16 1
+#define ALDI_DTYPE_F64 2
 
 /* ---- library bookkeeping -------------------------------------------------------------------- */
 const char* aldi_last_error(void);
@@ -264,6 +265,33 @@ int aldi_domain_head_loss(const void* feat, int dtype, int n, int c, long long f
 /* backward of ReLU -> AdaptiveAvgPool2d(1) (aldi/align.py:113): dh[n,p,ch] = h>0 ? dgap[n,ch]*scale : 0, ndh = -dh */
 int aldi_gap_backward(const void* h, const float* dgap, int dtype, int n, long long pix, int c_p, int c, float scale,
                       void* dh, void* ndh, void* stream);
+
+/* ---- multi-scale deformable attention (Deformable-DETR, BASELINE configs[3]) --------------------------------------
+ * Replaces MSDA.ms_deform_attn_forward / ms_deform_attn_backward of the reference's CUDA extension
+ * (aldi/detr/libs/DeformableDETRDetectron2/deformable_detr/models/ops/src/vision.cpp:13-16,
+ * src/ms_deform_attn.h:21-62, called from functions/ms_deform_attn_func.py:24-36).  Same tensors, same layouts:
+ * value (N,S,M,D); sampling_loc (N,Lq,M,L,P,2) as (x,y) in [0,1]; attn_weight (N,Lq,M,L,P); out / grad_out (N,Lq,M*D).
+ * spatial_h/w and level_start are HOST arrays of L ints (the reference passes device int64 tensors and reads them in
+ * every thread).  dtype F32 or F64 (what the reference dispatches).  grad_value must be zero-filled by the caller
+ * (it is accumulated with atomics); grad_loc and grad_attn are fully overwritten.  The reference's im2col_step only
+ * batches its launches and has no numerical effect; the host mirror keeps its `N % im2col_step == 0` check. */
+typedef struct {
+  const void* value;
+  const void* sampling_loc;
+  const void* attn_weight;
+  const int* spatial_h;     /* host, L */
+  const int* spatial_w;     /* host, L */
+  const int* level_start;   /* host, L */
+  int n, s, m, d, lq, l, p;
+  int dtype;
+  void* out;                /* forward */
+  const void* grad_out;     /* backward */
+  void* grad_value;
+  void* grad_loc;
+  void* grad_attn;
+} aldi_msda_params;
+int aldi_msda_forward(const aldi_msda_params* p, void* stream);
+int aldi_msda_backward(const aldi_msda_params* p, void* stream);
 
 #ifdef __cplusplus
 }
