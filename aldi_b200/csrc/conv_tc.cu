@@ -45,7 +45,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiChunk = 64;                    // channels per epilogue chunk (128-byte rows)
 constexpr int kEpiBytes = kBlockM * kEpiChunk * 2;  // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kMaxEpiBufs = 4;
+constexpr int kMaxEpiBufs = 8;
 constexpr int kSmemLimit = 226 * 1024;     // dynamic budget (static barriers etc. live in the remaining 1 KB)
 
 struct ConvArgs {
@@ -70,6 +70,8 @@ struct ConvArgs {
   int tma_epi;       // bf16 output through shared memory + TMA store
   int epi_res, epi_mask;  // residual / mask tiles arrive by TMA (tma_epi only)
   int epi_bufs;      // depth of the residual / mask tile ring (2..4): bytes in flight for the HBM-bound layers
+  int epi_prefetch;  // tiles ahead whose residual / mask boxes warp 2 prefetches into the L2 (0 = off)
+  int a_prefetch;    // K blocks ahead of the smem ring whose A boxes warp 0 prefetches into the L2 (0 = off)
   int debug;         // ALDI_CONV_DEBUG (perf bisection only): 1 no TMA store, 2 also no smem staging, 3 empty epilogue
 };
 
@@ -181,6 +183,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int thi = m_tile % a.tiles_h;
         const int img = m_tile / a.tiles_h;
         const int h0 = thi * a.th, w0 = twi * a.tw;
+        if (a.a_prefetch) {
+          // 1x1 layers stream x straight from HBM: warm the L2 with the NEXT tile's A boxes while this tile runs
+          const int nt = tile + gridDim.x;
+          if (nt < a.num_tiles) {
+            int mt = nt / a.num_n_tiles;
+            const int pw = mt % a.tiles_w;
+            mt /= a.tiles_w;
+            const int ph = mt % a.tiles_h;
+            const int pi = mt / a.tiles_h;
+            for (int kc = 0; kc < a.kchunks; ++kc)
+              tma_prefetch_4d(&tmA, kc * kBlockK, pw * a.tw - a.pad_w, ph * a.th - a.pad_h, pi);
+          }
+        }
         for (int kb = 0; kb < a.num_kb; ++kb) {
           const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
           const int r = tap / a.taps_w, s = tap - r * a.taps_w;
@@ -231,7 +246,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       const uint32_t res_bytes = a.res_mode == 2 ? kEpiBytes / 4 : kEpiBytes;
       const uint32_t bytes = (a.epi_res ? res_bytes : 0u) + (a.epi_mask ? (uint32_t)kEpiBytes : 0u);
+      // the residual / mask tiles are cold in HBM and the ring is only 2-4 chunks deep: warm the L2 `epi_prefetch`
+      // tiles ahead so the ring's loads see L2 latency instead of DRAM latency
+      auto prefetch_tile = [&](int t) {
+        if (t >= a.num_tiles) return;
+        const int nt = t % a.num_n_tiles;
+        int mt = t / a.num_n_tiles;
+        const int pw = mt % a.tiles_w;
+        mt /= a.tiles_w;
+        const int ph = mt % a.tiles_h;
+        const int pi = mt / a.tiles_h;
+        for (int c0 = 0; c0 < BLOCK_N; c0 += kEpiChunk) {
+          const int cb = nt * BLOCK_N + c0;
+          if (a.epi_res) {
+            if (a.res_mode == 2) tma_prefetch_4d(&tmR, cb, (pw * a.tw) >> 1, (ph * a.th) >> 1, pi);
+            else tma_prefetch_4d(&tmR, cb, pw * a.tw, ph * a.th, pi);
+          }
+          if (a.epi_mask) tma_prefetch_4d(&tmM, cb, pw * a.tw, ph * a.th, pi);
+        }
+      };
+      for (int d = 1; d < a.epi_prefetch; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        if (a.epi_prefetch) prefetch_tile(tile + a.epi_prefetch * gridDim.x);
         const int n_tile = tile % a.num_n_tiles;
         int m_tile = tile / a.num_n_tiles;
         const int twi = m_tile % a.tiles_w;
@@ -618,6 +654,8 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   const int res_mode = (tma_epi && p->accumulate) ? 1 : p->res_mode;
 
   int block_n = (p->cout_p % 256 == 0) ? 256 : (p->cout_p % 128 == 0) ? 128 : 64;
+  static const char* force_bn = getenv("ALDI_CONV_BN");  // perf bisection only: cap the N tile
+  if (force_bn && atoi(force_bn) >= 64 && atoi(force_bn) < block_n && p->cout_p % atoi(force_bn) == 0) block_n = atoi(force_bn);
   // shared-memory plan: [stages x (A | B)] [2 output chunks] [epi_bufs x (residual chunk, mask chunk)].
   // Keep >= 3 pipeline stages (narrowing the N tile if needed), then deepen the residual/mask ring up to 4 —
   // for the HBM-bound 1x1 layers the bytes in flight per SM are what sets the achieved bandwidth.
@@ -637,7 +675,13 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   static const char* force_stages = getenv("ALDI_CONV_STAGES");  // perf bisection only
   if (force_stages && atoi(force_stages) >= 1 && atoi(force_stages) < stages) stages = atoi(force_stages);
-  const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
+  // whatever the stage granularity leaves over deepens the residual / mask ring for free
+  int epi_total = epi_bytes;
+  while (set_bytes && epi_bufs < kMaxEpiBufs && stages * stage_bytes + epi_total + set_bytes + 1024 <= kSmemLimit) {
+    ++epi_bufs;
+    epi_total += set_bytes;
+  }
+  const int smem_bytes = stages * stage_bytes + epi_total + 1024;
 
   int th, tw;
   pick_patch(p->ho, p->wo, (tma_epi && res_mode == 2) ? 64 : 128, &th, &tw);
@@ -669,6 +713,12 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   a.stages = stages;
   a.tma_epi = tma_epi; a.epi_res = epi_res; a.epi_mask = epi_mask;
   a.epi_bufs = epi_bufs;
+  static const char* epf = getenv("ALDI_EPI_PREFETCH");
+  static const char* apf = getenv("ALDI_A_PREFETCH");
+  // measured (tools/gpu_diag.py perf_res4): L2 prefetching costs 5-15 % on these layers — they are bound by L2
+  // throughput, not latency, and a prefetch is one more pass through the L2 — so both stay off unless asked for
+  a.epi_prefetch = (epi_res || epi_mask) ? (epf ? atoi(epf) : 0) : 0;
+  a.a_prefetch = (p->taps_h * p->taps_w == 1) ? (apf ? atoi(apf) : 0) : 0;
   static const char* dbg = getenv("ALDI_CONV_DEBUG");
   a.debug = dbg ? atoi(dbg) : 0;
 

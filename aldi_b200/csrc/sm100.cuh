@@ -89,6 +89,15 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared memory, no completion tracking): pulls a tile that a later TMA load will
+// need from HBM into the L2 so that load sees L2 latency
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // TMA store (shared::cta -> global, bulk async-group completion).  The smem source must have been made visible to
 // the async proxy (fence_proxy_async) and must not be overwritten before bulk_wait_group_read lets it go.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {

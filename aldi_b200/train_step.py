@@ -618,6 +618,34 @@ class B200TrainStep:
         w = self.student if which == "student" else self.teacher
         return self.layout.unpack_state_dict(w.flat)
 
+    def load_state_dict(self, sd, which="student", strict=True):
+        """Write a Detectron2-keyed state_dict into the flat buffer of the student or the teacher and re-derive the
+        GEMM operands.  Returns (missing_keys, unexpected_keys) like nn.Module.load_state_dict; with strict=False keys
+        that are absent keep their current values and tensors of the wrong shape are reported as missing."""
+        w = self.student if which == "student" else self.teacher
+        known = {key: (layer, field, off, n, shape) for (layer, field), (off, n, key, shape) in self.layout.entries.items()}
+        missing = [k for k in known if k not in sd]
+        unexpected = [k for k in sd if k not in known]
+        bad_shape = [k for k in known if k in sd and tuple(sd[k].shape) != tuple(known[k][4])]
+        if strict and (missing or unexpected or bad_shape):
+            raise KeyError("load_state_dict(strict): missing %s unexpected %s wrong shape %s"
+                           % (missing[:5], unexpected[:5], bad_shape[:5]))
+        host = w.flat.detach().cpu()
+        for k, (layer, field, off, n, shape) in known.items():
+            if k in sd and k not in bad_shape:
+                host[off:off + n] = self.layout.to_internal(layer, field, torch.as_tensor(sd[k]).detach().to("cpu", torch.float32))
+        w.flat.copy_(host)
+        w.refresh()
+        return missing + bad_shape, unexpected
+
+    def optimizer_state(self):
+        """SGD momentum buffer keyed like the parameters (the `optimizer` checkpointable of the reference trainer)."""
+        return {"momentum_buffer": self.momentum_buf.detach().cpu().clone(), "iteration": self.iter}
+
+    def load_optimizer_state(self, state):
+        self.momentum_buf.copy_(state["momentum_buffer"].to(self.momentum_buf.device))
+        self.iter = int(state.get("iteration", self.iter))
+
 
 class LossDict(dict):
     """dict[str -> float] materialised lazily with ONE device->host read (keys known without a sync)."""

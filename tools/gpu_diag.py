@@ -451,6 +451,40 @@ def case_perf_small():
     return True
 
 
+def case_perf_res4():
+    """res4 conv3 (1x1 256->1024 + FrozenBN + residual + ReLU at 4x64x128) and conv1 (1x1 1024->256): the short
+    launches that sit far above both rooflines in the step profile; run under ncu / with the ALDI_CONV_* knobs."""
+    import torch
+    from aldi_b200 import ops
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for name, n, h, w, cin, cout, with_res in (("conv3 1x1 256->1024 +res", 4, 64, 128, 256, 1024, True),
+                                                ("conv1 1x1 1024->256", 4, 64, 128, 1024, 256, False),
+                                                ("res5 conv3 1x1 512->2048 +res", 4, 32, 64, 512, 2048, True)):
+        g = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(cout, cin, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+        res = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+        sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+        bi = torch.randn(cout, device="cuda", generator=g)
+        out = torch.empty(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+        kw = dict(scale=sc, bias=bi, relu=True)
+        if with_res:
+            kw.update(residual=res, res_mode=1)
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            e0.record()
+            ops.conv(x, wt, out, **kw)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        nbytes = (x.numel() + out.numel() * (2 if with_res else 1) + wt.numel()) * 2
+        t = sorted(ts[2:])[len(ts[2:]) // 2]
+        print("[perf_res4] %s: %.1f us (cold L2)  %.0f GB/s  %.0f TFLOP/s" % (
+            name, t, nbytes / t / 1e3, 2.0 * n * h * w * cin * cout / t / 1e6), flush=True)
+    return True
+
+
 CASES = [
     "optim", "fwd_f32", "bwd_f32",
     "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "fwd_epilogue2",
