@@ -71,6 +71,20 @@ class MsdaParams(ctypes.Structure):
     ]
 
 
+AUG_MAX_RADIUS = 8
+
+
+class AugParams(ctypes.Structure):
+    _fields_ = [
+        ("h", c_int), ("w", c_int),
+        ("src_plane", c_ll), ("src_row", c_ll), ("dst_plane", c_ll), ("dst_row", c_ll),
+        ("do_color", c_int), ("contrast_w", c_double), ("brightness_w", c_double), ("saturation_w", c_double),
+        ("do_gray", c_int), ("blur_radius", c_int), ("blur_taps", c_double * (2 * AUG_MAX_RADIUS + 1)),
+        ("num_erase", c_int), ("erase_rect", (c_int * 4) * 3), ("erase_seed", ctypes.c_uint * 3),
+        ("mic_mask", c_void_p), ("mic_h", c_int), ("mic_w", c_int),
+    ]
+
+
 class RpnLevels(ctypes.Structure):
     _fields_ = [
         ("num_levels", c_int), ("num_anchors", c_int),
@@ -137,6 +151,8 @@ SIGNATURES = {
     "aldi_distill_roi_loss": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_float, c_int, c_float, c_float,
                                       c_float, P, c_int, c_int, c_int, P, P]),
     "aldi_domain_bce_loss": (c_int, [P, c_int, c_int, c_float, c_float, c_float, P, c_int, c_int, P, P]),
+    "aldi_strong_augment_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "aldi_strong_augment": (c_int, [P, P, ctypes.POINTER(AugParams), P, c_size_t, P]),
     "aldi_msda_forward": (c_int, [ctypes.POINTER(MsdaParams), P]),
     "aldi_msda_backward": (c_int, [ctypes.POINTER(MsdaParams), P]),
 }

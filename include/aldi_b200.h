@@ -293,6 +293,30 @@ typedef struct {
 int aldi_msda_forward(const aldi_msda_params* p, void* stream);
 int aldi_msda_backward(const aldi_msda_params* p, void* stream);
 
+/* ---- strong augmentation on the device ---------------------------------------------------------------
+ * Replaces, per planar uint8 image (3, h, w), aldi/aug.py:39-60 build_strong_augmentation (+ MICTransform,
+ * aldi/aug.py:154-176) that the reference runs on dataloader workers: colour jitter / grayscale / gaussian blur over
+ * H, W and channels / up to three random-erase rectangles / MIC block mask, with the random PARAMETERS drawn by the
+ * host in the reference's RNG order.  src and dst may alias only when no blur is requested. */
+#define ALDI_AUG_MAX_RADIUS 8            /* int(4 * sigma + 0.5) for sigma <= 2.0 (aldi/aug.py:50) */
+typedef struct {
+  int h, w;
+  long long src_plane, src_row, dst_plane, dst_row; /* strides in bytes */
+  int do_color;                                      /* RandomApply(p=0.8) fired */
+  double contrast_w, brightness_w, saturation_w;     /* the three np.random.uniform(0.6, 1.4) draws */
+  int do_gray;                                       /* RandomApply(RandomSaturation(0,0), p=0.2) fired */
+  int blur_radius;                                   /* -1: no blur; else int(4*sigma+0.5) */
+  double blur_taps[2 * ALDI_AUG_MAX_RADIUS + 1];     /* scipy _gaussian_kernel1d(sigma, 0, radius), centre at [radius] */
+  int num_erase;
+  int erase_rect[3][4];                              /* h0, w0, h, w (aldi/aug.py:124-137) */
+  unsigned int erase_seed[3];                        /* fill noise = hash(seed, pixel, channel) * 255 */
+  const unsigned char* mic_mask;                     /* device (mic_h, mic_w) bytes, 1 = keep; NULL = no MIC */
+  int mic_h, mic_w;
+} aldi_aug_params;
+size_t aldi_strong_augment_workspace_bytes(int h, int w);
+int aldi_strong_augment(const unsigned char* src, unsigned char* dst, const aldi_aug_params* p, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

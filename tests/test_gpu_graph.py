@@ -62,6 +62,7 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     a.step((None, ls, uw, us))
     torch.cuda.synchronize()
     path = DetectionCheckpointerWithEMA(a, str(tmp_path)).save("model_0000000")
+    saved_teacher = a.teacher.flat.clone()
     other = arch.synthetic_state_dict(seed=77)
     b = B200TrainStep(cfg, other)
     b.debug = None
@@ -79,4 +80,4 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     c = B200TrainStep(cfg, other)
     DetectionCheckpointerWithEMA(c, str(tmp_path / "fresh")).resume_or_load(path, resume=False)
     nt = c.layout.numel
-    assert torch.equal(c.student.flat[:nt], a.teacher.flat[:nt])
+    assert torch.equal(c.student.flat[:nt], saved_teacher[:nt])
