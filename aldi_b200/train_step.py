@@ -126,6 +126,7 @@ class MicroBatch:
         self.gt = GroundTruth(self.boxes, classes, counts, gmax)
         self._full_canvas = True
         self._copied = None
+        self.scratch = None
         # recorded on the compute stream after the last consumer of these buffers (initially: after the zero-fills
         # above, which a prefetch on the copy stream must not overtake)
         self.free_event = None
@@ -135,30 +136,47 @@ class MicroBatch:
 
     @staticmethod
     def shape_key(data, with_gt):
-        hs = [int(d["image"].shape[1]) for d in data]
-        ws = [int(d["image"].shape[2]) for d in data]
+        hs = [int(d["image"].shape[1]) if d.get("image") is not None else int(d["height"]) for d in data]
+        ws = [int(d["image"].shape[2]) if d.get("image") is not None else int(d["width"]) for d in data]
         hp = (max(hs) + 31) // 32 * 32
         wp = (max(ws) + 31) // 32 * 32
         g = max([len(d["boxes"]) for d in data] + [1]) if with_gt else 1
         gmax = max(128, (g + 31) // 32 * 32)
         return len(data), hp, wp, gmax
 
-    def load(self, data, seed, pass_id, with_gt):
-        """Stage one micro-batch; returns the host->device bytes moved."""
+    def load(self, data, seed, pass_id, with_gt, weak_source=None, augmenter=None):
+        """Stage one micro-batch; returns the host->device bytes moved.
+        Items carrying "aug_params" get their strong view DERIVED ON THE DEVICE (aldi_b200/augment.py):
+        from the paired weak micro-batch `weak_source` when the item has no image of its own (unlabeled_strong), else
+        from the item's own weak image staged through a scratch canvas (labeled_strong)."""
         n, gmax = self.n, self.gmax
         if self._copied is not None:
             self._copied.synchronize()   # the pinned mirrors are free again once the previous load's copies ran
-        hs = [int(d["image"].shape[1]) for d in data]
-        ws = [int(d["image"].shape[2]) for d in data]
+        hs = [int(d["image"].shape[1]) if d.get("image") is not None else int(d["height"]) for d in data]
+        ws = [int(d["image"].shape[2]) if d.get("image") is not None else int(d["width"]) for d in data]
         same = all(h == self.hp and w == self.wp for h, w in zip(hs, ws))
         if not (same and self._full_canvas):
             self.images.zero_()
         self._full_canvas = same
         nbytes = 0
         for i, d in enumerate(data):
-            self.images[i, :, :hs[i], :ws[i]].copy_(d["image"], non_blocking=True)
-            if not d["image"].is_cuda:
-                nbytes += d["image"].numel()
+            params = d.get("aug_params")
+            img = d.get("image")
+            if params is None:
+                self.images[i, :, :hs[i], :ws[i]].copy_(img, non_blocking=True)
+            else:
+                assert augmenter is not None, "items with aug_params need a StrongAugmenter"
+                if img is not None:
+                    if self.scratch is None:
+                        self.scratch = torch.zeros_like(self.images[0])
+                    self.scratch[:, :hs[i], :ws[i]].copy_(img, non_blocking=True)
+                    src = self.scratch
+                else:
+                    assert weak_source is not None, "an image-less strong item needs its weak micro-batch"
+                    src = weak_source.images[i]
+                augmenter.apply(src, self.images[i], params, valid_hw=(hs[i], ws[i]))
+            if img is not None and not img.is_cuda:
+                nbytes += img.numel()
         m = self.h_meta
         m.zero_()
         m[0] = seed - (1 << 32) if seed >= (1 << 31) else seed
@@ -251,6 +269,9 @@ class B200TrainStep:
         # device-computed ones, one GroundTruth per distillation micro-batch
         self.pseudo_override = None
         self.pseudo_log = []
+        # {"labeled": StrongAugmenter, "unlabeled": StrongAugmenter}: set to derive strong views on the device from
+        # items that carry "aug_params" 
+        self.augmenters = {}
 
     # ---- aldi/ema.py:52-57 -------------------------------------------------------------------------
     def ema_update(self, it):
@@ -352,13 +373,15 @@ class B200TrainStep:
             mb = self._mb_cache.get(key)
             if mb is None:
                 mb = self._mb_cache[key] = MicroBatch(*key[1:], self.device)
+            aug = self.augmenters.get("labeled" if with_gt else "unlabeled")
+            weak = out[0] if (kind == "strong" and out) else None   # distill parts are staged (weak, strong)
             if stream is None:
-                self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt)
+                self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt, weak, aug)
             else:
                 with torch.cuda.stream(stream):
                     if mb.free_event is not None:
                         stream.wait_event(mb.free_event)
-                    self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt)
+                    self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt, weak, aug)
                     ready = torch.cuda.Event()
                     ready.record(stream)
                 torch.cuda.current_stream().wait_event(ready)

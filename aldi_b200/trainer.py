@@ -31,6 +31,7 @@ def unpack_data_weak_strong(labeled, unlabeled, batch_contents):
         out = []
         for d in batch:
             e = dict(d)
+            e.pop("aug_params", None)          # the weak view is what the strong one is derived FROM
             if "img_weak" in e:
                 e["image"] = e["img_weak"]
             out.append(e)
@@ -50,7 +51,7 @@ class SyntheticWeakStrongLoader:
     images (there is no dataset on the box): per-rank batch sizes follow ALDITrainer.build_train_loader
     (aldi/trainer.py:211-240): IMS_PER_BATCH split by BATCH_RATIOS, divided by the world size."""
 
-    def __init__(self, cfg, height, width, rank=0, world=1, seed=1234, pin=False):
+    def __init__(self, cfg, height, width, rank=0, world=1, seed=1234, pin=False, gpu_aug=False):
         contents, ratios = cfg.DATASETS.BATCH_CONTENTS, cfg.DATASETS.BATCH_RATIOS
         total = cfg.SOLVER.IMS_PER_BATCH
         sizes = [int(total * r / sum(ratios)) for r in ratios]
@@ -63,6 +64,13 @@ class SyntheticWeakStrongLoader:
         self.contents, self.h, self.w, self.pin = contents, height, width, pin
         self.seed, self.rank, self.it = seed, rank, 0
         self.num_classes = cfg.MODEL.ROI_HEADS.NUM_CLASSES
+        # gpu_aug: ship only the weak view; strong items carry the drawn augmentation parameters and the step derives
+        # the strong view in HBM (aldi_b200/augment.py) — what get_augs(cfg, labeled, ...) would do on the workers
+        self.augmenters = None
+        if gpu_aug:
+            from .augment import StrongAugmenter
+            self.augmenters = {"labeled": StrongAugmenter.from_config(cfg, True),
+                               "unlabeled": StrongAugmenter.from_config(cfg, False)}
 
     def __iter__(self):
         return self
@@ -75,6 +83,14 @@ class SyntheticWeakStrongLoader:
         unlabeled = None
         if self.unlabeled_bs:
             unlabeled = [dict(s, img_weak=w["image"]) for w, s in zip(uw, us)]
+        if self.augmenters is not None:
+            # the synthetic generator's own strong views are dropped: labeled items keep the weak image + parameters,
+            # unlabeled strong items are image-less (their weak twin is staged right before them)
+            if labeled is not None:
+                labeled = [dict(d, aug_params=self.augmenters["labeled"].draw(self.h, self.w)) for d in labeled]
+            if unlabeled is not None:
+                unlabeled = [{"image": None, "img_weak": d["img_weak"], "height": d["height"], "width": d["width"],
+                              "aug_params": self.augmenters["unlabeled"].draw(self.h, self.w)} for d in unlabeled]
         if self.pin:
             for b in (labeled or []) + (unlabeled or []):
                 for k in ("image", "img_weak"):
@@ -101,6 +117,8 @@ class ALDITrainer:
         self.step_impl.debug = None
         self.data_loader = data_loader if data_loader is not None else self.build_train_loader(cfg, image_size, self.rank,
                                                                                                self.world)
+        if getattr(self.data_loader, "augmenters", None):
+            self.step_impl.augmenters = self.data_loader.augmenters
         self._data_iter = iter(self.data_loader)
         self.iter = self.start_iter = 0
         self.max_iter = cfg.SOLVER.MAX_ITER
@@ -108,8 +126,8 @@ class ALDITrainer:
 
     # ---- aldi/trainer.py:211-240 ---------------------------------------------------------------------------
     @classmethod
-    def build_train_loader(cls, cfg, image_size=(512, 512), rank=0, world=1):
-        return SyntheticWeakStrongLoader(cfg, image_size[0], image_size[1], rank=rank, world=world, pin=True)
+    def build_train_loader(cls, cfg, image_size=(512, 512), rank=0, world=1, gpu_aug=False):
+        return SyntheticWeakStrongLoader(cfg, image_size[0], image_size[1], rank=rank, world=world, pin=True, gpu_aug=gpu_aug)
 
     # ---- D2 WarmupMultiStepLR via SOLVER.* --------------------------------------------------------------------
     def lr(self, it):

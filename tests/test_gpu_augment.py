@@ -117,3 +117,31 @@ def test_param_draws_follow_reference_order():
     assert got["color"] == want["color"] and got["gray"] == want["gray"] and got["sigma"] == want["sigma"]
     assert [r for r, _ in got["erase"]] == [r for r, _ in want["erase"]]
     assert np.array_equal(got["mic"], want["mic"])
+
+
+def test_step_derives_strong_views_on_the_device():
+    """The train step stages only weak images; strong items carry `aug_params` (aldi_b200/trainer.py gpu_aug) and the
+    student's input canvas must equal the oracle's strong augmentation of the weak image."""
+    import parity_utils as pu
+    from aldi_b200.augment import StrongAugmenter
+    from aldi_b200.train_step import B200TrainStep, StepConfig
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(5, 1, 2, 96, 128)
+    aug = StrongAugmenter(labeled=False, include_erasing=False, mic=(0.5, 32))
+    random.seed(31); np.random.seed(31)
+    params = [aug.draw(96, 128) for _ in uw]
+    us_dev = [{"image": None, "height": 96, "width": 128, "aug_params": p} for p in params]
+    step = B200TrainStep(StepConfig(dtype="bf16", ims_per_gpu=2, ema_start_iter=-1), sd_s, teacher_state_dict=sd_t)
+    step.debug = None
+    step.augmenters = {"unlabeled": aug, "labeled": StrongAugmenter(labeled=True)}
+    before = step.h2d_bytes
+    random.seed(1)
+    losses = dict(step.run_model((None, ls, uw, us_dev)).items())
+    assert all(np.isfinite(v) for v in losses.values())
+    strong_mb = [m for k, m in step._mb_cache.items() if k[0] == "strong"][0]
+    for i, (d, p) in enumerate(zip(uw, params)):
+        want = aug_ref.strong_augment(d["image"].permute(1, 2, 0).numpy(), p)
+        got = strong_mb.images[i, :, :96, :128].permute(1, 2, 0).cpu().numpy()
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 2e-2, (i, int(diff.max()), float((diff != 0).mean()))
+    # only the labeled image and the two weak target images crossed the bus
+    assert step.h2d_bytes < 3 * 3 * 96 * 128 + 8192    # + GT boxes and metadata; a 4th image would add 36 KB
