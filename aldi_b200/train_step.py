@@ -532,9 +532,10 @@ class B200TrainStep:
         rpn_out, _ = det.rpn_head(W, feats, lv, save=False)
         return feats, lv, rpn_out
 
-    def pseudo_label(self, b, feats, lv, rpn_out, score_thresh=None):
+    def pseudo_label(self, b, feats, lv, rpn_out, score_thresh=None, W=None):
         """aldi/pseudolabeler.py:15-30: teacher.inference(do_postprocess=False) then scores > threshold."""
-        cfg, det, W = self.cfg, self.det, self.teacher
+        cfg, det = self.cfg, self.det
+        W = W if W is not None else self.teacher
         n = b.n
         props = det.proposals(rpn_out, lv, b.sizes, cfg.rpn_pre_topk[1], cfg.rpn_post_topk[1], cfg.rpn_nms_thresh)
         p = props["boxes"].shape[1]
@@ -552,6 +553,43 @@ class B200TrainStep:
         ops.call("aldi_pseudo_label_threshold", dets["boxes"], dets["scores"], dets["cats"], dets["count"],
                  cfg.test_topk, n, cfg.pseudo_threshold, gb, gc, gs, cnt, gmax)
         return GroundTruth(gb, gc, cnt, gmax, gs), dets
+
+    # ---- model.inference(batched_inputs, do_postprocess) (detectron2 GeneralizedRCNN.inference) -----------------
+    def inference(self, batched_inputs, which="teacher", do_postprocess=True):
+        """Eval-mode detections of the EMA teacher (what `EMA.inference` / the periodic evaluation of the teacher run,
+        aldi/ema.py:59-60, aldi/trainer.py:173-185) or of the student: RPN test top-k, box head, score threshold
+        TEST score 0.05, per-class NMS 0.5, top 100.  Returns detectron2's output format: a list of
+        {"instances": Instances(pred_boxes, scores, pred_classes)} rescaled to each input's (height, width)
+        (detector_postprocess) when do_postprocess, else the bare Instances in the network input frame
+        (aldi/pseudolabeler.py:21 calls it that way).  ONE device->host copy per micro-batch."""
+        from .structures import Boxes, Instances
+        cfg, det = self.cfg, self.det
+        W = self.teacher if which == "teacher" else self.student
+        out = []
+        for i in range(0, len(batched_inputs), cfg.ims_per_gpu):
+            data = batched_inputs[i:i + cfg.ims_per_gpu]
+            key = ("infer",) + MicroBatch.shape_key(data, False)
+            mb = self._mb_cache.get(key)
+            if mb is None:
+                mb = self._mb_cache[key] = MicroBatch(*key[1:], self.device)
+            mb.load(data, 0, 0, False)
+            feats, _ = det.backbone(W, mb.images, mb.sizes, save=False)
+            lv = det.levels(feats)
+            rpn_out, _ = det.rpn_head(W, feats, lv, save=False)
+            _, dets = self.pseudo_label(mb, feats, lv, rpn_out, score_thresh=cfg.test_score_thresh, W=W)
+            cnt = dets["count"].cpu().tolist()
+            boxes, scores, cats = dets["boxes"].cpu(), dets["scores"].cpu(), dets["cats"].cpu()
+            for j, d in enumerate(data):
+                k = cnt[j]
+                h_in, w_in = int(mb.h_meta[1 + MicroBatch.SITES * mb.n + 2 * j]), int(mb.h_meta[2 + MicroBatch.SITES * mb.n + 2 * j])
+                inst = Instances((h_in, w_in), pred_boxes=Boxes(boxes[j, :k].clone()), scores=scores[j, :k].clone(),
+                                 pred_classes=cats[j, :k].long())
+                if not do_postprocess:
+                    out.append(inst)
+                    continue
+                oh, ow = int(d.get("height", h_in)), int(d.get("width", w_in))
+                out.append({"instances": detector_postprocess(inst, oh, ow)})
+        return out
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
     def _distill_body(self, bw, bs, gscale, pass_id, base=SLOT_BASE["distill"]):
@@ -668,6 +706,23 @@ class B200TrainStep:
     def load_optimizer_state(self, state):
         self.momentum_buf.copy_(state["momentum_buffer"].to(self.momentum_buf.device))
         self.iter = int(state.get("iteration", self.iter))
+
+
+def detector_postprocess(results, output_height, output_width):
+    """detectron2.modeling.postprocessing.detector_postprocess for box-only Instances: scale the boxes from the network
+    input frame to the requested output resolution, clip to it, drop boxes that became empty."""
+    from .structures import Boxes, Instances
+    scale_x, scale_y = output_width / results.image_size[1], output_height / results.image_size[0]
+    b = results.pred_boxes.tensor.clone()
+    b[:, 0::2] *= scale_x
+    b[:, 1::2] *= scale_y
+    b[:, 0].clamp_(min=0, max=output_width)
+    b[:, 1].clamp_(min=0, max=output_height)
+    b[:, 2].clamp_(min=0, max=output_width)
+    b[:, 3].clamp_(min=0, max=output_height)
+    keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    return Instances((output_height, output_width), pred_boxes=Boxes(b[keep]), scores=results.scores[keep],
+                     pred_classes=results.pred_classes[keep])
 
 
 class LossDict(dict):

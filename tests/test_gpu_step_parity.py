@@ -201,3 +201,40 @@ def test_domain_alignment_step_matches_oracle():
     check_losses(dev_losses, ora)
     worst = check_grads(step, student)
     print("alignment step: losses", dev_losses, "worst grad rel err", worst)
+
+
+def test_teacher_inference_and_postprocess_match_oracle():
+    """the EMA teacher's evaluation-mode inference (detectron2 GeneralizedRCNN.inference) and
+    detector_postprocess.  Detections are matched as sets above a score floor: near the 0.05 test threshold a 1e-6
+    score difference decides membership, which is not a property of either implementation."""
+    from aldi_b200.train_step import B200TrainStep, StepConfig
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(33, 0, 3, 128, 160)
+    step = B200TrainStep(StepConfig(dtype="fp32", ims_per_gpu=2, ema_start_iter=-1), sd_s, teacher_state_dict=sd_t)
+    raw = step.inference(uw, which="teacher", do_postprocess=False)
+    _, teacher = pu.oracle_models(sd_s, sd_t)
+    teacher.eval()
+    with torch.no_grad():
+        ora = teacher.inference(pu.to_d2(uw, False), do_postprocess=False)
+    assert len(raw) == len(ora) == 3
+    matched = 0
+    for got, want in zip(raw, ora):
+        assert got.image_size == want.image_size
+        for a, b in ((got, want), (want, got)):
+            ab, asc, ac = a.pred_boxes.tensor, a.scores, a.pred_classes
+            bb, bsc, bc = b.pred_boxes.tensor, b.scores, b.pred_classes
+            for i in range(len(asc)):
+                if float(asc[i]) < 0.1:
+                    continue
+                ok = (bc == ac[i]) & ((bsc - asc[i]).abs() < 1e-4) & ((bb - ab[i]).abs().max(dim=1).values < 2e-2)
+                assert bool(ok.any()), (i, float(asc[i]), int(ac[i]), ab[i].tolist())
+                matched += 1
+    assert matched > 0
+    # detector_postprocess: ask for outputs at twice the input resolution
+    big = [dict(d, height=256, width=320) for d in uw]
+    post = step.inference(big, which="teacher", do_postprocess=True)
+    for r, p in zip(raw, post):
+        inst = p["instances"]
+        assert inst.image_size == (256, 320)
+        keep = ((r.pred_boxes.tensor[:, 2] - r.pred_boxes.tensor[:, 0]) > 0) & ((r.pred_boxes.tensor[:, 3] - r.pred_boxes.tensor[:, 1]) > 0)
+        assert torch.allclose(inst.pred_boxes.tensor, r.pred_boxes.tensor[keep] * 2.0, atol=1e-4)
+        assert torch.equal(inst.pred_classes, r.pred_classes[keep])
