@@ -213,7 +213,12 @@ def step_config_from_cfg(cfg, dtype=None):
         raise NotImplementedError("MODEL.RPN.PRE_NMS_TOPK_TRAIN/TEST up to 2048 per level are supported (the ALDI configs "
                                   "use 2000 / 1000, configs/detectron2/Base-RCNN-FPN.yaml:14-15); got %d / %d"
                                   % (cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST))
+    A = cfg.DOMAIN_ADAPT.ALIGN
     return StepConfig(
+        img_da_enabled=A.IMG_DA_ENABLED, img_da_layer=A.IMG_DA_LAYER, img_da_weight=A.IMG_DA_WEIGHT,
+        img_da_input_dim=A.IMG_DA_INPUT_DIM, img_da_hidden_dims=tuple(A.IMG_DA_HIDDEN_DIMS),
+        ins_da_enabled=A.INS_DA_ENABLED, ins_da_weight=A.INS_DA_WEIGHT, ins_da_input_dim=A.INS_DA_INPUT_DIM,
+        ins_da_hidden_dims=tuple(A.INS_DA_HIDDEN_DIMS),
         num_classes=cfg.MODEL.ROI_HEADS.NUM_CLASSES, ims_per_gpu=cfg.SOLVER.IMS_PER_GPU, ema_alpha=cfg.EMA.ALPHA,
         ema_start_iter=cfg.EMA.START_ITER, pseudo_threshold=cfg.DOMAIN_ADAPT.TEACHER.THRESHOLD,
         do_hard_cls=D.HARD_ROIH_CLS_ENABLED, do_hard_obj=D.HARD_OBJ_ENABLED, do_hard_rpn_reg=D.HARD_RPN_REG_ENABLED,

@@ -110,8 +110,9 @@ class ALDITrainer:
             raise RuntimeError("aldi_b200 runs the train step on a CUDA device only (MODEL.DEVICE=%s): there is no CPU "
                                "fallback; the CPU arm of bench.py is the oracle" % cfg.MODEL.DEVICE)
         assert cfg.EMA.ENABLED or not cfg.DOMAIN_ADAPT.TEACHER.ENABLED, "Teacher requires EMA.ENABLED"
-        sd = state_dict if state_dict is not None else arch.synthetic_state_dict(0, cfg.MODEL.ROI_HEADS.NUM_CLASSES)
         scfg = step_config_from_cfg(cfg, dtype=dtype)
+        sd = state_dict if state_dict is not None else arch.synthetic_state_dict(0, cfg.MODEL.ROI_HEADS.NUM_CLASSES,
+                                                                                align=scfg.align_spec())
         self.step_impl = B200TrainStep(scfg, sd, device=device or "cuda:%d" % torch.cuda.current_device(),
                                        process_group=process_group)
         self.step_impl.debug = None
