@@ -66,13 +66,13 @@ nms_mask_kernel(const float* __restrict__ sbox, const int* __restrict__ scat, co
   const int cj = cb * 64 + threadIdx.x;
   if (cj < nv) {
     cbox[threadIdx.x] = reinterpret_cast<const float4*>(sbox)[(size_t)img * cpad + cj];
-    ccat[threadIdx.x] = scat[(size_t)img * cpad + cj];
+    ccat[threadIdx.x] = scat ? scat[(size_t)img * cpad + cj] : 0;   // scat == nullptr: one category per segment
   }
   __syncthreads();
   const int i = rb * 64 + threadIdx.x;
   if (i >= nv) return;
   const float4 bi = reinterpret_cast<const float4*>(sbox)[(size_t)img * cpad + i];
-  const int ci = scat[(size_t)img * cpad + i];
+  const int ci = scat ? scat[(size_t)img * cpad + i] : 0;
   const float iarea = (bi.z - bi.x) * (bi.w - bi.y);
   unsigned long long bits = 0ull;
   const int ncol = min(64, nv - cb * 64);
@@ -101,7 +101,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const float* __rest
                 const float* __restrict__ sscore, const int* __restrict__ scat, const int* __restrict__ sperm,
                 const int* __restrict__ nvalid, int cpad, int post_topk, float* __restrict__ out_box,
                 float* __restrict__ out_score, int* __restrict__ out_cat, int* __restrict__ out_src,
-                int* __restrict__ out_count) {
+                int* __restrict__ out_count, int* __restrict__ kept_out) {
   extern __shared__ int s_keptlist[];  // sorted-order indices of the kept boxes
   const int img = blockIdx.x;
   const int nv = nvalid[img];
@@ -150,7 +150,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const float* __rest
     }
     __syncthreads();
     const unsigned long long kept = s_kept;
-    if (t < 64 && ((kept >> t) & 1ull)) {
+    if (!kept_out && t < 64 && ((kept >> t) & 1ull)) {
       const int rank = __popcll(kept & ((1ull << t) - 1ull));
       const size_t src = (size_t)img * cpad + c * 64 + t, dst = (size_t)img * post_topk + s_base + rank;
       reinterpret_cast<float4*>(out_box)[dst] = reinterpret_cast<const float4*>(sbox)[src];
@@ -162,6 +162,103 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const float* __rest
   }
   __syncthreads();
   if (t == 0) out_count[img] = s_total;
+  if (kept_out)   // segmented NMS: the merge kernel gathers; hand it the kept positions (ascending = score order)
+    for (int k = t; k < s_total; k += 256) kept_out[(size_t)img * post_topk + k] = s_keptlist[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segmented NMS (RPN: category = FPN level, and every level's candidates arrive already sorted by score from
+// aldi_rpn_topk_decode).  Boxes of different segments never suppress each other, so the greedy scans of the
+// segments are independent: instead of ONE 16K-key sort, a (16K)^2/2 bit matrix of which 80 % is cross-level and
+// a 150-chunk serial scan per image, each (image, level) gets a stable compaction, a 2K x 2K matrix and a 32-chunk
+// scan, all in parallel, and a rank-by-binary-search merge restores the global score order and the keep[:post_topk]
+// cut.  Result identical to aldi_nms_sorted (same keys: score descending, candidate position ascending).
+struct SegTable {
+  int num_seg;
+  int off[8], len[8];
+};
+
+// stable compaction of the valid candidates of one (image, segment): block = 1024
+__global__ void __launch_bounds__(1024)
+nms_seg_compact_kernel(const float* __restrict__ box, const float* __restrict__ score,
+                       const unsigned char* __restrict__ valid, int cand_stride, SegTable segs, int cap,
+                       float* __restrict__ sbox, float* __restrict__ sscore, int* __restrict__ sperm,
+                       int* __restrict__ nvalid) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int seg = blockIdx.x, img = blockIdx.y;
+  const int off = segs.off[seg], len = segs.len[seg];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t dst0 = ((size_t)img * segs.num_seg + seg) * cap;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < len; c0 += 1024) {
+    const int i = c0 + threadIdx.x;
+    const size_t src = (size_t)img * cand_stride + off + i;
+    const bool ok = i < len && (!valid || valid[src]);
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (ok) {
+      const size_t dst = dst0 + before + __popc(b & ((1u << lane) - 1u));
+      reinterpret_cast<float4*>(sbox)[dst] = reinterpret_cast<const float4*>(box)[src];
+      sscore[dst] = score[src];
+      sperm[dst] = off + i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nvalid[img * segs.num_seg + seg] = s_base;
+}
+
+// global rank of every kept box = its index in its own segment's kept list + the number of kept boxes of the other
+// segments that sort before it; block = 1024, grid = N
+__global__ void __launch_bounds__(1024)
+nms_seg_merge_kernel(const float* __restrict__ sbox, const float* __restrict__ sscore, const int* __restrict__ sperm,
+                     const int* __restrict__ kept, const int* __restrict__ kept_count, int num_seg, int cap,
+                     int post_topk, float* __restrict__ out_box, float* __restrict__ out_score,
+                     int* __restrict__ out_cat, int* __restrict__ out_src, int* __restrict__ out_count) {
+  const int img = blockIdx.x;
+  int total = 0;
+  for (int s = 0; s < num_seg; ++s) total += kept_count[img * num_seg + s];
+  auto key_of = [&](int s, int k) -> unsigned long long {
+    const size_t base = ((size_t)img * num_seg + s);
+    const int j = kept[base * post_topk + k];
+    return ((unsigned long long)fkey(sscore[base * cap + j]) << 32) |
+           (unsigned long long)(0xFFFFFFFFu - (uint32_t)sperm[base * cap + j]);
+  };
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int s = 0, k = e;
+    while (k >= kept_count[img * num_seg + s]) { k -= kept_count[img * num_seg + s]; ++s; }
+    const unsigned long long mine = key_of(s, k);
+    int rank = k;
+    for (int o = 0; o < num_seg; ++o) {
+      if (o == s) continue;
+      int lo = 0, hi = kept_count[img * num_seg + o];   // first index whose key is NOT greater than mine
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (key_of(o, mid) > mine) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < post_topk) {
+      const size_t base = ((size_t)img * num_seg + s);
+      const int j = kept[base * post_topk + k];
+      const size_t dst = (size_t)img * post_topk + rank;
+      reinterpret_cast<float4*>(out_box)[dst] = reinterpret_cast<const float4*>(sbox)[base * cap + j];
+      out_score[dst] = sscore[base * cap + j];
+      out_cat[dst] = s;
+      out_src[dst] = sperm[base * cap + j];
+    }
+  }
+  if (threadIdx.x == 0) out_count[img] = min(total, post_topk);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -457,9 +554,74 @@ extern "C" int aldi_nms_sorted(const float* cand_box, const float* cand_score, c
   ALDI_CUDA_LAUNCH_CHECK("aldi_nms_sorted(mask)");
   ALDI_CHECK_ARG(post_topk > 0 && post_topk <= 8192, "aldi_nms_sorted: post_topk must be in (0, 8192]");
   nms_scan_kernel<<<n_images, 256, (size_t)post_topk * sizeof(int), stream>>>(mask, sbox, sscore, scat, sperm, nvalid, cpad, post_topk, out_box,
-                                                out_score, out_cat, out_src, out_count);
+                                                out_score, out_cat, out_src, out_count, nullptr);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_nms_sorted(scan)");
+  return ALDI_OK;
+}
+
+static int seg_cap_for(const int* seg_len, int num_seg) {
+  int mx = 1;
+  for (int i = 0; i < num_seg; ++i) mx = seg_len[i] > mx ? seg_len[i] : mx;
+  int cap = 64;
+  while (cap < mx) cap <<= 1;
+  return cap;
+}
+
+extern "C" size_t aldi_nms_segmented_workspace_bytes(int n_images, int num_seg, const int* seg_len, int post_topk) {
+  const size_t cap = (size_t)seg_cap_for(seg_len, num_seg);
+  const size_t per = cap * (16 + 4 + 4) + cap * (cap / 64) * 8 + (size_t)post_topk * 4 + 8;
+  return per * (size_t)n_images * num_seg + 4096;
+}
+
+extern "C" int aldi_nms_segmented(const float* cand_box, const float* cand_score, const unsigned char* cand_valid,
+                                  int n_images, int cand_stride, int num_seg, const int* seg_off, const int* seg_len,
+                                  float iou_thresh, int post_topk, void* workspace, size_t workspace_bytes,
+                                  float* out_box, float* out_score, int* out_cat, int* out_src, int* out_count,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(cand_box && cand_score && seg_off && seg_len && workspace && out_box && out_score && out_cat && out_src &&
+                     out_count, "aldi_nms_segmented: null pointer");
+  ALDI_CHECK_ARG(n_images > 0 && num_seg >= 1 && num_seg <= 8, "aldi_nms_segmented: 1..8 segments per image");
+  ALDI_CHECK_ARG(post_topk > 0 && post_topk <= 8192, "aldi_nms_segmented: post_topk must be in (0, 8192]");
+  SegTable T;
+  T.num_seg = num_seg;
+  for (int i = 0; i < 8; ++i) { T.off[i] = 0; T.len[i] = 0; }
+  for (int i = 0; i < num_seg; ++i) {
+    ALDI_CHECK_ARG(seg_len[i] >= 0 && seg_len[i] <= 4096 && seg_off[i] >= 0 && seg_off[i] + seg_len[i] <= cand_stride,
+                   "aldi_nms_segmented: segment %d (%d at %d) outside the candidate stride %d or longer than 4096", i,
+                   seg_len[i], seg_off[i], cand_stride);
+    T.off[i] = seg_off[i]; T.len[i] = seg_len[i];
+  }
+  ALDI_CHECK_ARG(workspace_bytes >= aldi_nms_segmented_workspace_bytes(n_images, num_seg, seg_len, post_topk),
+                 "aldi_nms_segmented: workspace too small");
+  const int cap = seg_cap_for(seg_len, num_seg);
+  const size_t ns = (size_t)n_images * num_seg;
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* sbox = reinterpret_cast<float*>(ws);      ws += ns * cap * 16;
+  float* sscore = reinterpret_cast<float*>(ws);    ws += ns * cap * 4;
+  int* sperm = reinterpret_cast<int*>(ws);         ws += ns * cap * 4;
+  int* kept = reinterpret_cast<int*>(ws);          ws += ((ns * post_topk * 4 + 255) / 256) * 256;
+  int* nvalid = reinterpret_cast<int*>(ws);        ws += ((ns * 4 + 255) / 256) * 256;
+  int* kept_count = reinterpret_cast<int*>(ws);    ws += ((ns * 4 + 255) / 256) * 256;
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
+  nms_seg_compact_kernel<<<dim3(num_seg, n_images), 1024, 0, stream>>>(cand_box, cand_score, cand_valid, cand_stride, T, cap,
+                                                                       sbox, sscore, sperm, nvalid);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_nms_segmented(compact)");
+  const int wused = cap / 64;
+  nms_mask_kernel<<<dim3(wused, wused, (unsigned)ns), 64, 0, stream>>>(sbox, nullptr, nvalid, cap, iou_thresh, mask);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_nms_segmented(mask)");
+  nms_scan_kernel<<<(unsigned)ns, 256, (size_t)post_topk * sizeof(int), stream>>>(mask, sbox, sscore, nullptr, sperm, nvalid, cap,
+                                                                                post_topk, nullptr, nullptr, nullptr, nullptr,
+                                                                                kept_count, kept);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_nms_segmented(scan)");
+  nms_seg_merge_kernel<<<n_images, 1024, 0, stream>>>(sbox, sscore, sperm, kept, kept_count, num_seg, cap, post_topk, out_box,
+                                                      out_score, out_cat, out_src, out_count);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_nms_segmented(merge)");
   return ALDI_OK;
 }
 

@@ -363,9 +363,30 @@ class Detector:
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         ops.call("aldi_rpn_topk_decode", rpn_out, _l.ctypes.byref(lv), n, pre_topk, sizes, cb, cs, cc, ci, cv, stride,
                  err_flag, ws, wsb)
-        out = self.nms(cb, cs, cc, cv, None, nms_thresh, post_topk)
+        # batched_nms by level: every level's candidates are already score-sorted, so the levels are compacted,
+        # masked and scanned in parallel and merged by rank (aldi_nms_segmented == aldi_nms_sorted on these inputs)
+        lens = [min(lv.h[i] * lv.w[i] * lv.num_anchors, pre_topk) for i in range(lv.num_levels)]
+        offs = [sum(lens[:i]) for i in range(lv.num_levels)]
+        out = self.nms_segmented(cb, cs, cv, offs, lens, nms_thresh, post_topk)
         out["cand"] = (cb, cs, cc, ci, cv)
         return out
+
+    @staticmethod
+    def nms_segmented(cb, cs, cv, offs, lens, thresh, post_topk):
+        n, stride = cs.shape
+        dev = cs.device
+        L = _l.load()
+        k = len(lens)
+        c_off, c_len = (_l.ctypes.c_int * k)(*offs), (_l.ctypes.c_int * k)(*lens)
+        wsb = int(L.aldi_nms_segmented_workspace_bytes(n, k, c_len, post_topk))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ob = torch.zeros(n, post_topk, 4, device=dev)
+        osc = torch.zeros(n, post_topk, device=dev)
+        oc = torch.zeros(n, post_topk, dtype=torch.int32, device=dev)
+        osrc = torch.zeros(n, post_topk, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        ops.call("aldi_nms_segmented", cb, cs, cv, n, stride, k, c_off, c_len, thresh, post_topk, ws, wsb, ob, osc, oc, osrc, cnt)
+        return {"boxes": ob, "scores": osc, "cats": oc, "src": osrc, "count": cnt}
 
     @staticmethod
     def nms(cb, cs, cc, cv, counts, thresh, post_topk):

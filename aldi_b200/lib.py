@@ -134,6 +134,9 @@ SIGNATURES = {
                                      P]),
     "aldi_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aldi_nms_sorted": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_int, P, c_size_t, P, P, P, P, P, P]),
+    "aldi_nms_segmented_workspace_bytes": (c_size_t, [c_int, c_int, ctypes.POINTER(c_int), c_int]),
+    "aldi_nms_segmented": (c_int, [P, P, P, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_float, c_int,
+                                   P, c_size_t, P, P, P, P, P, P]),
     "aldi_rpn_label_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aldi_rpn_label_anchors": (c_int, [ctypes.POINTER(RpnLevels), c_int, P, P, c_int, c_float, c_float, c_int, c_float,
                                        P, P, P, c_size_t, P, P, P, P]),

@@ -204,6 +204,14 @@ int aldi_nms_sorted(const float* cand_box, const float* cand_score, const int* c
                     const unsigned char* cand_valid, const int* cand_count, int n_images, int cand_stride,
                     float iou_thresh, int post_topk, void* workspace, size_t workspace_bytes, float* out_box,
                     float* out_score, int* out_cat, int* out_src, int* out_count, void* stream);
+/* Same result as aldi_nms_sorted for candidates that arrive as `num_seg` score-sorted segments per image whose
+ * category is the segment index (the RPN: one segment per FPN level, straight from aldi_rpn_topk_decode): the
+ * segments are compacted, masked and scanned in parallel and merged by rank.  seg_off / seg_len: HOST arrays. */
+size_t aldi_nms_segmented_workspace_bytes(int n_images, int num_seg, const int* seg_len, int post_topk);
+int aldi_nms_segmented(const float* cand_box, const float* cand_score, const unsigned char* cand_valid, int n_images,
+                       int cand_stride, int num_seg, const int* seg_off, const int* seg_len, float iou_thresh,
+                       int post_topk, void* workspace, size_t workspace_bytes, float* out_box, float* out_score,
+                       int* out_cat, int* out_src, int* out_count, void* stream);
 /* Sampling seed: `d_seed` is a DEVICE pointer to one uint32 (the value aldi/helpers.py:17-26 ManualSeed would
  * feed torch.manual_seed) so that a captured CUDA graph of the step can be replayed with a new seed.       */
 /* RPN.label_and_sample_anchors: Matcher([lo,hi],[0,-1,1], low-quality) + subsample_labels; labels (N,R) int8 */

@@ -209,3 +209,41 @@ def test_roi_inference_exact():
             assert torch.allclose(out["scores"][i, :len(want)].cpu(), want, rtol=1e-5), (thr, c, len(want))
             assert torch.equal(out["cats"][i, :len(want)].cpu().long(), ref[i].pred_classes[keep])
             assert torch.allclose(out["boxes"][i, :len(want)].cpu(), ref[i].pred_boxes.tensor[keep], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("seed,quant", [(0, 0.0), (1, 0.25)])
+def test_segmented_nms_equals_sorted_nms(seed, quant):
+    """aldi_nms_segmented (per-level compaction / mask / scan in parallel + rank merge) must reproduce aldi_nms_sorted
+    bit for bit on level-major, per-level score-sorted candidates — including invalid candidates, score ties across and
+    within levels (quantised scores) and the keep[:post_topk] cut."""
+    from aldi_b200.detector import Detector
+    g = torch.Generator().manual_seed(seed)
+    n, lens = 3, [2000, 2000, 1200, 300, 45]
+    offs = [sum(lens[:i]) for i in range(len(lens))]
+    stride = sum(lens)
+    cb = torch.zeros(n, stride, 4)
+    cs = torch.zeros(n, stride)
+    cc = torch.zeros(n, stride, dtype=torch.int32)
+    for i in range(n):
+        for l, (o, k) in enumerate(zip(offs, lens)):
+            s = torch.randn(k, generator=g) * 2
+            if quant:
+                s = (s / quant).round() * quant
+            s = s.sort(descending=True).values
+            ctr = torch.rand(k, 2, generator=g) * 600
+            wh = torch.rand(k, 2, generator=g) * 120 * (l + 1) + 4
+            cb[i, o:o + k] = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+            cs[i, o:o + k] = s
+            cc[i, o:o + k] = l
+    cv = (torch.rand(n, stride, generator=g) > 0.03).to(torch.uint8)
+    cb, cs, cc, cv = cb.cuda(), cs.cuda(), cc.cuda(), cv.cuda()
+    for post in (1000, 137):
+        a = Detector.nms(cb, cs, cc, cv, None, 0.7, post)
+        b = Detector.nms_segmented(cb, cs, cv, offs, lens, 0.7, post)
+        torch.cuda.synchronize()
+        assert torch.equal(a["count"], b["count"])
+        for i in range(n):
+            c = int(a["count"][i])
+            assert c > 0
+            for k in ("src", "cats", "scores", "boxes"):
+                assert torch.equal(a[k][i, :c], b[k][i, :c]), (post, i, k)
