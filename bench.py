@@ -263,6 +263,17 @@ def run_ours(args):
         return
     for _ in range(max(args.warmup, 3)):
         one_step(dev, False)
+    if args.ncu_step:
+        # profiling aid: exactly ONE eagerly issued step between cudaProfilerStart/Stop, for
+        #   ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum ...
+        # (a number printed under ncu is never a bench value: nothing is printed)
+        step.cfg.cuda_graph = False
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        one_step(dev, False)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     if args.kineto_out:
         from torch.profiler import ProfilerActivity, profile
         barrier()
@@ -355,8 +366,20 @@ def run_ours(args):
         s = summ["aldi_conv_tc"]
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = s["flops"] / (s["ms"] * 1e-3) / 1e12
+        # DRAM traffic per launch of this kernel from the committed ncu capture of the same step (profiles/, made with
+        # `ncu --metrics ...dram__bytes_{read,write}.sum` over `bench.py --ncu-step`); algorithmic bytes beside it
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_traffic.json")))
+            traffic = tj["kernels"]["conv_tc"]["dram_bytes_per_launch"]
+            traffic_src = "profiles/r01_step_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d launches)" \
+                % tj["kernels"]["conv_tc"]["launches"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd + dgrad)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_unit": "bytes per launch (average)", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": s["bytes"] / max(s["launches"], 1),
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_per_step": s["launches"], "ms_per_step": s["ms"],
                     "share_of_step": s["ms"] / ms_step,
@@ -417,6 +440,7 @@ def main():
     ap.add_argument("--profile-out", default="", help="write the per-layer-shape kernel table (markdown) here")
     ap.add_argument("--kineto-out", default="", help="debug: profile 3 steps with torch.profiler (CUPTI) and write per-kernel "
                     "in-situ device times here")
+    ap.add_argument("--ncu-step", action="store_true", help="debug: warm up, run ONE eager step inside cudaProfilerStart/Stop, exit")
     ap.add_argument("--trace-losses", type=int, default=0, help="debug: run this many steps printing the loss dict, then exit")
     ap.add_argument("--base-lr", type=float, default=None, help="override SOLVER.BASE_LR (default: the reference's 0.06)")
     args = ap.parse_args()
