@@ -293,7 +293,9 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
   a.n_tiles = aldi_div_up(p->cin_store, block_n);
   int base_items = a.taps * a.m_tiles * a.n_tiles;
   // split K so that there are ~2 waves of work items but each keeps >= 8 pixel tiles
-  int want = aldi_div_up(2 * aldi_num_sms(), base_items);
+  static const char* waves_env = getenv("ALDI_WGRAD_WAVES");  // perf bisection: work-item waves the split-K aims at
+  const int waves = (waves_env && atoi(waves_env) >= 1) ? atoi(waves_env) : 2;
+  int want = aldi_div_up(waves * aldi_num_sms(), base_items);
   int max_split = a.pix_tiles / 8 > 0 ? a.pix_tiles / 8 : 1;
   a.ksplit = want < 1 ? 1 : (want > max_split ? max_split : want);
   a.num_items = base_items * a.ksplit;
