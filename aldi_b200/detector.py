@@ -404,12 +404,20 @@ class Detector:
         return {"boxes": ob, "scores": osc, "cats": oc, "src": osrc, "count": cnt}
 
     # ---- box head -------------------------------------------------------------------------------------
-    def box_head(self, W, feats, rois, roi_batch, save):
+    @staticmethod
+    def _roi_groups(groups, m, n):
+        """groups: [(first_row, rows, first_image, images)] — `roi_batch` holds image indices LOCAL to its group (two
+        passes batched into one forward keep their own RoI sampling); default: one group over everything."""
+        return groups if groups is not None else [(0, m, 0, n)]
+
+    def box_head(self, W, feats, rois, roi_batch, save, groups=None):
         m = rois.shape[0]
         dev, dt = rois.device, W.dtype
         plv = [feats["p%d" % l] for l in (2, 3, 4, 5)]
         pooled = torch.empty(m, 7, 7, 256, device=dev, dtype=dt)
-        ops.roi_align(plv, rois, roi_batch, out=pooled, scales=[1.0 / s for s in FPN_STRIDES[:4]])
+        for r0, rows, i0, ni in self._roi_groups(groups, m, plv[0].shape[0]):
+            ops.roi_align([p[i0:i0 + ni] for p in plv], rois[r0:r0 + rows], roi_batch[r0:r0 + rows],
+                          out=pooled[r0:r0 + rows], scales=[1.0 / s for s in FPN_STRIDES[:4]])
         x = pooled.view(1, 1, m, 7 * 7 * 256)
         f1 = self.conv(W, "fc1", x, relu=True)
         f2 = self.conv(W, "fc2", f1, relu=True)
@@ -509,7 +517,7 @@ class Detector:
         return out
 
     def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch, on_ready=None,
-                 align=None):
+                 align=None, groups=None):
         """Accumulate d(loss)/d(params) into the flat gradient buffer G.
         d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64).
         on_ready(tag): called when a bucket of G ("heads", "fpn", "res5", "res4", "res3") has received its last
@@ -546,8 +554,11 @@ class Detector:
             self._dgrad(W, "fc1", df1, dx)
             plv = [feats["p%d" % l] for l in (2, 3, 4, 5)]
             dfeat = [torch.zeros(p.shape, device=dev, dtype=torch.float32) for p in plv]
-            ops.roi_align(plv, rois, roi_batch, dout=dx.view(m, 7, 7, 256), dfeats=dfeat,
-                          scales=[1.0 / s for s in FPN_STRIDES[:4]])
+            dxv = dx.view(m, 7, 7, 256)
+            for r0, rows, i0, ni in self._roi_groups(groups, m, n):
+                ops.roi_align([p[i0:i0 + ni] for p in plv], rois[r0:r0 + rows], roi_batch[r0:r0 + rows],
+                              dout=dxv[r0:r0 + rows], dfeats=[d[i0:i0 + ni] for d in dfeat],
+                              scales=[1.0 / s for s in FPN_STRIDES[:4]])
             for l, d in zip((2, 3, 4, 5), dfeat):
                 # first writer of dP[l]: the fp32 scatter map becomes the activation-dtype gradient (no memset + add)
                 dP[l] = torch.empty_like(feats["p%d" % l])

@@ -80,6 +80,9 @@ class StepConfig:
         self.ins_da_hidden_dims = (1024,)
         self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": parity path
         self.cuda_graph = False                  # replay each micro-batch as a captured CUDA graph (2nd use onwards)
+        # run the student on a source micro-batch and a distillation micro-batch as ONE batch (same weights, FrozenBN:
+        # no cross-image coupling) -> twice the tiles per launch, half the launches; ALDI_NO_FUSE=1 is the A/B knob
+        self.fuse_passes = os.environ.get("ALDI_NO_FUSE") != "1"
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError("unknown StepConfig field %s" % k)
@@ -109,9 +112,10 @@ class MicroBatch:
 
     SITES = 3  # sampling.SITE_RPN, SITE_ROI, SITE_RPN_DISTILL
 
-    def __init__(self, n, hp, wp, gmax, device):
+    def __init__(self, n, hp, wp, gmax, device, images=None):
         self.n, self.hp, self.wp, self.gmax = n, hp, wp, gmax
-        self.images = torch.zeros(n, 3, hp, wp, dtype=torch.uint8, device=device)
+        # `images`: a (n, 3, hp, wp) view of a larger canvas shared with another micro-batch (fused student pass)
+        self.images = images if images is not None else torch.zeros(n, 3, hp, wp, dtype=torch.uint8, device=device)
         ni = 1 + self.SITES * n + 2 * n + n + n * gmax
         self.h_meta = torch.zeros(ni, dtype=torch.int32).pin_memory() if device.type == "cuda" else torch.zeros(ni, dtype=torch.int32)
         self.h_boxes = torch.zeros(n, gmax, 4).pin_memory() if device.type == "cuda" else torch.zeros(n, gmax, 4)
@@ -272,6 +276,7 @@ class B200TrainStep:
         # {"labeled": StrongAugmenter, "unlabeled": StrongAugmenter}: set to derive strong views on the device from
         # items that carry "aug_params" 
         self.augmenters = {}
+        self._teacher_out = None   # outputs of the last teacher pass, consumed by the fused student pass
 
     # ---- aldi/ema.py:52-57 -------------------------------------------------------------------------
     def ema_update(self, it):
@@ -335,12 +340,19 @@ class B200TrainStep:
             item["pass_id"] = 100 + i if item["kind"] == "distill" else i
             item["keys"] = [(kind,) + MicroBatch.shape_key(d, gt) for kind, d, gt in item["parts"]]
             self.seed_log[item["pass_id"]] = item["seed"]
+        if cfg.fuse_passes and do_distill and not do_align:
+            plan = self._fuse_plan(plan)
+        last_bwd = max(i for i, it in enumerate(plan) if it["kind"] != "teacher")
+        bodies = {"source": self._source_body, "distill": self._distill_body, "align_target": self._align_target_body,
+                  "teacher": self._teacher_body, "fused": self._fused_body}
         for i, item in enumerate(plan):
             self.seed = item["seed"]
-            self._last_backward = i == len(plan) - 1
+            self._last_backward = i == last_bwd
             mbs = item.get("staged") or self._stage(item, None)
-            body = {"source": self._source_body, "distill": self._distill_body, "align_target": self._align_target_body}[item["kind"]]
-            self._run(tuple(item["keys"]) + (gscale, self._last_backward, item["base"]),
+            if item["kind"] == "teacher":
+                item["fused"]["weak_mb"] = mbs[0]      # the strong views may be derived from it on the device
+            body = bodies[item["kind"]]
+            self._run((item["kind"],) + tuple(item["keys"]) + (gscale, self._last_backward, item["base"]),
                       lambda: body(*mbs, gscale, item["pass_id"], item["base"]))
             if self.device.type == "cuda":
                 for m in mbs:
@@ -351,6 +363,32 @@ class B200TrainStep:
                     nxt["staged"] = self._stage(nxt, self._copy_stream())
         self._out_keys = out_keys
         return LossDict(self, out_keys)
+
+    def _fuse_plan(self, plan):
+        """Pair the k-th source micro-batch with the k-th distillation micro-batch: [teacher(weak_k), fused(source_k +
+        strong_k)].  Pass ids, seeds and salts stay those of the reference-order plan, so every sample drawn is the
+        same; only the order in which the gradient contributions are summed changes.  Pairs whose canvases differ
+        in size, and unpaired micro-batches, run through the unfused bodies."""
+        src = [it for it in plan if it["kind"] == "source"]
+        dst = [it for it in plan if it["kind"] == "distill"]
+        out, used = [], set()
+        for s_it, d_it in zip(src, dst):
+            (_, sdata, _), = s_it["parts"]
+            (_, wdata, _), (_, tdata, _) = d_it["parts"]
+            ks, kt = MicroBatch.shape_key(sdata, True), MicroBatch.shape_key(tdata, False)
+            if ks[1:3] != kt[1:3]:
+                continue
+            used.update((id(s_it), id(d_it)))
+            canvas = ("canvas", ks[0], kt[0], ks[1], ks[2])
+            fused = {"kind": "fused", "seed": d_it["seed"], "base": (s_it["base"], d_it["base"]),
+                     "pass_id": (s_it["pass_id"], d_it["pass_id"]), "canvas": canvas,
+                     "parts": [("fsource", sdata, True, s_it["seed"], s_it["pass_id"], 0),
+                               ("fstrong", tdata, False, d_it["seed"], d_it["pass_id"], ks[0])],
+                     "keys": [("fsource",) + ks + (kt[0],), ("fstrong",) + kt + (ks[0],)]}
+            out.append({"kind": "teacher", "seed": d_it["seed"], "base": d_it["base"], "pass_id": d_it["pass_id"],
+                        "parts": [("weak", wdata, False)], "keys": [d_it["keys"][0]], "fused": fused})
+            out.append(fused)
+        return out + [it for it in plan if id(it) not in used]
 
     def losses_to_host(self, out_keys=None):
         vals = self.loss_acc.cpu()  # one D2H read of the step's loss vector (the reference syncs per loss)
@@ -369,19 +407,30 @@ class B200TrainStep:
         prefetch (ordered after the buffers' last consumer, the compute stream then waits for the copies) or None
         for plain in-order staging on the compute stream."""
         out = []
-        for key, (kind, data, with_gt) in zip(item["keys"], item["parts"]):
+        for key, part in zip(item["keys"], item["parts"]):
+            kind, data, with_gt = part[:3]
+            seed, pass_id = (part[3], part[4]) if len(part) > 3 else (item["seed"], item["pass_id"])
             mb = self._mb_cache.get(key)
             if mb is None:
-                mb = self._mb_cache[key] = MicroBatch(*key[1:], self.device)
+                view = None
+                if len(part) > 5:
+                    # fused student pass: both micro-batches are views of ONE image canvas, source images first
+                    ck = item["canvas"]
+                    canvas = self._mb_cache.get(ck)
+                    if canvas is None:
+                        canvas = self._mb_cache[ck] = torch.zeros(ck[1] + ck[2], 3, ck[3], ck[4], dtype=torch.uint8,
+                                                                  device=self.device)
+                    view = canvas[part[5]:part[5] + key[1]]
+                mb = self._mb_cache[key] = MicroBatch(*key[1:5], self.device, images=view)
             aug = self.augmenters.get("labeled" if with_gt else "unlabeled")
-            weak = out[0] if (kind == "strong" and out) else None   # distill parts are staged (weak, strong)
+            weak = out[0] if (kind == "strong" and out) else item.get("weak_mb") if kind == "fstrong" else None
             if stream is None:
-                self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt, weak, aug)
+                self.h2d_bytes += mb.load(data, seed, pass_id, with_gt, weak, aug)
             else:
                 with torch.cuda.stream(stream):
                     if mb.free_event is not None:
                         stream.wait_event(mb.free_event)
-                    self.h2d_bytes += mb.load(data, item["seed"], item["pass_id"], with_gt, weak, aug)
+                    self.h2d_bytes += mb.load(data, seed, pass_id, with_gt, weak, aug)
                     ready = torch.cuda.Event()
                     ready.record(stream)
                 torch.cuda.current_stream().wait_event(ready)
@@ -590,6 +639,102 @@ class B200TrainStep:
                 oh, ow = int(d.get("height", h_in)), int(d.get("width", w_in))
                 out.append({"instances": detector_postprocess(inst, oh, ow)})
         return out
+
+    # ---- fused schedule: teacher pass, then ONE student pass over (source + strong target) images --------------------
+    def _teacher_body(self, bw, gscale, pass_id, base):
+        """First half of aldi/distill.py:144-168 for one micro-batch: teacher trunk + RPN once, pseudo labels.  The
+        outputs stay referenced (`_teacher_out`) because the student pass that consumes them is a separate graph."""
+        t_feats, t_lv, t_rpn_out = self.teacher_forward(bw)
+        pseudo, _ = self.pseudo_label(bw, t_feats, t_lv, t_rpn_out)
+        self.last_pseudo = pseudo
+        if self.debug is not None:
+            self.pseudo_log.append(pseudo)
+        if self.pseudo_override is not None:
+            pseudo = self.pseudo_override[len(self.pseudo_log) - 1]
+        self._teacher_out = {"feats": t_feats, "lv": t_lv, "rpn_out": t_rpn_out, "pseudo": pseudo}
+
+    def _fused_body(self, bsrc, bstr, gscale, pass_ids, bases):
+        """Student forward + backward of a source micro-batch (hard losses against GT) and a distillation micro-batch
+        (soft losses against the teacher) as ONE batch of ns + nt images: the trunk, FPN, RPN head and box head see
+        twice the tiles per launch; labelling, sampling and the losses run per half with that half's seed, salts,
+        ground truth and normalisers, so every loss and gradient equals the two separate passes of the reference
+        (aldi/trainer.py:86-97) up to the order of the floating-point sums."""
+        cfg, det, W = self.cfg, self.det, self.student
+        (pass_src, pass_dst), (base_src, base_dst) = pass_ids, bases
+        ns, nt, R = bsrc.n, bstr.n, cfg.roi_batch
+        n = ns + nt
+        T = self._teacher_out
+        pseudo, t_feats, t_lv, t_rpn_out = T["pseudo"], T["feats"], T["lv"], T["rpn_out"]
+        images = self._mb_cache[("canvas", ns, nt, bsrc.hp, bsrc.wp)]
+        sizes = torch.empty(n, 2, dtype=torch.int32, device=self.device)
+        sizes[:ns].copy_(bsrc.sizes)
+        sizes[ns:].copy_(bstr.sizes)
+        feats, saved = det.backbone(W, images, sizes, save=True)
+        lv = det.levels(feats)
+        rpn_out, rpn_ts = det.rpn_head(W, feats, lv, save=True)
+        props = det.proposals(rpn_out, lv, sizes, cfg.rpn_pre_topk[0], cfg.rpn_post_topk[0], cfg.rpn_nms_thresh, self.err_flag)
+        m = n * R
+        rois = torch.empty(m, 4, device=self.device)
+        roi_gt = torch.empty(m, 4, device=self.device)
+        roi_batch = torch.empty(m, dtype=torch.int32, device=self.device)
+        roi_class = torch.empty(m, dtype=torch.int32, device=self.device)
+        roi_src = torch.empty(m, dtype=torch.int32, device=self.device)
+        roi_count = torch.zeros(n, dtype=torch.int32, device=self.device)
+        roi_stats = torch.zeros(n, 2, dtype=torch.int32, device=self.device)
+        pstride = props["boxes"].shape[1]
+        halves = ((bsrc, bsrc.gt, 0, ns), (bstr, pseudo, ns, nt))
+        for b, gt, i0, k in halves:
+            r0, r1 = i0 * R, (i0 + k) * R
+            ops.call("aldi_roi_label_sample", props["boxes"][i0:i0 + k], props["count"][i0:i0 + k], pstride, k, gt.boxes,
+                     gt.classes, gt.counts, gt.gmax, cfg.roi_iou, cfg.num_classes, R, cfg.roi_pos_fraction, b.seed,
+                     b.salts[sampling.SITE_ROI], 1, rois[r0:r1], roi_batch[r0:r1], roi_class[r0:r1], roi_gt[r0:r1],
+                     roi_src[r0:r1], roi_count[i0:i0 + k], roi_stats[i0:i0 + k])
+        groups = [(0, ns * R, 0, ns), (ns * R, nt * R, ns, nt)]
+        pred, head_saved = det.box_head(W, feats, rois, roi_batch, save=True, groups=groups)
+        # teacher RoI head on the student's sampled TARGET proposals (ReplaceProposalsOnce + shared seed)
+        t_pred, _ = det.box_head(self.teacher, t_feats, rois[ns * R:], roi_batch[ns * R:], save=False)
+        d_rpn = torch.zeros(n, lv.total_locs, 64, device=self.device, dtype=self.dtype)
+        dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
+        w10 = ops.host_floats((10.0, 10.0, 5.0, 5.0))
+        # ---- source half: hard losses (aldi/trainer.py:86-90)
+        labels, matched, _ = self._label_anchors(lv, bsrc, bsrc.gt, sampling.SITE_RPN)
+        ops.call("aldi_rpn_loss", rpn_out[:ns], _l.ctypes.byref(lv), ns, labels, matched, bsrc.gt.boxes, bsrc.gt.counts,
+                 bsrc.gt.gmax, cfg.rpn_batch, 1.0, 1.0, gscale, d_rpn[:ns], self.dtc, 64, 0,
+                 self.loss_acc[base_src + 2:base_src + 4])
+        ops.call("aldi_roi_loss", pred[:ns * R], det.PRED_CH, ns * R, cfg.num_classes, roi_class[:ns * R], rois[:ns * R],
+                 roi_gt[:ns * R], roi_count[:ns], ns, w10, 1.0, 1.0, gscale, dpred[:ns * R], self.dtc, 64,
+                 self.loss_acc[base_src:base_src + 2])
+        # ---- target half: distillation losses (aldi/distill.py:170-278)
+        hard_rpn = cfg.do_hard_obj or cfg.do_hard_rpn_reg
+        acc = 0
+        if hard_rpn:
+            hl, hm, _ = self._label_anchors(lv, bstr, pseudo, sampling.SITE_RPN)
+            ops.call("aldi_rpn_loss", rpn_out[ns:], _l.ctypes.byref(lv), nt, hl, hm, pseudo.boxes, pseudo.counts, pseudo.gmax,
+                     cfg.rpn_batch, 1.0 if cfg.do_hard_obj else 0.0, 1.0 if cfg.do_hard_rpn_reg else 0.0, gscale,
+                     d_rpn[ns:], self.dtc, 64, 0, self.loss_acc[base_dst + 2:base_dst + 4])
+            acc = 1
+        dlabels, _, dstats = self._label_anchors(t_lv, bstr, pseudo, sampling.SITE_RPN_DISTILL)   # T2
+        ops.call("aldi_distill_rpn_loss", rpn_out[ns:], t_rpn_out, _l.ctypes.byref(lv), nt, dlabels, dstats,
+                 cfg.obj_temperature, 1.0 if cfg.do_obj_dst else 0.0, 1.0 if cfg.do_rpn_reg_dst else 0.0, gscale, d_rpn[ns:],
+                 self.dtc, 64, acc, self.loss_acc[base_dst + 4:base_dst + 6])
+        acc = 0
+        if cfg.do_hard_cls or cfg.do_hard_roi_reg:
+            ops.call("aldi_roi_loss", pred[ns * R:], det.PRED_CH, nt * R, cfg.num_classes, roi_class[ns * R:], rois[ns * R:],
+                     roi_gt[ns * R:], roi_count[ns:], nt, w10, 1.0 if cfg.do_hard_cls else 0.0,
+                     1.0 if cfg.do_hard_roi_reg else 0.0, gscale, dpred[ns * R:], self.dtc, 64,
+                     self.loss_acc[base_dst:base_dst + 2])
+            acc = 1
+        ops.call("aldi_distill_roi_loss", pred[ns * R:], t_pred, det.PRED_CH, nt * R, cfg.num_classes, roi_class[ns * R:],
+                 roi_count[ns:], nt, cfg.cls_temperature, 1 if cfg.cls_loss_type == "KL" else 0,
+                 1.0 if cfg.do_cls_dst else 0.0, 1.0 if cfg.do_roih_reg_dst else 0.0, gscale, dpred[ns * R:], self.dtc, 64, acc,
+                 self.loss_acc[base_dst + 6:base_dst + 8])
+        if self.debug is not None:
+            fw_t = {"lv": lv, "rpn_out": rpn_out[ns:], "pred": pred[ns * R:], "roi_count": roi_count[ns:],
+                    "rois": rois[ns * R:], "roi_class": roi_class[ns * R:], "roi_batch": roi_batch[ns * R:]}
+            self.debug = {"fw": fw_t, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": dlabels, "stats": dstats,
+                          "pseudo": pseudo}
+        det.backward(W, self.grad, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch,
+                     on_ready=self._bucket_ready(), groups=groups)
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
     def _distill_body(self, bw, bs, gscale, pass_id, base=SLOT_BASE["distill"]):

@@ -137,7 +137,7 @@ def test_step_derives_strong_views_on_the_device():
     random.seed(1)
     losses = dict(step.run_model((None, ls, uw, us_dev)).items())
     assert all(np.isfinite(v) for v in losses.values())
-    strong_mb = [m for k, m in step._mb_cache.items() if k[0] == "strong"][0]
+    strong_mb = [m for k, m in step._mb_cache.items() if k[0] in ("strong", "fstrong")][0]
     for i, (d, p) in enumerate(zip(uw, params)):
         want = aug_ref.strong_augment(d["image"].permute(1, 2, 0).numpy(), p)
         got = strong_mb.images[i, :, :96, :128].permute(1, 2, 0).cpu().numpy()
