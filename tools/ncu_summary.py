@@ -27,7 +27,7 @@ def main():
     for r in rd:
         if len(r) <= iv:
             continue
-        d = launches.setdefault(r[ii], {"name": re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("(anonymous namespace)::", ""),
+        d = launches.setdefault(r[ii], {"name": re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", ""),
                                         "ns": 0.0, "rd": None, "wr": None})
         v = float(r[iv].replace(",", ""))
         if r[im] == "gpu__time_duration.sum":
