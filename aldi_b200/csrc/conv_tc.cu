@@ -46,6 +46,10 @@ constexpr int kEpiChunk = 64;                    // channels per epilogue chunk 
 constexpr int kEpiBytes = kBlockM * kEpiChunk * 2;  // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kMaxEpiBufs = 8;
+constexpr int kHaloW = 16;                         // halo row pitch in pixels: 8-row swizzle groups stay 1024-aligned
+constexpr int kHaloH = 18;                         // 16 output rows + 2
+constexpr int kHaloBytes = kHaloH * kHaloW * 128;  // 36 KB per 64-channel chunk
+constexpr int kMaxHaloStages = 4;
 constexpr int kSmemLimit = 226 * 1024;     // dynamic budget (static barriers etc. live in the remaining 1 KB)
 
 struct ConvArgs {
@@ -70,6 +74,10 @@ struct ConvArgs {
   int tma_epi;       // bf16 output through shared memory + TMA store
   int epi_res, epi_mask;  // residual / mask tiles arrive by TMA (tma_epi only)
   int epi_bufs;      // depth of the residual / mask tile ring (2..4): bytes in flight for the HBM-bound layers
+  int halo;          // 3x3 small-channel mode: the A operand of all 9 taps comes from ONE halo tile per 64-channel chunk
+  int halo_stages;   // depth of the halo ring (each 18 x 16 pixels x 128 B = 36 KB)
+  int halo_bo;       // descriptor base-offset convention (1: tap column shift, 2: zero) — bring-up knob
+  int b_resident;    // halo mode, one N tile: all 9 x kchunks weight blocks stay in shared memory for the whole kernel
   int epi_prefetch;  // tiles ahead whose residual / mask boxes warp 2 prefetches into the L2 (0 = off)
   int a_prefetch;    // K blocks ahead of the smem ring whose A boxes warp 0 prefetches into the L2 (0 = off)
   int debug;         // ALDI_CONV_DEBUG (perf bisection only): 1 no TMA store, 2 also no smem staging, 3 empty epilogue
@@ -123,12 +131,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // [stages x (A | B)] [out x2] [res x2] [mask x2]   (all 16 KB pieces, 1024-byte aligned)
-  uint8_t* s_out = smem + a.stages * C::kStageBytes;
+  // halo mode: [halo_stages x 36 KB] [stages x B] [out] [res] [mask]
+  uint8_t* s_bring = smem + (a.halo ? a.halo_stages * kHaloBytes : 0);
+  uint8_t* s_out = a.halo ? s_bring + a.stages * C::kBBytes : smem + a.stages * C::kStageBytes;
   uint8_t* s_res = s_out + 2 * kEpiBytes;
   uint8_t* s_mask = s_res + (a.epi_res ? a.epi_bufs * kEpiBytes : 0);
 
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t halo_full_bar[kMaxHaloStages];
+  __shared__ __align__(8) uint64_t halo_empty_bar[kMaxHaloStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t epi_full_bar[kMaxEpiBufs];
@@ -148,6 +160,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kMaxHaloStages; ++i) {
+      mbar_init(&halo_full_bar[i], 1);
+      mbar_init(&halo_empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -173,8 +189,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hstage = 0;
+      uint32_t phase = 0, hphase = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int n_tile = tile % a.num_n_tiles;
         int m_tile = tile / a.num_n_tiles;
@@ -183,6 +199,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int thi = m_tile % a.tiles_h;
         const int img = m_tile / a.tiles_h;
         const int h0 = thi * a.th, w0 = twi * a.tw;
+        if (a.halo) {
+          // one halo tile per 64-channel chunk feeds all nine taps; the weights stream through the B ring, or are
+          // loaded once when all of them fit (a stage of 8 KB is 128 cycles of MMA work: no ring hides TMA latency)
+          if (a.b_resident && tile == (int)blockIdx.x) {
+            mbar_expect_tx(&full_bar[0], (uint32_t)(9 * a.kchunks) * C::kBBytes);
+            for (int i = 0; i < 9 * a.kchunks; ++i)
+              tma_load_2d(s_bring + i * C::kBBytes, &tmB, &full_bar[0], i * kBlockK, n_tile * BLOCK_N);
+          }
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&halo_empty_bar[hstage], hphase ^ 1);
+            mbar_expect_tx(&halo_full_bar[hstage], kHaloBytes);
+            tma_load_4d(smem + hstage * kHaloBytes, &tmA, &halo_full_bar[hstage], kc * kBlockK, w0 - a.pad_w, h0 - a.pad_h, img);
+            if (++hstage == a.halo_stages) { hstage = 0; hphase ^= 1; }
+            for (int tap = 0; tap < 9 && !a.b_resident; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], C::kBBytes);
+              tma_load_2d(s_bring + stage * C::kBBytes, &tmB, &full_bar[stage], (tap * a.kchunks + kc) * kBlockK, n_tile * BLOCK_N);
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         if (a.a_prefetch) {
           // 1x1 layers stream x straight from HBM: warm the L2 with the NEXT tile's A boxes while this tile runs
           const int nt = tile + gridDim.x;
@@ -213,8 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hstage = 0;
+      uint32_t phase = 0, hphase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -222,6 +260,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if (a.halo) {
+          if (a.b_resident && it == 0) {
+            mbar_wait(&full_bar[0], 0);
+            tc_fence_after();
+          }
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&halo_full_bar[hstage], hphase);
+            tc_fence_after();
+            const uint32_t hbase = smem_u32(smem + hstage * kHaloBytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int r = tap / 3, sx = tap - r * 3;
+              if (a.b_resident) {
+                uint64_t adesc = make_smem_desc_sw128(hbase + (uint32_t)((r * kHaloW + sx) * 128), 16, kHaloW * 128);
+                const uint64_t bdesc =
+                    make_smem_desc_sw128(smem_u32(s_bring + (tap * a.kchunks + kc) * C::kBBytes), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
+                continue;
+              }
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              // rows of the shifted operand: pixel (ty + r, tx + sx) of the halo; 8 pixels of one tile row are one
+              // swizzle group (stride 128 B), the next tile row is kHaloW pixels = 2048 B further
+              uint64_t adesc = make_smem_desc_sw128(hbase + (uint32_t)((r * kHaloW + sx) * 128), 16, kHaloW * 128);
+              if (a.halo_bo == 1) adesc |= (uint64_t)(sx & 7) << 49;
+              const uint64_t bdesc = make_smem_desc_sw128(smem_u32(s_bring + stage * C::kBBytes), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&halo_empty_bar[hstage]);
+            if (++hstage == a.halo_stages) { hstage = 0; hphase ^= 1; }
+          }
+          umma_commit(&tmem_full_bar[acc]);
+          continue;
+        }
         for (int kb = 0; kb < a.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -681,12 +758,45 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
     ++epi_bufs;
     epi_total += set_bytes;
   }
-  const int smem_bytes = stages * stage_bytes + epi_total + 1024;
+  int smem_bytes = stages * stage_bytes + epi_total + 1024;
 
   int th, tw;
   pick_patch(p->ho, p->wo, (tma_epi && res_mode == 2) ? 64 : 128, &th, &tw);
+  // 3x3 layers with few channels: load ONE 18 x 16-pixel halo tile per 64-channel chunk and address the nine shifted
+  // A operands inside it (UMMA swizzles on absolute shared-memory address bits: a start address shifted by whole
+  // 128-byte rows needs NO descriptor base offset as long as the 8-row groups stay 1024-byte aligned — measured,
+  // tools/gpu_diag.py --case halo), with all 9 weight blocks resident in shared memory.  Measured 111.7 -> 89.1 us for
+  // res2's 3x3 64 -> 64 at 4 x 256 x 512; what is left is the tensor pipe itself: a 128 x N x 16 tcgen05.mma costs the
+  // same ~128 cycles for N = 64, 128 or 256 (the 3x3 layers scale 1 : 2 : 4 with N at every size), so N = 64 tiles
+  // cannot pass 25 % of the bf16 peak.  With streamed weights (128 channels) the halo path is no faster, so it is
+  // taken only when the weights fit.  ALDI_CONV_HALO: 0 off, 2 default, 3 also with streamed weights, 1 = base-offset
+  // = tap column (wrong results; kept as the record of the descriptor experiment).
+  static const char* halo_env = getenv("ALDI_CONV_HALO");
+  const int halo_mode = halo_env ? atoi(halo_env) : 2;
+  int halo = 0, halo_stages = 0, b_resident = 0;
+  if (halo_mode > 0 && p->taps_h == 3 && p->taps_w == 3 && p->x_c <= 128 && res_mode != 2 && block_n <= 128) {
+    const int bbytes = block_n * kBlockK * 2;
+    const int nb = 9 * (p->x_c / 64);
+    // weights resident when they fit beside two halo stages (64 -> 64: 72 KB); else a deeper ring
+    const bool resident = p->cout_p == block_n && nb * bbytes + 2 * kHaloBytes + out_bytes + 2 * set_bytes + 1024 <= kSmemLimit;
+    b_resident = resident ? 1 : 0;
+    int bst = resident ? nb : 6;
+    while (!resident && bst > 3 && (kSmemLimit - 1024 - out_bytes - 2 * set_bytes - bst * bbytes) / kHaloBytes < 2) --bst;
+    int hst = (kSmemLimit - 1024 - out_bytes - 2 * set_bytes - bst * bbytes) / kHaloBytes;
+    if (hst > kMaxHaloStages) hst = kMaxHaloStages;
+    if (hst >= 2 && (resident || halo_mode == 3)) {
+      halo = 1; halo_stages = hst; th = 16; tw = 8;
+      stages = bst;
+      epi_bufs = 2;
+      int used = halo_stages * kHaloBytes + bst * bbytes + out_bytes + 2 * set_bytes + 1024;
+      while (set_bytes && epi_bufs < kMaxEpiBufs && used + set_bytes <= kSmemLimit) { ++epi_bufs; used += set_bytes; }
+    }
+  }
 
+  if (halo)
+    smem_bytes = halo_stages * kHaloBytes + stages * block_n * kBlockK * 2 + out_bytes + (set_bytes ? epi_bufs * set_bytes : 0) + 1024;
   ConvArgs a;
+  a.halo = halo; a.halo_stages = halo_stages; a.halo_bo = halo_mode; a.b_resident = halo ? b_resident : 0;
   a.n = p->n; a.ho = p->ho; a.wo = p->wo;
   a.th = th; a.tw = tw;
   a.tw_shift = 0;
@@ -723,7 +833,8 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   a.debug = dbg ? atoi(dbg) : 0;
 
   CUtensorMap tm[5];
-  int rc = make_cl_tmap(&tm[0], p->x, p->x_c, p->x_w, p->x_h, p->x_n, p->x_sw, p->x_sh, p->x_sn, tw, th);
+  int rc = make_cl_tmap(&tm[0], p->x, p->x_c, p->x_w, p->x_h, p->x_n, p->x_sw, p->x_sh, p->x_sn, halo ? kHaloW : tw,
+                        halo ? kHaloH : th);
   if (rc) return rc;
   {
     uint64_t ktot = (uint64_t)p->taps_h * p->taps_w * p->x_c;

@@ -247,3 +247,22 @@ def test_segmented_nms_equals_sorted_nms(seed, quant):
             assert c > 0
             for k in ("src", "cats", "scores", "boxes"):
                 assert torch.equal(a[k][i, :c], b[k][i, :c]), (post, i, k)
+
+
+def test_conv_halo_path_matches_fp32_kernel():
+    """conv_tc's halo-tile mode (3x3, 64 -> 64 channels: nine shifted UMMA operands inside one shared-memory tile,
+    resident weights) against the fp32 CUDA-core kernel, on sizes that are not multiples of the 16 x 8 tile."""
+    from aldi_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n, h, w in ((2, 48, 72), (1, 37, 50), (3, 16, 8)):
+        x = torch.randn(n, h, w, 64, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(64, 9 * 64, device="cuda", generator=g) / 24.0).bfloat16()
+        sc = torch.rand(64, device="cuda", generator=g) + 0.5
+        bi = torch.randn(64, device="cuda", generator=g)
+        out = torch.zeros(n, h, w, 64, device="cuda", dtype=torch.bfloat16)
+        ref = torch.zeros(n, h, w, 64, device="cuda", dtype=torch.float32)
+        ops.conv(x, wt, out, taps_h=3, taps_w=3, pad_h=1, pad_w=1, scale=sc, bias=bi, relu=True)
+        ops.conv(x.float(), wt.float(), ref, taps_h=3, taps_w=3, pad_h=1, pad_w=1, scale=sc, bias=bi, relu=True)
+        torch.cuda.synchronize()
+        err = (out.float() - ref).abs().max() / ref.abs().max()
+        assert float(err) < 1e-2, (n, h, w, float(err))

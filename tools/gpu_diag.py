@@ -485,6 +485,55 @@ def case_perf_res4():
     return True
 
 
+def case_halo():
+    """3x3 convs with <= 128 input channels through the halo-tile path (ALDI_CONV_HALO=1|2 in the environment):
+    numerics against the fp32 CUDA-core kernel on odd sizes, then timing at the production sizes."""
+    import torch
+    from aldi_b200 import ops
+    ok = True
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for name, n, h, w, cin, cout, extra in (("c64 plain", 2, 48, 72, 64, 64, {}), ("c64 bn+relu", 1, 37, 50, 64, 64, {"bn": True}),
+                                            ("c128 plain", 2, 32, 40, 128, 128, {}), ("c128 mask", 1, 40, 24, 128, 128, {"mask": True}),
+                                            ("c128 acc", 1, 16, 16, 128, 128, {"acc": True})):
+        x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(cout, 9 * cin, device="cuda", generator=g) / (9 * cin) ** 0.5).bfloat16()
+        kw, kwf = {}, {}
+        if extra.get("bn"):
+            sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+            bi = torch.randn(cout, device="cuda", generator=g)
+            kw = kwf = dict(scale=sc, bias=bi, relu=True)
+        out = torch.zeros(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+        ref = torch.zeros(n, h, w, cout, device="cuda", dtype=torch.float32)
+        if extra.get("mask"):
+            m = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+            kw, kwf = dict(mask=m), dict(mask=m.float())
+        if extra.get("acc"):
+            out = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+            ref = out.float().clone()
+            kw = kwf = dict(accumulate=True)
+        ops.conv(x, wt, out, taps_h=3, taps_w=3, pad_h=1, pad_w=1, **kw)
+        ops.conv(x.float(), wt.float(), ref, taps_h=3, taps_w=3, pad_h=1, pad_w=1, **kwf)
+        torch.cuda.synchronize()
+        ok &= report("halo " + name, out, ref)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for name, n, h, w, c in (("3x3 64->64 4x256x512", 4, 256, 512, 64), ("3x3 64->64 8x256x512", 8, 256, 512, 64),
+                             ("3x3 128->128 8x128x256", 8, 128, 256, 128)):
+        x = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(c, 9 * c, device="cuda", generator=g) / (9 * c) ** 0.5).bfloat16()
+        out = torch.empty(n, h, w, c, device="cuda", dtype=torch.bfloat16)
+        ts = []
+        for _ in range(8):
+            flush.zero_()
+            e0.record()
+            ops.conv(x, wt, out, taps_h=3, taps_w=3, pad_h=1, pad_w=1)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        t = sorted(ts[2:])[3]
+        print("[halo perf] %s: %.1f us  %.0f TFLOP/s" % (name, t, 2.0 * n * h * w * 9 * c * c / t / 1e6), flush=True)
+    return ok
+
+
 CASES = [
     "optim", "fwd_f32", "bwd_f32",
     "fwd_1x1_min", "fwd_1x1_k256", "fwd_1x1_n128", "fwd_3x3", "fwd_3x3_big", "fwd_epilogue", "fwd_epilogue2",
