@@ -36,6 +36,9 @@ struct WgradArgs {
   const float* scale;
   float* dw;
   int cout_store, cin_store;
+  int tap_pair;   // cin == 128: one N = 256 MMA covers TWO taps (x boxes of tap 2i | tap 2i+1 side by side) — a
+                  // 128 x N x 16 tcgen05.mma costs the same for N = 128 and N = 256; `taps` then counts tap PAIRS
+  int taps_real;
 };
 
 template <int BLOCK_N, int MH>
@@ -121,10 +124,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 #pragma unroll
           for (int b = 0; b < C::kABoxes; ++b)
             tma_load_4d(sa + b * kBoxBytes, &tmY, &full_bar[stage], mt * kBlockM * MH + b * 64, w0, h0, img);
+          if (a.tap_pair) {
+            // boxes 0,1: channels 0-63 / 64-127 of tap 2*tap; boxes 2,3: the same of tap 2*tap+1 (clamped: the odd
+            // ninth tap is computed twice and stored once)
 #pragma unroll
-          for (int b = 0; b < C::kNB; ++b)
-            tma_load_4d(sb + b * kBoxBytes, &tmX, &full_bar[stage], nt * BLOCK_N + b * 64, w0 + s - a.pad_w,
-                        h0 + r - a.pad_h, img);
+            for (int b = 0; b < C::kNB; ++b) {
+              int t2 = 2 * tap + (b >> 1);
+              if (t2 >= a.taps_real) t2 = a.taps_real - 1;
+              const int r2 = t2 / a.taps_w, s2 = t2 - r2 * a.taps_w;
+              tma_load_4d(sb + b * kBoxBytes, &tmX, &full_bar[stage], (b & 1) * 64, w0 + s2 - a.pad_w, h0 + r2 - a.pad_h,
+                          img);
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < C::kNB; ++b)
+              tma_load_4d(sb + b * kBoxBytes, &tmX, &full_bar[stage], nt * BLOCK_N + b * 64, w0 + s - a.pad_w,
+                          h0 + r - a.pad_h, img);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -183,12 +199,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const int cout = (mt * MH + half) * kBlockM + row;
         const bool valid = cout < a.cout_store;
         const float sc = (valid && a.scale) ? __ldg(a.scale + cout) : 1.f;
-        float* drow = a.dw + ((long long)cout * a.taps + tap) * a.cin_store;
+        int tap_out = tap, cbase = nt * BLOCK_N + c0;
+        bool store = true;
+        if (a.tap_pair) {
+          tap_out = 2 * tap + (c0 >= 128 ? 1 : 0);
+          cbase = c0 & 127;
+          store = tap_out < a.taps_real;
+        }
+        float* drow = a.dw + ((long long)cout * a.taps_real + tap_out) * a.cin_store;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MH + half) * BLOCK_N + c0), raw);
         tmem_ld_wait();
-        const int cbase = nt * BLOCK_N + c0;
-        if (valid && cbase < a.cin_store) {
+        if (valid && store && cbase < a.cin_store) {
           if (vec_ok && cbase + 32 <= a.cin_store) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -272,6 +294,9 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
                  "aldi_wgrad_tc: x/dy must be 16-byte aligned");
 
   int block_n = (p->x_c % 256 == 0) ? 256 : (p->x_c % 128 == 0) ? 128 : 64;
+  static const char* no_pair = getenv("ALDI_WGRAD_NO_TAP_PAIR");
+  const bool tap_pair = !no_pair && p->x_c == 128 && p->cin_store == 128 && p->taps_h * p->taps_w > 1;
+  if (tap_pair) block_n = 256;
   int th, tw;
   pick_patch64(p->ho, p->wo, &th, &tw);
 
@@ -280,7 +305,9 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
   a.tiles_h = aldi_div_up(p->ho, th);
   a.tiles_w = aldi_div_up(p->wo, tw);
   a.pix_tiles = p->n * a.tiles_h * a.tiles_w;
-  a.taps = p->taps_h * p->taps_w;
+  a.taps_real = p->taps_h * p->taps_w;
+  a.tap_pair = tap_pair ? 1 : 0;
+  a.taps = tap_pair ? (a.taps_real + 1) / 2 : a.taps_real;
   a.taps_w = p->taps_w;
   a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   // 256-row M tile when cout allows and the items are long enough (split-K atomics dominate short ones)
@@ -290,7 +317,7 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
   const bool long_items = force_mh2 || ((p->taps_h * p->taps_w > 1) ? pix_tiles0 >= 1024 : pix_tiles0 >= 4096);
   const int mh = (!force_mh1 && p->dy_c % 256 == 0 && p->cout_store > kBlockM && long_items) ? 2 : 1;
   a.m_tiles = aldi_div_up(p->cout_store, kBlockM * mh);
-  a.n_tiles = aldi_div_up(p->cin_store, block_n);
+  a.n_tiles = tap_pair ? 1 : aldi_div_up(p->cin_store, block_n);
   int base_items = a.taps * a.m_tiles * a.n_tiles;
   // split K so that there are ~2 waves of work items but each keeps >= 8 pixel tiles
   static const char* waves_env = getenv("ALDI_WGRAD_WAVES");  // perf bisection: work-item waves the split-K aims at

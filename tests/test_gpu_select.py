@@ -266,3 +266,20 @@ def test_conv_halo_path_matches_fp32_kernel():
         torch.cuda.synchronize()
         err = (out.float() - ref).abs().max() / ref.abs().max()
         assert float(err) < 1e-2, (n, h, w, float(err))
+
+
+@pytest.mark.parametrize("cin,cout,k", [(128, 128, 3), (128, 512, 1), (256, 256, 3), (128, 128, 1)])
+def test_wgrad_tc_matches_fp32_kernel(cin, cout, k):
+    """wgrad_tc (incl. the tap-paired N = 256 mode for 128 input channels) against the fp32 CUDA-core kernel."""
+    from aldi_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n, h, w = 2, 40, 56
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+    dw = torch.zeros(cout, k * k * cin, device="cuda")
+    ref = torch.zeros(cout, k * k * cin, device="cuda")
+    ops.wgrad(x, dy, dw, taps_h=k, taps_w=k, pad_h=k // 2, pad_w=k // 2)
+    ops.wgrad(x.float(), dy.float(), ref, taps_h=k, taps_w=k, pad_h=k // 2, pad_w=k // 2)
+    torch.cuda.synchronize()
+    err = (dw - ref).abs().max() / ref.abs().max()
+    assert float(err) < 5e-3, float(err)
