@@ -694,6 +694,8 @@ int make_cl_tmap(CUtensorMap* tm, const void* base, int c, int w, int h, int n, 
 
 }  // namespace
 
+int aldi_conv_tn_try(const aldi_conv_params* p, cudaStream_t stream, int* handled);   // conv_tn.cu
+
 extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(p && p->x && p->w && p->out, "aldi_conv_tc: null pointer");
@@ -725,6 +727,12 @@ extern "C" int aldi_conv_tc(const aldi_conv_params* p, void* stream_) {
 
   // bf16 outputs whose channel extent is a whole number of 64-channel chunks leave through TMA; `accumulate`
   // becomes "residual = the output tile itself" (never combined with another residual by the callers)
+  {
+    // few output channels, several taps: pixels go on the MMA's N dimension (conv_tn.cu)
+    int handled = 0;
+    const int rc = aldi_conv_tn_try(p, stream, &handled);
+    if (rc || handled) return rc;
+  }
   const bool tma_epi = p->out_dtype == ALDI_DTYPE_BF16 && p->cout_store == p->cout_p && !(p->accumulate && p->res_mode);
   const bool epi_res = tma_epi && (p->res_mode || p->accumulate);
   const bool epi_mask = tma_epi && p->mask;
