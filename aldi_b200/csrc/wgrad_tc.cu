@@ -27,7 +27,8 @@ namespace {
 constexpr int kBlockM = 128;   // cout rows per MMA (one or two of them per item)
 constexpr int kPix = 64;       // pixels (K) per stage
 constexpr int kBoxBytes = kPix * 128;  // 8 KB per 64-channel box
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;   // warps: 0 TMA, 1 MMA, 2-5 epilogue, 6-9 bias-gradient column sums
+constexpr int kSumWarps = 4;
 
 struct WgradArgs {
   int tiles_h, tiles_w, th, tw, pix_tiles;
@@ -36,6 +37,7 @@ struct WgradArgs {
   const float* scale;
   float* dw;
   int cout_store, cin_store;
+  float* dbias;   // bias gradient fused into this pass (nullable): column sums of the dy stages already in shared memory
   int tap_pair;   // cin == 128: one N = 256 MMA covers TWO taps (x boxes of tap 2i | tap 2i+1 side by side) — a
                   // 128 x N x 16 tcgen05.mma costs the same for N = 128 and N = 256; `taps` then counts tap PAIRS
   int taps_real;
@@ -84,7 +86,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     prefetch_tmap(&tmX);
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], a.dbias ? 1 + kSumWarps : 1);   // the MMA commit + (if present) the column-sum warps
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -179,6 +181,67 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp >= 6) {
+    // ---- bias gradient: dbias[co] += sum over pixels of dy[pixel, co], from the dy boxes the MMA is consuming anyway.
+    // Items with tap 0 and cin tile 0 cover every (cout tile, pixel range) exactly once.  A box is 64 pixel rows x
+    // 128 B (64 channels), 128-byte swizzled: lane l reads 16-byte chunk (l & 7) of rows (l >> 3) + 4 i.
+    if (a.dbias) {
+      const int sw = warp - 6;   // this warp sums boxes sw, sw + kSumWarps, ...
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+        int tap, nt, mt, ks;
+        decode_item(a, item, tap, nt, mt, ks);
+        const bool mine = tap == 0 && nt == 0;
+        const int pt0 = (int)((long long)a.pix_tiles * ks / a.ksplit);
+        const int pt1 = (int)((long long)a.pix_tiles * (ks + 1) / a.ksplit);
+        float acc[C::kABoxes][8];
+#pragma unroll
+        for (int b = 0; b < C::kABoxes; ++b)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[b][k] = 0.f;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          if (mine) {
+            const uint8_t* sa = smem + stage * C::kStageBytes;
+            const int chunk = lane & 7, r0 = lane >> 3;
+#pragma unroll
+            for (int b = 0; b < C::kABoxes; ++b) {
+              if ((b % kSumWarps) != sw) continue;
+#pragma unroll 4
+              for (int i = 0; i < 16; ++i) {
+                const int r = r0 + 4 * i;
+                const uint4 q4 = *reinterpret_cast<const uint4*>(sa + b * kBoxBytes + r * 128 + ((chunk ^ (r & 7)) << 4));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __bfloat1622float2(h[k]);
+                  acc[b][2 * k] += f.x;
+                  acc[b][2 * k + 1] += f.y;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int b = 0; b < C::kABoxes; ++b) {
+            if ((b % kSumWarps) != sw) continue;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float v = acc[b][k];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              const int cout = mt * kBlockM * MH + b * 64 + (lane & 7) * 8 + k;
+              if (lane < 8 && cout < a.cout_store) atomicAdd(a.dbias + cout, v);
+            }
+          }
+        }
       }
     }
   } else {
@@ -328,6 +391,7 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
   a.num_items = base_items * a.ksplit;
   a.scale = p->scale;
   a.dw = p->dw;
+  a.dbias = p->dbias;
   a.cout_store = p->cout_store;
   a.cin_store = p->cin_store;
 

@@ -12,6 +12,7 @@ Detectron2 for the reference (aldi/model.py:27-29 -> detectron2 GeneralizedRCNN;
 There is no PyTorch-op fallback: torch only allocates memory.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -499,9 +500,15 @@ class Detector:
     def _wgrad(self, W, G, name, x, dy):
         g = W.geom[name]
         xv = x[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else x
+        # bias gradient: aldi_wgrad_tc can sum the dy tiles it already holds in shared memory (dbias=).  Measured: the
+        # four extra warps' shared-memory reads slow the MMA pipeline by as much as the 21 aldi_colsum launches cost
+        # (wgrad 6.83 -> 7.36 ms, colsum 0.75 -> 0 ms per step: 30.79 vs 30.77 ms), so the separate kernel stays the
+        # default; ALDI_FUSED_DBIAS=1 selects the fused path.
+        fused_bias = (not g.norm) and dy.dtype == torch.bfloat16 and os.environ.get("ALDI_FUSED_DBIAS") == "1"
         ops.wgrad(xv, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
-                  scale=W.scale.get(name), cout_store=g.cout, cin_store=g.cin)
-        if not g.norm:
+                  scale=W.scale.get(name), cout_store=g.cout, cin_store=g.cin,
+                  dbias=W.view(name, "bias", G) if fused_bias else None)
+        if not g.norm and not fused_bias:
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             assert dy.is_contiguous()
             ops.call("aldi_colsum", dy, _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32, 1, rows, 0, dy.shape[3], g.cout,
@@ -636,8 +643,11 @@ class Detector:
     def _wgrad_strided_bias(self, W, G, name, x, dy):
         """wgrad + bias grad where dy is a strided level view of the concatenated RPN gradient map."""
         g = W.geom[name]
+        fused_bias = dy.dtype == torch.bfloat16 and os.environ.get("ALDI_FUSED_DBIAS") == "1"
         ops.wgrad(x, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
-                  cout_store=g.cout, cin_store=g.cin)
+                  cout_store=g.cout, cin_store=g.cin, dbias=W.view(name, "bias", G) if fused_bias else None)
+        if fused_bias:
+            return
         n, h, w, c = dy.shape
         dtc = _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32
         # rows of one image's level slab are contiguous; images are total_locs * c apart

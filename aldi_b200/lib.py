@@ -39,6 +39,7 @@ class WgradParams(ctypes.Structure):
         ("n", c_int), ("ho", c_int), ("wo", c_int),
         ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int), ("stride", c_int),
         ("scale", c_void_p), ("dw", c_void_p), ("cout_store", c_int), ("cin_store", c_int),
+        ("dbias", c_void_p),
     ]
 
 

@@ -173,7 +173,7 @@ def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
 
 
 def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, cout_store=None,
-          cin_store=None):
+          cin_store=None, dbias=None):
     """dw[co, tap, ci] += scale[co] * sum_pixels dy[pixel, co] * x[pixel shifted by tap, ci]  (fp32 atomics)."""
     n, xh, xw, xc, x_sn, x_sh, x_sw = _cl4(x, "x")
     dn, oh, ow, dc, d_sn, d_sh, d_sw = _cl4(dy, "dy")
@@ -186,6 +186,7 @@ def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
     p.taps_h = taps_h; p.taps_w = taps_w; p.pad_h = pad_h; p.pad_w = pad_w; p.stride = stride
     p.scale = scale.data_ptr() if scale is not None else None
     p.dw = dw.data_ptr()
+    p.dbias = dbias.data_ptr() if (dbias is not None and x.dtype == torch.bfloat16) else None
     p.cout_store = int(cout_store if cout_store is not None else dc)
     p.cin_store = int(cin_store if cin_store is not None else xc)
     assert dw.numel() == p.cout_store * taps_h * taps_w * p.cin_store

@@ -133,6 +133,8 @@ typedef struct {
   const float* scale;       /* [dy_c] or NULL */
   float* dw;                /* fp32 [cout_store][taps][cin_store] */
   int cout_store, cin_store;
+  float* dbias;             /* NULL, or fp32 [cout_store]: dbias[co] += sum_{n,h,w} dy[n,h,w,co] in the same pass
+                             * (the bias gradient of the layer; aldi_wgrad_tc only, aldi_wgrad_f32 ignores it) */
 } aldi_wgrad_params;
 int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream);
 int aldi_wgrad_f32(const aldi_wgrad_params* p, void* stream);

@@ -283,3 +283,24 @@ def test_wgrad_tc_matches_fp32_kernel(cin, cout, k):
     torch.cuda.synchronize()
     err = (dw - ref).abs().max() / ref.abs().max()
     assert float(err) < 5e-3, float(err)
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(256, 256, 3, (40, 56)), (1024, 256, 1, (24, 40)), (256, 64, 1, (64, 64)),
+                                           (128, 128, 3, (33, 47)), (12544, 1024, 1, (1, 300))])
+def test_wgrad_fused_bias_gradient(cin, cout, k, hw):
+    """aldi_wgrad_tc(dbias=): the bias gradient summed from the dy stages inside the weight-gradient kernel must equal
+    aldi_colsum (incl. split-K items, several cout tiles, ragged pixel tiles, the box head's (1,1,M,C) layout)."""
+    from aldi_b200 import lib as _l, ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n, (h, w) = 2, hw
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+    store = cout if cout != 64 else 41                        # predictor-like: 41 of 64 padded channels
+    dw = torch.zeros(store, k * k * cin, device="cuda")
+    db = torch.zeros(store, device="cuda")
+    ops.wgrad(x, dy, dw, taps_h=k, taps_w=k, pad_h=k // 2, pad_w=k // 2, cout_store=store, dbias=db)
+    ref = torch.zeros(store, device="cuda")
+    ops.call("aldi_colsum", dy, _l.BF16, 1, n * h * w, 0, cout, store, 1.0, ref)
+    torch.cuda.synchronize()
+    assert torch.allclose(db, ref, rtol=1e-4, atol=1e-2), float((db - ref).abs().max())
+    assert float(ref.abs().max()) > 1.0
