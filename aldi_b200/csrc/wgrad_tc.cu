@@ -384,7 +384,11 @@ extern "C" int aldi_wgrad_tc(const aldi_wgrad_params* p, void* stream_) {
   int base_items = a.taps * a.m_tiles * a.n_tiles;
   // split K so that there are ~2 waves of work items but each keeps >= 8 pixel tiles
   static const char* waves_env = getenv("ALDI_WGRAD_WAVES");  // perf bisection: work-item waves the split-K aims at
-  const int waves = (waves_env && atoi(waves_env) >= 1) ? atoi(waves_env) : 2;
+  static const char* waves2_env = getenv("ALDI_WGRAD_WAVES_MH2");
+  int waves = (waves_env && atoi(waves_env) >= 1) ? atoi(waves_env) : 2;
+  // measured: one wave of longer items for the 256-row tile (whose epilogue cannot overlap the next main loop) is
+  // slower than two (wgrad 7.36 vs 6.84 ms per step), so both tile heights aim at two waves
+  if (mh == 2 && waves2_env && atoi(waves2_env) >= 1) waves = atoi(waves2_env);
   int want = aldi_div_up(waves * aldi_num_sms(), base_items);
   int max_split = a.pix_tiles / 8 > 0 ? a.pix_tiles / 8 : 1;
   a.ksplit = want < 1 ? 1 : (want > max_split ? max_split : want);
