@@ -376,10 +376,17 @@ def run_ours(args):
                 % tj["kernels"]["conv_tc"]["launches"]
         except Exception:
             pass
+        # per-launch roofline floor = max(flops / tensor peak, algorithmic bytes / HBM peak), summed over the step's
+        # conv launches: most ResNet layers at this resolution are HBM-bound, which the tensor fraction alone hides
+        bw = float(peaks.get("hbm_gbs", 6650.0))
+        floor_ms = sum(max(d["flops"] / (peak * 1e12), d["bytes"] / (bw * 1e9)) * 1e3
+                       for (nm, _), d in prof.summary(by_key=True).items() if nm == "aldi_conv_tc")
+        roofline_extra = {"floor_ms_per_step": floor_ms, "floor_frac": floor_ms / s["ms"],
+                          "floor_note": "sum over launches of max(flops/tensor peak, algorithmic bytes/HBM peak) / measured ms"}
         roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd + dgrad)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                     "traffic_unit": "bytes per launch (average)", "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": s["bytes"] / max(s["launches"], 1),
+                    "algorithmic_bytes_per_launch": s["bytes"] / max(s["launches"], 1), **roofline_extra,
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_per_step": s["launches"], "ms_per_step": s["ms"],
                     "share_of_step": s["ms"] / ms_step,
