@@ -121,6 +121,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // (an M = 64 instruction was timed too: same duration as M = 128, so 64-channel layers gain nothing from it)
       constexpr uint32_t idesc = make_idesc_bf16(128, kPixTile, 0, 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
