@@ -157,6 +157,16 @@ SIGNATURES = {
     "aldi_domain_bce_loss": (c_int, [P, c_int, c_int, c_float, c_float, c_float, P, c_int, c_int, P, P]),
     "aldi_strong_augment_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aldi_strong_augment": (c_int, [P, P, ctypes.POINTER(AugParams), P, c_size_t, P]),
+    "aldi_layernorm_forward": (c_int, [P, P, P, c_float, c_ll, c_int, c_int, c_int, P, P, P]),
+    "aldi_layernorm_backward": (c_int, [P, P, P, P, c_ll, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "aldi_dwconv7": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]),
+    "aldi_dwconv7_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "aldi_gelu": (c_int, [P, P, P, c_size_t, c_int, P]),
+    "aldi_layerscale_forward": (c_int, [P, P, P, P, c_ll, c_ll, c_int, c_int, c_int, P, P]),
+    "aldi_layerscale_backward": (c_int, [P, P, P, P, c_ll, c_ll, c_int, c_int, c_int, P, P, P]),
+    "aldi_space_to_depth": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_patchify_image": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "aldi_adamw_step": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
     "aldi_msda_forward": (c_int, [ctypes.POINTER(MsdaParams), P]),
     "aldi_msda_backward": (c_int, [ctypes.POINTER(MsdaParams), P]),
 }

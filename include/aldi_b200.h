@@ -327,6 +327,35 @@ size_t aldi_strong_augment_workspace_bytes(int h, int w);
 int aldi_strong_augment(const unsigned char* src, unsigned char* dst, const aldi_aug_params* p, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- ConvNeXt building blocks (BASELINE configs[4], aldi/backbone.py:189-346), channels-last, dtype F32 | BF16 -------
+ * rows = pixels, `stride` = padded channel count of a row (multiple of 8), c = real channels.                      */
+/* LayerNorm over channels per pixel (both data formats of aldi/backbone.py:321-346); stats[row] = (mean, rstd) */
+int aldi_layernorm_forward(const void* x, const float* gamma, const float* beta, float eps, long long rows, int c,
+                           int stride, int dtype, void* y, float* stats, void* stream);
+int aldi_layernorm_backward(const void* x, const float* gamma, const float* stats, const void* dy, long long rows, int c,
+                            int stride, int dtype, void* dx, int accumulate, float* dgamma, float* dbeta, void* stream);
+/* depthwise 7x7, padding 3 (ConvNextBlock.dwconv); w fp32 [c][49]; flip=1 -> data gradient (reversed taps, bias NULL) */
+int aldi_dwconv7(const void* x, const float* w, const float* bias, int n, int h, int wd, int c, int stride, int dtype,
+                 int flip, void* y, int accumulate, void* stream);
+int aldi_dwconv7_wgrad(const void* x, const void* dy, int n, int h, int wd, int c, int stride, int dtype, float* dw,
+                       void* stream);
+/* exact GELU: da == NULL -> out = gelu(h); else out = da * gelu'(h) */
+int aldi_gelu(const void* h, const void* da, void* out, size_t n, int dtype, void* stream);
+/* out = input + gamma * u * keep[image]  (layer scale + DropPath + residual, aldi/backbone.py:222-227); and its gradients */
+int aldi_layerscale_forward(const void* u, const void* input, const float* gamma, const float* keep, long long rows,
+                            long long rows_per_image, int c, int stride, int dtype, void* out, void* stream);
+int aldi_layerscale_backward(const void* u, const void* dy, const float* gamma, const float* keep, long long rows,
+                             long long rows_per_image, int c, int stride, int dtype, void* du, float* dgamma, void* stream);
+/* k x k stride-k "patchify" convs (aldi/backbone.py:249-258) as 1x1 GEMMs: out[n,y,x,(dy*b+dx)*c+ch] = in[n,b*y+dy,b*x+dx,ch];
+ * inverse=1 scatters a (coarse, b*b*c) gradient back onto the fine map */
+int aldi_space_to_depth(const void* in, void* out, int n, int ho, int wo, int block, int c, int in_stride, int out_stride,
+                        int dtype, int inverse, void* stream);
+int aldi_patchify_image(const unsigned char* images, const int* sizes, void* out, int n, int hp, int wp, int block,
+                        int out_stride, int dtype, const float* h_mean, const float* h_std, void* stream);
+/* torch.optim.AdamW over flat fp32 buffers (aldi/trainer.py:205-206); step counts from 1 */
+int aldi_adamw_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, size_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
