@@ -116,7 +116,10 @@ class _Linear:
         G = self.net.grad
         ops.wgrad(x, dy, self.net.view(self.key + ".weight", G), cout_store=self.cout, cin_store=self.cin)
         rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
-        ops.call("aldi_colsum", dy, self.net.dtc, 1, rows, 0, dy.shape[3], self.cout, 1.0, self.net.view(self.key + ".bias", G))
+        db = self.net.view(self.key + ".bias", G)
+        flat_dy = dy.view(rows, dy.shape[3])
+        for c0 in range(0, self.cout, 2048):       # aldi_colsum handles up to 2048 channels per launch
+            ops.call("aldi_colsum", flat_dy[:, c0:], self.net.dtc, 1, rows, 0, dy.shape[3], min(2048, self.cout - c0), 1.0, db[c0:])
         if not want_dx:
             return None
         dx = torch.empty_like(x)
