@@ -64,9 +64,11 @@ def align_specs(align):
     return specs
 
 
-def rcnn_specs(num_classes=8, freeze_at=2, align=None):
-    specs = resnet_specs(freeze_at)
-    for lvl, c in zip((2, 3, 4, 5), (256, 512, 1024, 2048)):
+def rcnn_specs(num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
+    """bottom_up_channels: None -> ResNet-50 bottom-up in this table; a 4-tuple -> another bottom-up (ConvNeXt:
+    aldi_b200/convnext.py keeps its own parameter buffer) whose stage widths feed the FPN laterals."""
+    specs = resnet_specs(freeze_at) if bottom_up_channels is None else OrderedDict()
+    for lvl, c in zip((2, 3, 4, 5), bottom_up_channels or (256, 512, 1024, 2048)):
         specs["fpn_lateral%d" % lvl] = ConvSpec("backbone.fpn_lateral%d" % lvl, c, 256, 1, 1, 0, bias=True)
         specs["fpn_output%d" % lvl] = ConvSpec("backbone.fpn_output%d" % lvl, 256, 256, 3, 1, 1, bias=True)
     rp = "proposal_generator.rpn_head."
@@ -92,10 +94,10 @@ def d2_shape(name, s):
     return (s.cout, s.cin, s.k, s.k)
 
 
-def state_dict_entries(num_classes=8, freeze_at=2, align=None):
+def state_dict_entries(num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
     """[(d2_key, shape, layer_name, field)] in a fixed order; field in {weight,bias,norm.<f>}."""
     out = []
-    for name, s in rcnn_specs(num_classes, freeze_at, align).items():
+    for name, s in rcnn_specs(num_classes, freeze_at, align, bottom_up_channels).items():
         out.append((s.key + ".weight", d2_shape(name, s), name, "weight"))
         if s.bias:
             out.append((s.key + ".bias", (s.cout,), name, "bias"))
@@ -105,14 +107,14 @@ def state_dict_entries(num_classes=8, freeze_at=2, align=None):
     return out
 
 
-def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None):
+def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
     """Deterministic CPU-generated weights with O(1) activations (stands in for a burn-in checkpoint).
 
     Scales are chosen so that a bf16 trunk stays in range, RPN logits are well separated and the
     box classifier is confident enough (>0.8) on some RoIs for the pseudo-label path to be non-empty.
     """
     sd = OrderedDict()
-    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at, align)):
+    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at, align, bottom_up_channels)):
         g = torch.Generator().manual_seed(seed * 100003 + idx)
         if field == "weight":
             fan_in = 1

@@ -31,10 +31,11 @@ def _pad64(c):
 class FlatLayout:
     """Detectron2 state_dict keys <-> ranges of one flat fp32 buffer (trainable range first)."""
 
-    def __init__(self, num_classes=8, freeze_at=2, align=None):
+    def __init__(self, num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
         self.num_classes = num_classes
         self.align = align
-        self.specs = arch.rcnn_specs(num_classes, freeze_at, align)
+        self.bottom_up_channels = bottom_up_channels
+        self.specs = arch.rcnn_specs(num_classes, freeze_at, align, bottom_up_channels)
         member_of = {m: g for g, ms in FUSED.items() for m in ms}
         train, frozen, buffers = [], [], []
         done = set()
@@ -88,7 +89,7 @@ class FlatLayout:
         return flat.reshape(shape).clone()
 
     def pack_state_dict(self, sd):
-        flat = torch.zeros(self.numel, dtype=torch.float32)
+        flat = torch.zeros(max(self.numel, 4), dtype=torch.float32)
         missing = []
         for (layer, field), (off, n, key, shape) in self.entries.items():
             if key not in sd:
@@ -121,9 +122,12 @@ class LayerGeom:
 class DetectorWeights:
     """One model's parameters: flat fp32 master + GEMM operands + folded FrozenBN, refreshed by kernels."""
 
-    def __init__(self, layout, flat, dtype):
+    def __init__(self, layout, flat, dtype, bottom_up=None):
         self.layout, self.flat, self.dtype = layout, flat, dtype
         self.dev = flat.device
+        # a bottom-up that is not the ResNet-50 of this table (aldi_b200.convnext.ConvNeXtBackbone): own flat buffer,
+        # forward(images, sizes, keep_masks, save) -> {0..3: stage outputs}, backward({stage: gradient})
+        self.bottom_up = bottom_up
         self.geom = OrderedDict()
         sp = layout.specs
         member_of = {m: g for g, ms in FUSED.items() for m in ms}
@@ -151,6 +155,8 @@ class DetectorWeights:
                 self.scale[name] = torch.zeros(g.cout_p, device=self.dev)
             self.shift[name] = torch.zeros(g.cout_p, device=self.dev)
         self.no_dgrad = {"stem", "res3.0.conv1", "res3.0.shortcut", "fpn_lateral2", "img_align.out", "ins_align.out"}
+        if bottom_up is not None:
+            self.no_dgrad.discard("fpn_lateral2")   # every stage of that bottom-up trains
         self._tables = {}
 
     # ---- flat views -------------------------------------------------------------------------------
@@ -236,10 +242,10 @@ ANCHOR_RATIOS = (0.5, 1.0, 2.0)
 FPN_STRIDES = (4, 8, 16, 32, 64)
 
 
-def cell_anchors():
+def cell_anchors(anchor_sizes=None):
     """detectron2 DefaultAnchorGenerator.generate_cell_anchors (float64 math, stored as fp32)."""
     out = []
-    for sizes in ANCHOR_SIZES:
+    for sizes in (anchor_sizes or ANCHOR_SIZES):
         lvl = []
         for size in sizes:
             area = size ** 2.0
@@ -258,9 +264,9 @@ class Detector:
     RPN_CH = 16    # fp32 head output row: 3 logits + 12 deltas (+1 pad)
     PRED_CH = 64   # fp32 predictor row: K+1 logits + 4K deltas, padded
 
-    def __init__(self, num_classes=8):
+    def __init__(self, num_classes=8, anchor_sizes=None):
         self.K = num_classes
-        self.cells = cell_anchors()
+        self.cells = cell_anchors(anchor_sizes)
 
     # ---- generic layer ------------------------------------------------------------------------------
     @staticmethod
@@ -276,12 +282,16 @@ class Detector:
         return out
 
     # ---- trunk forward ---------------------------------------------------------------------------------
-    def backbone(self, W, images_u8, sizes, save):
+    def backbone(self, W, images_u8, sizes, save, keep_masks=None):
         """images_u8: (N,3,H,W) uint8 on device (already on the padded canvas); sizes: (N,2) int32 valid (h,w).
         Returns (features dict p2..p6 + res2..res5, saved-activation dict or None)."""
         n, _, hp, wp = images_u8.shape
         assert hp % 32 == 0 and wp % 32 == 0
         dev, dt = images_u8.device, W.dtype
+        if W.bottom_up is not None:
+            outs = W.bottom_up.forward(images_u8, sizes, keep_masks=keep_masks, save=save)
+            feats = {"res%d" % (i + 2): outs[i] for i in range(4)}
+            return self._fpn_forward(W, feats, {} if save else None, save)
         mean, std = ops.host_floats(PIXEL_MEAN), ops.host_floats(PIXEL_STD)
         g = W.geom["stem"]
         ho, wo = hp // 2, wp // 2
@@ -319,6 +329,9 @@ class Detector:
                     saved[p] = (x, h1, h2)
                 x = out
             feats["res%d" % stage] = x
+        return self._fpn_forward(W, feats, saved, save)
+
+    def _fpn_forward(self, W, feats, saved, save):
         # FPN top-down: lateral 1x1 with the nearest-2x upsampled coarser map added in the epilogue
         prev = None
         for lvl in (5, 4, 3, 2):
@@ -604,11 +617,19 @@ class Detector:
         for l in (2, 3, 4, 5):
             r = feats["res%d" % l]
             self._wgrad(W, G, "fpn_lateral%d" % l, r, dprev[l])
-            if l > 2:
+            if W.bottom_up is not None:
+                dres[l] = torch.empty_like(r)                 # stage outputs are LayerNorm outputs: no ReLU mask
+                self._dgrad(W, "fpn_lateral%d" % l, dprev[l], dres[l])
+            elif l > 2:
                 dres[l] = torch.empty_like(r)
                 self._dgrad(W, "fpn_lateral%d" % l, dprev[l], dres[l], mask=r)
             dprev[l] = None
         on_ready("fpn")
+        if W.bottom_up is not None:
+            W.bottom_up.backward({l - 2: dres[l] for l in (2, 3, 4, 5)})
+            for tag in ("res5", "res4", "res3"):
+                on_ready(tag)
+            return
         # ---- ResNet res5 -> res3 (stem + res2 frozen: aldi configs keep D2's FREEZE_AT=2)
         for stage in (5, 4, 3):
             dout = dres[stage]

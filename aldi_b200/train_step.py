@@ -78,6 +78,17 @@ class StepConfig:
         self.ins_da_weight = 0.01
         self.ins_da_input_dim = 1024
         self.ins_da_hidden_dims = (1024,)
+        # bottom-up: "resnet50" (BASELINE configs[0-1]) or "convnext" (configs[4], MODEL.CONVNEXT.*, aldi/config.py:94-99)
+        self.backbone = "resnet50"
+        self.convnext_depths = (3, 3, 27, 3)
+        self.convnext_dims = (192, 384, 768, 1536)
+        self.convnext_drop_path = 0.2
+        self.anchor_sizes = None                 # MODEL.ANCHOR_GENERATOR.SIZES (None: detectron2's 32..512)
+        self.pixel_mean = (103.530, 116.280, 123.675)
+        self.pixel_std = (1.0, 1.0, 1.0)
+        self.optimizer = "SGD"                   # SOLVER.OPTIMIZER: "SGD" | "ADAMW" (aldi/trainer.py:199-208)
+        self.adamw_betas = (0.9, 0.999)
+        self.adamw_eps = 1e-8
         self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": parity path
         self.cuda_graph = False                  # replay each micro-batch as a captured CUDA graph (2nd use onwards)
         # run the student on a source micro-batch and a distillation micro-batch as ONE batch (same weights, FrozenBN:
@@ -240,17 +251,42 @@ class B200TrainStep:
         self.dtype = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
         self.dtc = _l.BF16 if cfg.dtype == "bf16" else _l.F32
         _l.load()  # fail loudly if the CUDA library is missing
-        self.layout = FlatLayout(cfg.num_classes, align=cfg.align_spec())
-        self.det = Detector(cfg.num_classes)
+        convnext = cfg.backbone == "convnext"
+        if cfg.backbone not in ("resnet50", "convnext"):
+            raise NotImplementedError("MODEL.BACKBONE %s: ResNet-50-FPN and ConvNeXt-FPN are built" % cfg.backbone)
+        self.layout = FlatLayout(cfg.num_classes, align=cfg.align_spec(),
+                                 bottom_up_channels=tuple(cfg.convnext_dims) if convnext else None)
+        self.det = Detector(cfg.num_classes, cfg.anchor_sizes)
         flat = self.layout.pack_state_dict(state_dict).to(self.device)
-        tflat = flat.clone() if teacher_state_dict is None else \
-            self.layout.pack_state_dict(teacher_state_dict).to(self.device)
-        self.student = DetectorWeights(self.layout, flat, self.dtype)
-        self.teacher = DetectorWeights(self.layout, tflat, self.dtype)
+        tsd = state_dict if teacher_state_dict is None else teacher_state_dict
+        tflat = flat.clone() if teacher_state_dict is None else self.layout.pack_state_dict(tsd).to(self.device)
+        bu_s = bu_t = None
+        if convnext:
+            from .convnext import ConvNeXtBackbone
+            pre = "backbone.bottom_up."
+
+            def bottom_up(sd):
+                return ConvNeXtBackbone({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, depths=cfg.convnext_depths,
+                                        dims=cfg.convnext_dims, drop_path_rate=cfg.convnext_drop_path, dtype=cfg.dtype,
+                                        device=self.device, pixel_mean=cfg.pixel_mean, pixel_std=cfg.pixel_std)
+
+            bu_s, bu_t = bottom_up(state_dict), bottom_up(tsd)
+            self.keep_rng = torch.Generator().manual_seed(0)    # DropPath masks (host-drawn, aldi/backbone.py:176-181)
+            self.keep_override = None                           # test seam: list of per-forward mask lists
+        self.student = DetectorWeights(self.layout, flat, self.dtype, bottom_up=bu_s)
+        self.teacher = DetectorWeights(self.layout, tflat, self.dtype, bottom_up=bu_t)
         self.student.enable_dgrad()
         self.nt = self.layout.num_trainable
         self.grad = torch.zeros(self.nt, device=self.device)
         self.momentum_buf = torch.zeros(self.nt, device=self.device)
+        if cfg.optimizer.upper() == "ADAMW":
+            self.exp_avg_sq = torch.zeros(self.nt, device=self.device)
+            if bu_s is not None:
+                self.bu_exp_avg, self.bu_exp_avg_sq = torch.zeros_like(bu_s.flat), torch.zeros_like(bu_s.flat)
+        elif cfg.optimizer.upper() != "SGD":
+            raise ValueError("Unsupported optimizer/backbone combination {} {}.".format(cfg.optimizer, cfg.backbone))
+        elif bu_s is not None:
+            self.bu_momentum = torch.zeros_like(bu_s.flat)
         self.student.refresh()
         self.teacher.refresh()
         self.loss_acc = torch.zeros(LOSS_SLOTS, device=self.device)
@@ -283,6 +319,9 @@ class B200TrainStep:
         alpha = 0.0 if it <= self.cfg.ema_start_iter else self.cfg.ema_alpha
         ops.ema_update(self.teacher.flat, self.student.flat, alpha)
         self.teacher.refresh()
+        if self.teacher.bottom_up is not None:
+            ops.ema_update(self.teacher.bottom_up.flat, self.student.bottom_up.flat, alpha)
+            self.teacher.bottom_up.refresh()
 
     # ---- aldi/trainer.py:28-117 ----------------------------------------------------------------------
     def run_model(self, data):
@@ -340,7 +379,7 @@ class B200TrainStep:
             item["pass_id"] = 100 + i if item["kind"] == "distill" else i
             item["keys"] = [(kind,) + MicroBatch.shape_key(d, gt) for kind, d, gt in item["parts"]]
             self.seed_log[item["pass_id"]] = item["seed"]
-        if cfg.fuse_passes and do_distill and not do_align:
+        if cfg.fuse_passes and do_distill and not do_align and self.student.bottom_up is None:
             plan = self._fuse_plan(plan)
         last_bwd = max(i for i, it in enumerate(plan) if it["kind"] != "teacher")
         bodies = {"source": self._source_body, "distill": self._distill_body, "align_target": self._align_target_body,
@@ -443,7 +482,8 @@ class B200TrainStep:
         sampling seed and salts included, so a replay sees the new step's data.  The step's LAST backward under
         data parallelism is captured as a CHAIN of graphs cut where a gradient bucket becomes final: the NCCL
         all-reduce of that bucket is issued eagerly between two replays and overlaps the next segment."""
-        if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override:
+        if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override \
+                or self.student.bottom_up is not None:   # DropPath masks are host-drawn per forward: eager
             if self.profile_spin_cycles:
                 # profiling aid: park the GPU on a spin kernel while the host queues this micro-batch, so the kernels
                 # then run back to back (warm L2, no launch gaps) and per-launch CUDA events time exactly their durations
@@ -536,7 +576,7 @@ class B200TrainStep:
     def _student_forward(self, b, gt, pass_id, want_rpn_labels):
         cfg, det, W = self.cfg, self.det, self.student
         n = b.n
-        feats, saved = det.backbone(W, b.images, b.sizes, save=True)
+        feats, saved = det.backbone(W, b.images, b.sizes, save=True, keep_masks=self._keep_masks(W, n))
         lv = det.levels(feats)
         rpn_out, rpn_ts = det.rpn_head(W, feats, lv, save=True)
         out = {"feats": feats, "saved": saved, "lv": lv, "rpn_out": rpn_out, "rpn_ts": rpn_ts}
@@ -561,6 +601,14 @@ class B200TrainStep:
                    roi_count=roi_count, roi_stats=roi_stats, pred=pred, head_saved=head_saved)
         return out
 
+    def _keep_masks(self, W, n):
+        """DropPath factors of one training-mode forward of a ConvNeXt bottom-up (None for the ResNet)."""
+        if W.bottom_up is None:
+            return None
+        if self.keep_override is not None:
+            return self.keep_override.pop(0)
+        return W.bottom_up.draw_keep_masks(n, self.keep_rng)
+
     def _label_anchors(self, lv, b, gt, site):
         cfg, n = self.cfg, b.n
         total = lv.total_locs * lv.num_anchors
@@ -574,9 +622,11 @@ class B200TrainStep:
         return labels, matched, stats
 
     # ---- teacher: trunk + RPN once, eval-mode detections -> pseudo labels --------------------------------
-    def teacher_forward(self, b):
+    def teacher_forward(self, b, train_mode=False):
+        """train_mode: the teacher's second forward inside the distiller runs in TRAINING mode (aldi/distill.py:153-162),
+        which matters only for a bottom-up with DropPath; the FrozenBN ResNet gives identical features in both modes."""
         cfg, det, W = self.cfg, self.det, self.teacher
-        feats, _ = det.backbone(W, b.images, b.sizes, save=False)
+        feats, _ = det.backbone(W, b.images, b.sizes, save=False, keep_masks=self._keep_masks(W, b.n) if train_mode else None)
         lv = det.levels(feats)
         rpn_out, _ = det.rpn_head(W, feats, lv, save=False)
         return feats, lv, rpn_out
@@ -749,6 +799,9 @@ class B200TrainStep:
             pseudo = self.pseudo_override[len(self.pseudo_log) - 1]
         hard_rpn = cfg.do_hard_obj or cfg.do_hard_rpn_reg
         fw = self._student_forward(bs, pseudo, pass_id, want_rpn_labels=hard_rpn)
+        if self.teacher.bottom_up is not None and any(r > 0 for r in self.teacher.bottom_up.drop_rates):
+            # stochastic bottom-up: the soft targets come from a separate TRAINING-mode teacher forward
+            t_feats, t_lv, t_rpn_out = self.teacher_forward(bw, train_mode=True)
         # teacher RoI head on the student's sampled proposals (ReplaceProposalsOnce + shared seed)
         t_pred, _ = det.box_head(self.teacher, t_feats, fw["rois"], fw["roi_batch"], save=False)
         # fresh anchor sampling by the TEACHER's RPN on the pseudo labels (T2)
@@ -808,9 +861,25 @@ class B200TrainStep:
         lr = self.lr_at(self.iter) if lr is None else lr
         gs = self.allreduce_grads()
         p = self.student.flat[:self.nt]
-        ops.sgd_momentum_step(p, self.momentum_buf, self.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
+        bu = self.student.bottom_up
+        if bu is not None and self.reducer.active:
+            dist.all_reduce(bu.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.cfg.optimizer.upper() == "ADAMW":
+            b1, b2 = self.cfg.adamw_betas
+            ops.call("aldi_adamw_step", p, self.momentum_buf, self.exp_avg_sq, self.grad, self.nt, lr, b1, b2, self.cfg.adamw_eps,
+                     self.cfg.weight_decay, self.iter + 1, gs)
+            if bu is not None:
+                ops.call("aldi_adamw_step", bu.flat, self.bu_exp_avg, self.bu_exp_avg_sq, bu.grad, bu.flat.numel(), lr, b1, b2,
+                         self.cfg.adamw_eps, self.cfg.weight_decay, self.iter + 1, gs)
+        else:
+            ops.sgd_momentum_step(p, self.momentum_buf, self.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
+            if bu is not None:
+                ops.sgd_momentum_step(bu.flat, self.bu_momentum, bu.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
         self.grad.zero_()
         self.student.refresh(trainable_only=True)
+        if bu is not None:
+            bu.grad.zero_()
+            bu.refresh()
         self.iter += 1
 
     # ---- a whole iteration: before_step + run_step ----------------------------------------------------------
@@ -822,7 +891,10 @@ class B200TrainStep:
 
     def state_dict(self, which="student"):
         w = self.student if which == "student" else self.teacher
-        return self.layout.unpack_state_dict(w.flat)
+        out = self.layout.unpack_state_dict(w.flat)
+        if w.bottom_up is not None:
+            out.update({"backbone.bottom_up." + k: v for k, v in w.bottom_up.state_dict().items()})
+        return out
 
     def load_state_dict(self, sd, which="student", strict=True):
         """Write a Detectron2-keyed state_dict into the flat buffer of the student or the teacher and re-derive the

@@ -1099,10 +1099,17 @@ class StandardROIHeads(nn.Module):
 # ---------------------------------------------------------------------------------------------------
 class GeneralizedRCNN(nn.Module):
     def __init__(self, num_classes=8, pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0), freeze_at=2,
-                 **kwargs):
+                 bottom_up=None, fpn_in_features=None, anchor_sizes=None, **kwargs):
         super().__init__()
-        self.backbone = FPN(ResNet(freeze_at=freeze_at))
+        # bottom_up: any module exposing _out_feature_strides / _out_feature_channels (e.g. oracle/convnext_ref.ConvNeXt
+        # with fpn_in_features (0, 1, 2, 3): build_convnext_fpn_backbone, aldi/backbone.py:373-392)
+        if bottom_up is None:
+            self.backbone = FPN(ResNet(freeze_at=freeze_at))
+        else:
+            self.backbone = FPN(bottom_up, in_features=fpn_in_features)
         self.proposal_generator = RPN()
+        if anchor_sizes is not None:
+            self.proposal_generator.anchor_generator = DefaultAnchorGenerator(sizes=anchor_sizes)
         self.roi_heads = StandardROIHeads(num_classes=num_classes)
         self.register_buffer("pixel_mean", torch.tensor(pixel_mean).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor(pixel_std).view(-1, 1, 1), False)

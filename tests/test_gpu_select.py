@@ -304,3 +304,40 @@ def test_wgrad_fused_bias_gradient(cin, cout, k, hw):
     torch.cuda.synchronize()
     assert torch.allclose(db, ref, rtol=1e-4, atol=1e-2), float((db - ref).abs().max())
     assert float(ref.abs().max()) > 1.0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_roi_align_forward_backward_vs_torchvision(seed):
+    """Multi-level RoIAlign (forward and the pixel-centric backward) against detectron2's ROIPooler restatement on
+    torchvision.ops.roi_align: random boxes of every size, some partly or wholly outside the image, tiny boxes."""
+    from aldi_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    n, c = 2, 64
+    shapes = [(40, 48), (20, 24), (10, 12), (5, 6)]
+    feats = [torch.randn(n, c, h, w, generator=g) for h, w in shapes]
+    m = 96
+    ctr = torch.rand(m, 2, generator=g) * torch.tensor([192.0, 160.0])
+    wh = torch.exp(torch.rand(m, 2, generator=g) * 5.5) * 1.5          # 1.5 .. 370 px
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    boxes[:8] += 120.0                                                  # some far outside
+    boxes[8:12, 2:] = boxes[8:12, :2] + 0.3                             # tiny
+    batch = torch.randint(0, n, (m,), generator=g)
+    order = torch.argsort(batch, stable=True)
+    boxes, batch = boxes[order], batch[order]
+    dout = torch.randn(m, c, 7, 7, generator=g)
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    pooler = d2.ROIPooler()
+    out_ref = pooler(fr, [d2.Boxes(boxes[batch == i]) for i in range(n)])
+    out_ref.backward(dout)
+    fd = [f.permute(0, 2, 3, 1).contiguous().cuda() for f in feats]
+    out = torch.empty(m, 7, 7, c, device="cuda")
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    ops.roi_align(fd, boxes.cuda(), batch.int().cuda(), out=out, scales=scales)
+    dfe = [torch.zeros_like(f) for f in fd]
+    ops.roi_align(fd, boxes.cuda(), batch.int().cuda(), dout=dout.permute(0, 2, 3, 1).contiguous().cuda(), dfeats=dfe, scales=scales)
+    torch.cuda.synchronize()
+    assert torch.allclose(out.cpu().permute(0, 3, 1, 2), out_ref.detach(), rtol=1e-4, atol=1e-5)
+    for l in range(4):
+        got, want = dfe[l].cpu().permute(0, 3, 1, 2), fr[l].grad
+        err = (got - want).abs().max() / (want.abs().max() + 1e-12)
+        assert float(err) < 1e-4, (l, float(err))
