@@ -203,18 +203,27 @@ def add_aldi_config(cfg):
 def step_config_from_cfg(cfg, dtype=None):
     """cfg (reference key names) -> the StepConfig the B200 step consumes."""
     D = cfg.DOMAIN_ADAPT.DISTILL
-    if cfg.MODEL.META_ARCHITECTURE != "GeneralizedRCNN" or cfg.MODEL.BACKBONE.NAME != "build_resnet_fpn_backbone":
-        raise NotImplementedError("round 1 covers the Faster R-CNN R50-FPN path (BASELINE configs[0-1]); got %s / %s"
-                                  % (cfg.MODEL.META_ARCHITECTURE, cfg.MODEL.BACKBONE.NAME))
-    if (cfg.SOLVER.OPTIMIZER or "SGD").upper() != "SGD":
+    backbones = {"build_resnet_fpn_backbone": "resnet50", "build_convnext_fpn_backbone": "convnext"}
+    if cfg.MODEL.META_ARCHITECTURE != "GeneralizedRCNN" or cfg.MODEL.BACKBONE.NAME not in backbones:
+        raise NotImplementedError("Faster R-CNN on ResNet-50-FPN (BASELINE configs[0-1]) and ConvNeXt-FPN (configs[4]) are "
+                                  "built; got %s / %s" % (cfg.MODEL.META_ARCHITECTURE, cfg.MODEL.BACKBONE.NAME))
+    backbone = backbones[cfg.MODEL.BACKBONE.NAME]
+    optimizer = (cfg.SOLVER.OPTIMIZER or "SGD").upper()
+    if optimizer not in ("SGD", "ADAMW"):                       # aldi/trainer.py:207-208
         raise ValueError("Unsupported optimizer/backbone combination {} {}.".format(cfg.SOLVER.OPTIMIZER,
                                                                                      cfg.MODEL.BACKBONE.NAME))
+    extra = {}
+    if backbone == "convnext":
+        extra = dict(convnext_depths=tuple(cfg.MODEL.CONVNEXT.DEPTHS), convnext_dims=tuple(cfg.MODEL.CONVNEXT.DIMS),
+                     convnext_drop_path=cfg.MODEL.CONVNEXT.DROP_PATH_RATE)
     if max(cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST) > 2048:
         raise NotImplementedError("MODEL.RPN.PRE_NMS_TOPK_TRAIN/TEST up to 2048 per level are supported (the ALDI configs "
                                   "use 2000 / 1000, configs/detectron2/Base-RCNN-FPN.yaml:14-15); got %d / %d"
                                   % (cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST))
     A = cfg.DOMAIN_ADAPT.ALIGN
     return StepConfig(
+        backbone=backbone, optimizer=optimizer, pixel_mean=tuple(cfg.MODEL.PIXEL_MEAN), pixel_std=tuple(cfg.MODEL.PIXEL_STD),
+        anchor_sizes=tuple(tuple(s) for s in cfg.MODEL.ANCHOR_GENERATOR.SIZES), **extra,
         img_da_enabled=A.IMG_DA_ENABLED, img_da_layer=A.IMG_DA_LAYER, img_da_weight=A.IMG_DA_WEIGHT,
         img_da_input_dim=A.IMG_DA_INPUT_DIM, img_da_hidden_dims=tuple(A.IMG_DA_HIDDEN_DIMS),
         ins_da_enabled=A.INS_DA_ENABLED, ins_da_weight=A.INS_DA_WEIGHT, ins_da_input_dim=A.INS_DA_INPUT_DIM,

@@ -69,9 +69,13 @@ def test_yaml_base_chain_and_overrides(tmp_path):
 
 
 def test_unsupported_combinations_fail_with_reference_errors(tmp_path):
-    cfg = _cfg(tmp_path, ["SOLVER.OPTIMIZER", "ADAMW"])
+    cfg = _cfg(tmp_path, ["SOLVER.OPTIMIZER", "LAMB"])                     # aldi/trainer.py:207-208
     with pytest.raises(ValueError, match="Unsupported optimizer/backbone combination"):
         step_config_from_cfg(cfg)
+    assert step_config_from_cfg(_cfg(tmp_path, ["SOLVER.OPTIMIZER", "ADAMW"])).optimizer == "ADAMW"
+    cn = step_config_from_cfg(_cfg(tmp_path, ["MODEL.BACKBONE.NAME", "build_convnext_fpn_backbone", "MODEL.CONVNEXT.DIMS",
+                                              "[192, 384, 768, 1536]"]))
+    assert cn.backbone == "convnext" and cn.convnext_dims == (192, 384, 768, 1536)
     cfg = _cfg(tmp_path, ["MODEL.BACKBONE.NAME", "build_vitdet_b_backbone"])
     with pytest.raises(NotImplementedError):
         step_config_from_cfg(cfg)
