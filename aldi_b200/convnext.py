@@ -88,6 +88,24 @@ class ConvNeXtLayout:
         return out
 
 
+def synthetic_state_dict(depths, dims, seed=0, layer_scale_init_value=1e-6, in_chans=3):
+    """The reference's own initialisation (aldi/backbone.py:293-296, 201-212): trunc_normal(std 0.02) conv / linear
+    weights, zero biases, unit LayerNorms, gamma = layer_scale_init_value — stands in for the ImageNet checkpoint
+    (`models/convnext_large_1k_384_backbone.pkl`, configs/Base-RCNN-ConvNeXt-FPN.yaml:3) that cannot be fetched here."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for k, (_, _, shape) in ConvNeXtLayout(depths, dims, in_chans).entries.items():
+        if k.endswith("gamma"):
+            sd[k] = torch.full(shape, float(layer_scale_init_value))
+        elif k.endswith(".bias"):
+            sd[k] = torch.zeros(shape)
+        elif len(shape) == 1:                       # LayerNorm weights
+            sd[k] = torch.ones(shape)
+        else:
+            sd[k] = torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=g)
+    return sd
+
+
 class _Linear:
     """One dense layer on the implicit-GEMM kernels: packed forward / data-gradient operands + padded bias."""
 

@@ -111,8 +111,15 @@ class ALDITrainer:
                                "fallback; the CPU arm of bench.py is the oracle" % cfg.MODEL.DEVICE)
         assert cfg.EMA.ENABLED or not cfg.DOMAIN_ADAPT.TEACHER.ENABLED, "Teacher requires EMA.ENABLED"
         scfg = step_config_from_cfg(cfg, dtype=dtype)
-        sd = state_dict if state_dict is not None else arch.synthetic_state_dict(0, cfg.MODEL.ROI_HEADS.NUM_CLASSES,
-                                                                                align=scfg.align_spec())
+        sd = state_dict
+        if sd is None:
+            convnext = scfg.backbone == "convnext"
+            sd = arch.synthetic_state_dict(0, cfg.MODEL.ROI_HEADS.NUM_CLASSES, align=scfg.align_spec(),
+                                           bottom_up_channels=tuple(scfg.convnext_dims) if convnext else None)
+            if convnext:
+                from .convnext import synthetic_state_dict as convnext_init
+                sd.update({"backbone.bottom_up." + k: v for k, v in convnext_init(
+                    scfg.convnext_depths, scfg.convnext_dims, 0, cfg.MODEL.CONVNEXT.LAYER_SCALE_INIT_VALUE).items()})
         self.step_impl = B200TrainStep(scfg, sd, device=device or "cuda:%d" % torch.cuda.current_device(),
                                        process_group=process_group)
         self.step_impl.debug = None

@@ -314,3 +314,83 @@ def test_convnext_fpn_source_step_matches_oracle():
     new = step.state_dict("student")
     for k, v in student.state_dict().items():
         assert pu.rel_err(new[k], v) < 1e-5, (k, pu.rel_err(new[k], v))
+
+
+def test_convnext_fpn_aldi_step_matches_oracle():
+    """ALDI++ distillation step on the ConvNeXt-FPN detector: the teacher's pseudo-label pass runs in eval mode (no
+    DropPath), the student's and the teacher's soft-target passes in training mode, each with its own DropPath masks
+    (aldi/distill.py:144-168) — losses and the student's gradients against the oracle."""
+    from aldi_b200 import synth_data
+    from aldi_b200.train_step import B200TrainStep, StepConfig
+    from oracle import convnext_ref
+    depths, dims, dpr = (1, 1, 1, 1), (32, 64, 96, 128), 0.3
+    std = (57.375, 57.12, 58.395)
+    sd_s, sd_o = _convnext_inputs(31, depths, dims), _convnext_inputs(1031, depths, dims)
+    sd_t = {k: 0.95 * sd_s[k] + 0.05 * sd_o[k] for k in sd_s}
+    _, uw, us = synth_data.synthetic_batch(31, 0, 2, 96, 128)
+    g = torch.Generator().manual_seed(5)
+    rates = [x.item() for x in torch.linspace(0, dpr, sum(depths))]
+    draw = lambda: [None if r <= 0 else (torch.rand(2, generator=g) < (1 - r)).float() / (1 - r) for r in rates]  # noqa: E731
+    m_student, m_teacher = draw(), draw()
+    pu.install_device_sampler(pu.predict_seed_log(1234, 0, 1))
+
+    def oracle_model(sd):
+        bu = convnext_ref.ConvNeXt(depths=depths, dims=dims, drop_path_rate=dpr, layer_scale_init_value=1.0)
+        m = aldi_ref.ALDI(num_classes=8, bottom_up=bu, fpn_in_features=(0, 1, 2, 3), pixel_std=std)
+        m.load_state_dict(sd)
+        return m.train(), bu
+
+    student, bu_s = oracle_model(sd_s)
+    teacher, bu_t = oracle_model(sd_t)
+    bu_s.keep_queue = [m for m in m_student if m is not None]
+    bu_t.keep_queue = [m for m in m_teacher if m is not None]
+    dist = aldi_ref.ALDIDistiller(teacher, student, **pu.SOFT)
+    uw_o, us_o = pu.to_d2(uw, False), pu.to_d2(us, False)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, None, uw_o, us_o), 2, False, lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    assert not bu_s.keep_queue and not bu_t.keep_queue
+    cfg = StepConfig(dtype="fp32", ema_start_iter=-1, ims_per_gpu=2, backbone="convnext", convnext_depths=depths,
+                     convnext_dims=dims, convnext_drop_path=dpr, pixel_std=std, optimizer="ADAMW")
+    step = B200TrainStep(cfg, sd_s, teacher_state_dict=sd_t)
+    step.keep_override = [list(m_student), list(m_teacher)]
+    step.pseudo_override = [pu.pseudo_to_device([d["instances"] for d in uw_o], "cuda")]
+    random.seed(1234)
+    dev_losses = dict(step.run_model((None, None, uw, us)).items())
+    torch.cuda.synchronize()
+    check_losses(dev_losses, ora)
+    worst = check_grads(step, student)
+    named = dict(student.named_parameters())
+    bu = step.student.bottom_up
+    for k, got in bu.layout.unpack(bu.grad).items():
+        e = pu.rel_err(got, named["backbone.bottom_up." + k].grad)
+        assert e < 5e-3, (k, e)
+    print("convnext-fpn ALDI step: losses", dev_losses, "worst detector grad", worst)
+
+
+def test_convnext_trainer_runs():
+    """The trainer mirror on Base-RCNN-ConvNeXt-FPN-style cfg keys (tiny widths): EMA copy + update of both parameter
+    buffers, AdamW, DropPath drawn per forward, the loss dict of the ALDI++ flags, finite throughout."""
+    from aldi_b200.config import add_aldi_config, get_cfg
+    from aldi_b200.trainer import ALDITrainer
+    cfg = get_cfg()
+    add_aldi_config(cfg)
+    cfg.merge_from_list(["MODEL.BACKBONE.NAME", "build_convnext_fpn_backbone", "MODEL.CONVNEXT.DEPTHS", "[1, 1, 2, 1]",
+                         "MODEL.CONVNEXT.DIMS", "[64, 128, 192, 256]", "MODEL.CONVNEXT.LAYER_SCALE_INIT_VALUE", "0.1",
+                         "SOLVER.OPTIMIZER", "ADAMW", "SOLVER.BASE_LR", "0.0001", "SOLVER.WEIGHT_DECAY", "0.05",
+                         "SOLVER.IMS_PER_BATCH", "4", "SOLVER.IMS_PER_GPU", "2", "SOLVER.WARMUP_ITERS", "2",
+                         "MODEL.ROI_HEADS.NUM_CLASSES", "8", "MODEL.RPN.PRE_NMS_TOPK_TRAIN", "2000",
+                         "MODEL.RPN.PRE_NMS_TOPK_TEST", "1000", "MODEL.RPN.POST_NMS_TOPK_TRAIN", "1000",
+                         "MODEL.RPN.POST_NMS_TOPK_TEST", "1000", "SOLVER.AMP.ENABLED", "True", "EMA.ENABLED", "True",
+                         "DOMAIN_ADAPT.TEACHER.ENABLED", "True", "DOMAIN_ADAPT.DISTILL.ROIH_CLS_ENABLED", "True",
+                         "DOMAIN_ADAPT.DISTILL.OBJ_ENABLED", "True", "DOMAIN_ADAPT.DISTILL.ROIH_REG_ENABLED", "True",
+                         "DOMAIN_ADAPT.DISTILL.RPN_REG_ENABLED", "True", "DOMAIN_ADAPT.DISTILL.HARD_ROIH_CLS_ENABLED", "False",
+                         "DATASETS.BATCH_CONTENTS", "('labeled_strong', 'unlabeled_strong')", "DATASETS.BATCH_RATIOS", "(1, 1)"])
+    trainer = ALDITrainer(cfg, image_size=(96, 128))
+    hist = trainer.train(0, 3)
+    assert len(hist) == 3 and all(v == v and abs(v) != float("inf") for h in hist for v in h.values())
+    assert {"loss_cls_source_strong", "loss_obj_bce_distill", "loss_cls_ce_distill"} <= set(hist[-1])
+    sd = trainer.state_dict()
+    assert "backbone.bottom_up.stages.2.1.pwconv1.weight" in sd["model"] and "backbone.bottom_up.norm3.bias" in sd["ema"]
+    s, t = sd["model"]["backbone.bottom_up.stages.0.0.pwconv1.weight"], sd["ema"]["backbone.bottom_up.stages.0.0.pwconv1.weight"]
+    assert not torch.equal(s, t) and float((s - t).abs().max()) < 1e-2      # the teacher trails the student (EMA)
