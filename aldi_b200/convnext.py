@@ -9,10 +9,11 @@ tcgen05 implicit-GEMM kernels (conv_tc / wgrad_tc; fp32 CUDA-core kernels in par
 csrc/convnext.cu.  DropPath masks are per-(block, sample) factors in {0, 1/keep_prob} drawn on the host
 (`draw_keep_masks`) and applied inside the layer-scale + residual kernel.
 
-Status: the bottom-up alone, pinned against goldens produced by the reference's own class
-(tests/golden/make_convnext_golden.py, tests/test_gpu_convnext.py).  It returns the four normalised stage outputs the
-reference hands to Detectron2's FPN; wiring it under `Detector` (FPN laterals over `dims`, AdamW through
-`aldi_adamw_step`) is the next step.
+The bottom-up is pinned against goldens produced by the reference's own class (tests/golden/make_convnext_golden.py,
+tests/test_gpu_convnext.py) and returns the four normalised stage outputs the reference hands to Detectron2's FPN;
+`DetectorWeights(bottom_up=...)` puts it under the FPN / RPN / box head of `detector.Detector`
+(build_convnext_fpn_backbone, aldi/backbone.py:373-392), `B200TrainStep(StepConfig(backbone="convnext", ...))` trains
+it with AdamW and EMA (tests/test_gpu_step_parity.py::test_convnext_*).
 """
 from collections import OrderedDict
 
