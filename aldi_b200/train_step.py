@@ -902,7 +902,21 @@ class B200TrainStep:
         that are absent keep their current values and tensors of the wrong shape are reported as missing."""
         w = self.student if which == "student" else self.teacher
         known = {key: (layer, field, off, n, shape) for (layer, field), (off, n, key, shape) in self.layout.entries.items()}
-        missing = [k for k in known if k not in sd]
+        bu_missing = []
+        if w.bottom_up is not None:
+            # the ConvNeXt bottom-up keeps its own flat buffer under the "backbone.bottom_up." prefix
+            pre, lay = "backbone.bottom_up.", w.bottom_up.layout
+            host = w.bottom_up.flat.detach().cpu()
+            for k, (off, n, shape) in lay.entries.items():
+                t = sd.get(pre + k)
+                if t is None or tuple(t.shape) != tuple(shape):
+                    bu_missing.append(pre + k)
+                else:
+                    host[off:off + n] = lay.to_internal(torch.as_tensor(t).detach().to("cpu", torch.float32))
+            w.bottom_up.flat.copy_(host)
+            w.bottom_up.refresh()
+            sd = {k: v for k, v in sd.items() if not (k.startswith(pre) and k[len(pre):] in lay.entries)}
+        missing = [k for k in known if k not in sd] + bu_missing
         unexpected = [k for k in sd if k not in known]
         bad_shape = [k for k in known if k in sd and tuple(sd[k].shape) != tuple(known[k][4])]
         if strict and (missing or unexpected or bad_shape):

@@ -394,3 +394,13 @@ def test_convnext_trainer_runs():
     assert "backbone.bottom_up.stages.2.1.pwconv1.weight" in sd["model"] and "backbone.bottom_up.norm3.bias" in sd["ema"]
     s, t = sd["model"]["backbone.bottom_up.stages.0.0.pwconv1.weight"], sd["ema"]["backbone.bottom_up.stages.0.0.pwconv1.weight"]
     assert not torch.equal(s, t) and float((s - t).abs().max()) < 1e-2      # the teacher trails the student (EMA)
+    # checkpoint round trip incl. the bottom-up's own buffer
+    from aldi_b200.checkpoint import DetectionCheckpointerWithEMA
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        DetectionCheckpointerWithEMA(trainer.step_impl, tmp).save("model_0000002")
+        other = ALDITrainer(cfg, image_size=(96, 128))
+        assert not torch.equal(other.step_impl.student.bottom_up.flat, trainer.step_impl.student.bottom_up.flat)
+        DetectionCheckpointerWithEMA(other.step_impl, tmp).resume_or_load("", resume=True)
+        for a, b in ((other.step_impl.student, trainer.step_impl.student), (other.step_impl.teacher, trainer.step_impl.teacher)):
+            assert torch.equal(a.flat, b.flat) and torch.equal(a.bottom_up.flat, b.bottom_up.flat)

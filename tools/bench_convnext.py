@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--ims", type=int, default=2, help="source images = target images = SOLVER.IMS_PER_GPU")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--hw", default="1024x1824")
+    ap.add_argument("--profile", action="store_true", help="also print device ms per entry point for one step (CUDA events)")
     args = ap.parse_args()
     h, w = (int(v) for v in args.hw.split("x"))
     depths, dims = SIZES[args.size]
@@ -52,6 +53,14 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     vals = dict(losses.items())
+    if args.profile:
+        from aldi_b200 import ops
+        prof = ops.KernelProfiler()
+        ops.set_profiler(prof)
+        step.step((None, dev[0], dev[1], dev[2]))
+        ops.set_profiler(None)
+        for name, d in sorted(prof.summary().items(), key=lambda kv: -kv[1]["ms"])[:14]:
+            print("%-28s %4d launches %8.2f ms" % (name, d["launches"], d["ms"]), file=sys.stderr)
     print(json.dumps({"workload": "ALDI++ Faster R-CNN ConvNeXt-%s FPN, %dx%d synthetic, %d source + %d target images, AdamW, "
                       "DropPath 0.2, eager (no CUDA graph)" % (args.size, h, w, args.ims, args.ims),
                       "images_per_s": 2 * args.ims / (ms / 1e3), "ms_per_step": ms, "steps": args.steps, "dtype": "bf16",
