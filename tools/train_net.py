@@ -50,12 +50,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
-    sd = None
-    if cfg.MODEL.WEIGHTS:
-        ck = torch.load(cfg.MODEL.WEIGHTS, map_location="cpu")
-        sd = ck.get("model", ck)
-    trainer = ALDITrainer(cfg, state_dict=sd, process_group=pg, image_size=tuple(args.image_size),
+    trainer = ALDITrainer(cfg, process_group=pg, image_size=tuple(args.image_size),
                           dtype="bf16" if cfg.SOLVER.AMP.ENABLED else "fp32")
+    if cfg.MODEL.WEIGHTS and os.path.isfile(cfg.MODEL.WEIGHTS):
+        # DetectionCheckpointerWithEMA.resume_or_load(cfg.MODEL.WEIGHTS, resume=False): a .pth with an "ema" entry starts
+        # the model from the EMA weights (aldi/checkpoint.py:19-31, tools/train_net.py:73-76 of the reference)
+        from aldi_b200.checkpoint import DetectionCheckpointerWithEMA
+        DetectionCheckpointerWithEMA(trainer.step_impl, cfg.OUTPUT_DIR).resume_or_load(cfg.MODEL.WEIGHTS, resume=False)
+        trainer.step_impl.ema_update(-1)          # EMA(model) deep-copies the freshly loaded student (aldi/ema.py:12-13)
+    elif cfg.MODEL.WEIGHTS:
+        logging.getLogger("aldi_b200").warning("MODEL.WEIGHTS %s is not reachable here: synthetic initialisation", cfg.MODEL.WEIGHTS)
     hist = trainer.train(0, args.iters)
     if (not pg) or dist.get_rank() == 0:
         print({k: round(v, 5) for k, v in hist[-1].items()})
