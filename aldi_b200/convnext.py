@@ -169,6 +169,7 @@ class ConvNeXtBackbone:
                 p = "stages.%d.%d." % (i, j)
                 self.lin[p + "pwconv1"] = _Linear(self, p + "pwconv1", 4 * d, d)
                 self.lin[p + "pwconv2"] = _Linear(self, p + "pwconv2", d, 4 * d)
+        self._table = None
         self.refresh()
         self.saved = None
 
@@ -178,8 +179,36 @@ class ConvNeXtBackbone:
         return (self.flat if buf is None else buf)[off:off + n]
 
     def refresh(self):
-        for l in self.lin.values():
-            l.refresh()
+        """Re-derive every GEMM operand (forward, data-gradient, padded bias) from the master weights with ONE launch of
+        the batched refresh kernel (csrc/optim.cu) — the same descriptor table mechanism as DetectorWeights.refresh."""
+        if self._table is None:
+            L = _l.load()
+            descs = []
+
+            def desc(kind, **kw):
+                d = _l.RefreshDesc()
+                d.kind, d.out_dtype, d.eps = kind, self.dtc, 1e-6
+                for k, v in kw.items():
+                    setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+                descs.append(d)
+
+            for lin in self.lin.values():
+                w = self.view(lin.key + ".weight")
+                geo = dict(cout=lin.cout, taps=1, cin=lin.cin, cout_p=lin.cout_p, cin_p=lin.cin_p)
+                desc(0, w=w, out=lin.fwd, **geo)
+                if lin.bwd is not None:
+                    desc(1, w=w, out=lin.bwd, **geo)
+                desc(3, w=self.view(lin.key + ".bias"), out2=lin.bias, cout=lin.cout)
+            arr = (_l.RefreshDesc * len(descs))(*descs)
+            starts, tot = [], 0
+            for d in descs:
+                starts.append(tot)
+                tot += int(L.aldi_refresh_blocks(_l.ctypes.byref(d)))
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+            st = torch.tensor(starts, dtype=torch.int32).to(self.device)
+            self._table = (raw, st, len(descs), tot)
+        raw, st, n, tot = self._table
+        ops.call("aldi_refresh_operands", raw, st, n, tot)
 
     def state_dict(self):
         return self.layout.unpack(self.flat)
