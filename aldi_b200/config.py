@@ -213,6 +213,15 @@ def step_config_from_cfg(cfg, dtype=None):
         raise ValueError("Unsupported optimizer/backbone combination {} {}.".format(cfg.SOLVER.OPTIMIZER,
                                                                                      cfg.MODEL.BACKBONE.NAME))
     extra = {}
+    base_lr, weight_decay = cfg.SOLVER.BASE_LR, cfg.SOLVER.WEIGHT_DECAY
+    if optimizer == "ADAMW":
+        # aldi/trainer.py:205-206 -> get_adamw_optim(model) with no overrides (aldi/backbone.py:66-84): the optimizer is
+        # detectron2's configs/common/optim.py AdamW LazyConfig as it stands -- lr 1e-4, betas (0.9, 0.999), weight decay
+        # 0.1 -- and SOLVER.BASE_LR / SOLVER.WEIGHT_DECAY are never read on this branch (the ConvNeXt yaml's BASE_LR 0.06
+        # would diverge under AdamW).  The LR scheduler multiplies that 1e-4 (detectron2 LRMultiplier).  Its
+        # weight_decay_norm=0.0 exempts torch.nn norm modules only; ConvNeXt's LayerNorm is the reference's own
+        # nn.Module (aldi/backbone.py:331) and the FPN has no norm, so the decay is uniform over every parameter.
+        base_lr, weight_decay = 1e-4, 0.1
     if backbone == "convnext":
         extra = dict(convnext_depths=tuple(cfg.MODEL.CONVNEXT.DEPTHS), convnext_dims=tuple(cfg.MODEL.CONVNEXT.DIMS),
                      convnext_drop_path=cfg.MODEL.CONVNEXT.DROP_PATH_RATE)
@@ -233,8 +242,8 @@ def step_config_from_cfg(cfg, dtype=None):
         do_hard_cls=D.HARD_ROIH_CLS_ENABLED, do_hard_obj=D.HARD_OBJ_ENABLED, do_hard_rpn_reg=D.HARD_RPN_REG_ENABLED,
         do_hard_roi_reg=D.HARD_ROIH_REG_ENABLED, do_cls_dst=D.ROIH_CLS_ENABLED, do_obj_dst=D.OBJ_ENABLED,
         do_rpn_reg_dst=D.RPN_REG_ENABLED, do_roih_reg_dst=D.ROIH_REG_ENABLED, cls_temperature=D.CLS_TMP,
-        obj_temperature=D.OBJ_TMP, cls_loss_type=cfg.DOMAIN_ADAPT.CLS_LOSS_TYPE, base_lr=cfg.SOLVER.BASE_LR,
-        momentum=cfg.SOLVER.MOMENTUM, weight_decay=cfg.SOLVER.WEIGHT_DECAY,
+        obj_temperature=D.OBJ_TMP, cls_loss_type=cfg.DOMAIN_ADAPT.CLS_LOSS_TYPE, base_lr=base_lr,
+        momentum=cfg.SOLVER.MOMENTUM, weight_decay=weight_decay,
         rpn_pre_topk=(cfg.MODEL.RPN.PRE_NMS_TOPK_TRAIN, cfg.MODEL.RPN.PRE_NMS_TOPK_TEST),
         rpn_post_topk=(cfg.MODEL.RPN.POST_NMS_TOPK_TRAIN, cfg.MODEL.RPN.POST_NMS_TOPK_TEST),
         rpn_nms_thresh=cfg.MODEL.RPN.NMS_THRESH, rpn_batch=cfg.MODEL.RPN.BATCH_SIZE_PER_IMAGE,

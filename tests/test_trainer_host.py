@@ -72,7 +72,9 @@ def test_unsupported_combinations_fail_with_reference_errors(tmp_path):
     cfg = _cfg(tmp_path, ["SOLVER.OPTIMIZER", "LAMB"])                     # aldi/trainer.py:207-208
     with pytest.raises(ValueError, match="Unsupported optimizer/backbone combination"):
         step_config_from_cfg(cfg)
-    assert step_config_from_cfg(_cfg(tmp_path, ["SOLVER.OPTIMIZER", "ADAMW"])).optimizer == "ADAMW"
+    aw = step_config_from_cfg(_cfg(tmp_path, ["SOLVER.OPTIMIZER", "ADAMW", "SOLVER.BASE_LR", "0.06"]))
+    # get_adamw_optim() takes detectron2's common/optim.py AdamW unchanged: SOLVER.BASE_LR / WEIGHT_DECAY are not read
+    assert (aw.optimizer, aw.base_lr, aw.weight_decay, aw.adamw_betas) == ("ADAMW", 1e-4, 0.1, (0.9, 0.999))
     cn = step_config_from_cfg(_cfg(tmp_path, ["MODEL.BACKBONE.NAME", "build_convnext_fpn_backbone", "MODEL.CONVNEXT.DIMS",
                                               "[192, 384, 768, 1536]"]))
     assert cn.backbone == "convnext" and cn.convnext_dims == (192, 384, 768, 1536)
