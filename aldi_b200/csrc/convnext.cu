@@ -12,8 +12,20 @@
 //   aldi_patchify_image     uint8 NCHW image -> normalised 4x4x3 patches (48 of 64 channels), the stem's GEMM operand
 //   aldi_adamw_step         torch.optim.AdamW over the flat buffers (aldi/trainer.py:205-206)
 // All HBM-bound streams; fp32 arithmetic, activation dtype T in {float (parity mode), bf16}.
+#include <algorithm>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/aldi_b200.h"
+
+#define ALDI_CUDA_CHECK(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      aldi_set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                \
+      return ALDI_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
 
 namespace {
 
@@ -282,6 +294,245 @@ dw7_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int n, int h
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// bf16 depthwise 7x7 on shared-memory tiles (the default for bf16; the streaming kernels above remain for fp32 parity
+// mode).  The streaming forward re-reads every input element ~17x through L2 (7 filter rows x overlapping columns, no
+// reuse between output rows) and the streaming weight gradient 7x: both are L2-bound at a few per cent of the HBM
+// roofline.  Here a CTA stages a (16+6) x (16+6) pixel x 64 channel halo tile once (cp.async, zero-filled outside the
+// map, double-buffered against the previous tile's math) and a thread owns TWO channels -- one 32-bit word per pixel,
+// so a warp reads one conflict-free 128-byte wavefront per pixel -- with those channels' 49 taps (forward / data
+// gradient) or 49 partial sums (weight gradient) held in REGISTERS.  A warp owns two tile rows; a unit of work is
+// 2 rows x 8 pixels (forward: 1568 FMAs per 112 shared loads) or 1 row x 8 pixels (weight gradient: 784 per 106).
+constexpr int kDwT = 16, kDwHalo = kDwT + 6;
+constexpr int kDwXBytes = kDwHalo * kDwHalo * 128, kDwYBytes = kDwT * kDwT * 128;
+constexpr int kDwFwdSmem = 2 * kDwXBytes;
+constexpr int kDwWgScratch = 8 * 7 * 64 * (int)sizeof(float);
+constexpr int kDwWgSmem = 2 * (kDwXBytes + kDwYBytes) + kDwWgScratch;
+
+__device__ __forceinline__ uint32_t dw_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dw_cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dw_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void dw_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float2 dw_unpack(uint32_t v) {      // bf16x2 -> (low channel, high channel)
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
+// rows x cols pixels from (gy0, gx0) of image img, channels [c0, c0 + 64) -> dst + (row * cols + col) * 128 bytes;
+// pixels outside the map and channel chunks beyond the row stride arrive as zeros (cp.async src-size 0)
+__device__ __forceinline__ void dw_load_tile(const __nv_bfloat16* __restrict__ src, uint32_t dst, int img, int gy0, int gx0,
+                                             int rows, int cols, int h, int wd, int c0, int stride) {
+  const int chunks = rows * cols * 8;
+  for (int i = threadIdx.x; i < chunks; i += 256) {
+    const int k = i & 7, px = i >> 3;
+    const int row = px / cols, col = px - row * cols;
+    const int gy = gy0 + row, gx = gx0 + col;
+    const bool ok = gy >= 0 && gy < h && gx >= 0 && gx < wd && c0 + 8 * k < stride;
+    const __nv_bfloat16* p = ok ? src + (((long long)img * h + gy) * wd + gx) * stride + c0 + 8 * k : src;
+    dw_cp_async16(dst + (uint32_t)i * 16, p, ok ? 16 : 0);
+  }
+}
+
+struct DwTile { int cb, img, y0, x0; };
+__device__ __forceinline__ DwTile dw_tile(long long t, int n, int tiles_y, int tiles_x) {
+  DwTile d;
+  d.x0 = (int)(t % tiles_x) * kDwT;
+  t /= tiles_x;
+  d.y0 = (int)(t % tiles_y) * kDwT;
+  t /= tiles_y;
+  d.img = (int)(t % n);
+  d.cb = (int)(t / n);
+  return d;
+}
+
+template <bool FLIP>
+__global__ void __launch_bounds__(256, 1)
+dw7_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int n, int h,
+                int wd, int c, int stride, __nv_bfloat16* __restrict__ y, int accumulate) {
+  extern __shared__ __align__(128) unsigned char dw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_x = (wd + kDwT - 1) / kDwT, tiles_y = (h + kDwT - 1) / kDwT;
+  const long long total = (long long)((stride + 63) / 64) * n * tiles_y * tiles_x;
+  const uint32_t sbase = dw_smem_addr(dw_smem);
+  long long t = blockIdx.x;
+  if (t >= total) return;
+  {
+    const DwTile d = dw_tile(t, n, tiles_y, tiles_x);
+    dw_load_tile(x, sbase, d.img, d.y0 - 3, d.x0 - 3, kDwHalo, kDwHalo, h, wd, d.cb * 64, stride);
+    dw_cp_commit();
+  }
+  float2 wreg[49];
+  float2 breg = make_float2(0.f, 0.f);
+  int cur_cb = -1;
+  for (int it = 0; t < total; t += gridDim.x, ++it) {
+    const DwTile d = dw_tile(t, n, tiles_y, tiles_x);
+    const long long tn = t + gridDim.x;
+    if (tn < total) {
+      const DwTile e = dw_tile(tn, n, tiles_y, tiles_x);
+      dw_load_tile(x, sbase + ((it + 1) & 1) * kDwXBytes, e.img, e.y0 - 3, e.x0 - 3, kDwHalo, kDwHalo, h, wd, e.cb * 64, stride);
+    }
+    dw_cp_commit();
+    const int ch = d.cb * 64 + 2 * lane;
+    if (d.cb != cur_cb) {                                 // the tile index runs channel-block slowest: rare
+      cur_cb = d.cb;
+#pragma unroll
+      for (int tp = 0; tp < 49; ++tp) {
+        const int src = FLIP ? 48 - tp : tp;
+        wreg[tp].x = ch < c ? w[(size_t)ch * 49 + src] : 0.f;
+        wreg[tp].y = ch + 1 < c ? w[(size_t)(ch + 1) * 49 + src] : 0.f;
+      }
+      breg.x = (bias && ch < c) ? bias[ch] : 0.f;
+      breg.y = (bias && ch + 1 < c) ? bias[ch + 1] : 0.f;
+    }
+    dw_cp_wait<1>();
+    __syncthreads();
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kDwXBytes);
+#pragma unroll 1
+    for (int u = 0; u < 2; ++u) {
+      const int cx = u * 8;
+      float2 acc[2][8];
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[o][q] = breg;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                       // halo rows 2*warp + i feed output rows 2*warp + {0, 1}
+        const uint32_t* rowp = tile + ((2 * warp + i) * kDwHalo + cx) * 32 + lane;
+        float2 f[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) f[j] = dw_unpack(rowp[j * 32]);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int r = i - o;
+          if (r < 0 || r > 6) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int s7 = 0; s7 < 7; ++s7) {
+              acc[o][q].x = fmaf(f[q + s7].x, wreg[r * 7 + s7].x, acc[o][q].x);
+              acc[o][q].y = fmaf(f[q + s7].y, wreg[r * 7 + s7].y, acc[o][q].y);
+            }
+        }
+      }
+      if (ch < stride) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int gy = d.y0 + 2 * warp + o;
+          if (gy >= h) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int gx = d.x0 + cx + q;
+            if (gx >= wd) continue;
+            __nv_bfloat162* yp = reinterpret_cast<__nv_bfloat162*>(y + (((long long)d.img * h + gy) * wd + gx) * stride + ch);
+            float2 v = acc[o][q];
+            if (accumulate) {
+              const float2 old = __bfloat1622float2(*yp);
+              v.x += old.x;
+              v.y += old.y;
+            }
+            *yp = __floats2bfloat162_rn(v.x, v.y);
+          }
+        }
+      }
+    }
+    __syncthreads();                                      // the buffer is refilled by the next iteration's prefetch
+  }
+  dw_cp_wait<0>();
+}
+
+// weight gradient on the same tiles: x halo tile + dy tile in shared memory, 49 x 2 partial sums per thread in
+// registers over a CONTIGUOUS range of tiles; one cross-warp reduction + one atomicAdd per (channel, tap) per channel
+// block the range touches
+__global__ void __launch_bounds__(256, 1)
+dw7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int n, int h, int wd, int c,
+                      int stride, float* __restrict__ dw) {
+  extern __shared__ __align__(128) unsigned char dw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_x = (wd + kDwT - 1) / kDwT, tiles_y = (h + kDwT - 1) / kDwT;
+  const long long total = (long long)((stride + 63) / 64) * n * tiles_y * tiles_x;
+  const long long t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
+  if (t0 >= t1) return;
+  constexpr int kStage = kDwXBytes + kDwYBytes;
+  const uint32_t sbase = dw_smem_addr(dw_smem);
+  float* scratch = reinterpret_cast<float*>(dw_smem + 2 * kStage);          // [8 warps][7][64]
+  {
+    const DwTile d = dw_tile(t0, n, tiles_y, tiles_x);
+    dw_load_tile(x, sbase, d.img, d.y0 - 3, d.x0 - 3, kDwHalo, kDwHalo, h, wd, d.cb * 64, stride);
+    dw_load_tile(dy, sbase + kDwXBytes, d.img, d.y0, d.x0, kDwT, kDwT, h, wd, d.cb * 64, stride);
+    dw_cp_commit();
+  }
+  float2 acc[49];
+#pragma unroll
+  for (int tp = 0; tp < 49; ++tp) acc[tp] = make_float2(0.f, 0.f);
+  int cur_cb = dw_tile(t0, n, tiles_y, tiles_x).cb;
+
+  auto flush = [&](int cb) {
+    const int c0 = cb * 64;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      __syncthreads();
+#pragma unroll
+      for (int s7 = 0; s7 < 7; ++s7)
+        *reinterpret_cast<float2*>(scratch + (warp * 7 + s7) * 64 + 2 * lane) = acc[r * 7 + s7];
+      __syncthreads();
+      for (int i = threadIdx.x; i < 7 * 64; i += 256) {
+        const int s7 = i >> 6, cc = i & 63;
+        float v = 0.f;
+#pragma unroll
+        for (int wp = 0; wp < 8; ++wp) v += scratch[(wp * 7 + s7) * 64 + cc];
+        if (c0 + cc < c && v != 0.f) atomicAdd(dw + (size_t)(c0 + cc) * 49 + r * 7 + s7, v);
+      }
+    }
+#pragma unroll
+    for (int tp = 0; tp < 49; ++tp) acc[tp] = make_float2(0.f, 0.f);
+  };
+
+  int it = 0;
+  for (long long t = t0; t < t1; ++t, ++it) {
+    const DwTile d = dw_tile(t, n, tiles_y, tiles_x);
+    if (t + 1 < t1) {
+      const DwTile e = dw_tile(t + 1, n, tiles_y, tiles_x);
+      const uint32_t dst = sbase + ((it + 1) & 1) * kStage;
+      dw_load_tile(x, dst, e.img, e.y0 - 3, e.x0 - 3, kDwHalo, kDwHalo, h, wd, e.cb * 64, stride);
+      dw_load_tile(dy, dst + kDwXBytes, e.img, e.y0, e.x0, kDwT, kDwT, h, wd, e.cb * 64, stride);
+    }
+    dw_cp_commit();
+    if (d.cb != cur_cb) {
+      flush(cur_cb);
+      cur_cb = d.cb;
+    }
+    dw_cp_wait<1>();
+    __syncthreads();
+    const uint32_t* xt = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kStage);
+    const uint32_t* dt = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kStage + kDwXBytes);
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {                         // output row 2*warp + (u >> 1), columns (u & 1) * 8 ..
+      const int ro = 2 * warp + (u >> 1), cx = (u & 1) * 8;
+      float2 g[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = dw_unpack(dt[(ro * kDwT + cx + q) * 32 + lane]);
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        const uint32_t* rowp = xt + ((ro + r) * kDwHalo + cx) * 32 + lane;
+        float2 f[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) f[j] = dw_unpack(rowp[j * 32]);
+#pragma unroll
+        for (int s7 = 0; s7 < 7; ++s7)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            acc[r * 7 + s7].x = fmaf(g[q].x, f[q + s7].x, acc[r * 7 + s7].x);
+            acc[r * 7 + s7].y = fmaf(g[q].y, f[q + s7].y, acc[r * 7 + s7].y);
+          }
+      }
+    }
+    __syncthreads();
+  }
+  dw_cp_wait<0>();
+  flush(cur_cb);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_d(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
@@ -476,6 +727,22 @@ extern "C" int aldi_dwconv7(const void* x, const float* w, const float* bias, in
                             int flip, void* y, int accumulate, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(x && w && y && n > 0 && h > 0 && wd > 0 && c > 0 && stride >= c && stride % 8 == 0, "aldi_dwconv7: bad args");
+  static const bool legacy = getenv("ALDI_DW7_LEGACY") != nullptr;
+  if (dtype == ALDI_DTYPE_BF16 && !legacy) {
+    static bool attr = false;
+    if (!attr) {
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
+      attr = true;
+    }
+    const long long tiles = (long long)((stride + 63) / 64) * n * ((h + kDwT - 1) / kDwT) * ((wd + kDwT - 1) / kDwT);
+    const int tgrid = (int)std::min<long long>(tiles, aldi_num_sms());
+    if (flip) dw7_tile_kernel<true><<<tgrid, 256, kDwFwdSmem, stream>>>((const __nv_bfloat16*)x, w, bias, n, h, wd, c, stride, (__nv_bfloat16*)y, accumulate);
+    else dw7_tile_kernel<false><<<tgrid, 256, kDwFwdSmem, stream>>>((const __nv_bfloat16*)x, w, bias, n, h, wd, c, stride, (__nv_bfloat16*)y, accumulate);
+    ALDI_COUNT_LAUNCH();
+    ALDI_CUDA_LAUNCH_CHECK("aldi_dwconv7");
+    return ALDI_OK;
+  }
   const dim3 grid(blocks_for((long long)n * h * ((wd + 3) / 4), 32, 16), (stride + 63) / 64);
   if (dtype == ALDI_DTYPE_BF16) {
     if (flip) dw7_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, bias, n, h, wd, c, stride, (__nv_bfloat16*)y, accumulate);
@@ -493,6 +760,20 @@ extern "C" int aldi_dwconv7_wgrad(const void* x, const void* dy, int n, int h, i
                                   void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(x && dy && dw && n > 0 && c > 0 && stride >= c && stride % 8 == 0, "aldi_dwconv7_wgrad: bad args");
+  static const bool legacy = getenv("ALDI_DW7_LEGACY") != nullptr;
+  if (dtype == ALDI_DTYPE_BF16 && !legacy) {
+    static bool attr = false;
+    if (!attr) {
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwWgSmem));
+      attr = true;
+    }
+    const long long tiles = (long long)((stride + 63) / 64) * n * ((h + kDwT - 1) / kDwT) * ((wd + kDwT - 1) / kDwT);
+    const int tgrid = (int)std::min<long long>(tiles, aldi_num_sms());
+    dw7_wgrad_tile_kernel<<<tgrid, 256, kDwWgSmem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, n, h, wd, c, stride, dw);
+    ALDI_COUNT_LAUNCH();
+    ALDI_CUDA_LAUNCH_CHECK("aldi_dwconv7_wgrad");
+    return ALDI_OK;
+  }
   const dim3 grid(blocks_for((long long)n * h * ((wd + kWgRun - 1) / kWgRun), 32, 4), (stride + 63) / 64, 7);
   DISPATCH_T(dtype, (dw7_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)dy, n, h, wd, c, stride, dw)),
              (dw7_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, n, h, wd, c,

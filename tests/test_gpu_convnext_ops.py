@@ -46,7 +46,7 @@ def test_layernorm(mode, c, stride):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("c,stride,h,w", [(96, 128, 13, 19), (192, 192, 8, 8), (24, 64, 5, 30)])
+@pytest.mark.parametrize("c,stride,h,w", [(96, 128, 13, 19), (192, 192, 8, 8), (24, 64, 5, 30), (160, 192, 37, 50)])
 def test_dwconv7(mode, c, stride, h, w):
     from aldi_b200 import ops
     dt, code, tol = DT[mode]
@@ -73,6 +73,16 @@ def test_dwconv7(mode, c, stride, h, w):
     assert rel(y.cpu().float()[..., :c], yr.detach().permute(0, 2, 3, 1)) < tol
     assert rel(dx.cpu().float()[..., :c], xr.grad.permute(0, 2, 3, 1)) < tol
     assert rel(dw.cpu(), wr.grad.reshape(c, 49)) < tol
+    # accumulate: the data gradient is added onto what the residual branch already wrote; dw adds onto earlier passes
+    base = torch.randn(n, h, w, stride, generator=g).to(dt)
+    dx2 = base.cuda()
+    ops.call("aldi_dwconv7", dyd, wd, None, n, h, w, c, stride, code, 1, dx2, 1)
+    ops.call("aldi_dwconv7_wgrad", xd, dyd, n, h, w, c, stride, code, dw)
+    torch.cuda.synchronize()
+    assert rel(dx2.cpu().float()[..., :c], base.float()[..., :c] + xr.grad.permute(0, 2, 3, 1)) < tol
+    assert rel(dw.cpu(), 2 * wr.grad.reshape(c, 49)) < tol
+    if stride > c:                                                           # pad channels: old value + 0
+        assert torch.equal(dx2.cpu()[..., c:], base[..., c:])
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
