@@ -43,6 +43,11 @@ extern "C" void aldi_reset_launch_count(void) { g_aldi_launch_count = 0; }
 
 int aldi_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box) {
+  return aldi_make_tmap_bf16_sw(out, base, rank, dims, strides_bytes, box, 1);
+}
+
+int aldi_make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -65,7 +70,8 @@ int aldi_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                      bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     aldi_set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",

@@ -14,9 +14,14 @@
 // All HBM-bound streams; fp32 arithmetic, activation dtype T in {float (parity mode), bf16}.
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "sm100.cuh"
+#include "tmap.h"
 #include "../../include/aldi_b200.h"
+
+using namespace sm100;
 
 #define ALDI_CUDA_CHECK(expr)                                                        \
   do {                                                                               \
@@ -139,6 +144,182 @@ ln_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const fl
   for (int k = 0; k < CPL; ++k) {
     const int i = lane + 32 * k;
     if (i < c) { atomicAdd(&s_red[i], pg[k]); atomicAdd(&s_red[c + i], pb[k]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    if (s_red[i] != 0.f) atomicAdd(dgamma + i, s_red[i]);
+    if (s_red[c + i] != 0.f) atomicAdd(dbeta + i, s_red[c + i]);
+  }
+}
+
+// Vector variants (c and stride multiples of 8, c <= 2048): a lane owns 8-channel vectors j = lane + 32 k, moved as one
+// 16-byte (bf16) access instead of eight 2-byte ones; the forward keeps the row in registers (one read, one write) and
+// normalises RPW rows per warp iteration so that narrow rows still keep several loads in flight.
+template <typename T, int VPL, int RPW>
+__global__ void __launch_bounds__(256, 2)
+ln_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                  long long rows, int c, int stride, T* __restrict__ y, float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = c >> 3, svec = stride >> 3;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, wstep = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r0 = w0 * RPW; r0 < rows; r0 += wstep * RPW) {
+    float v[RPW][VPL][8];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nvec && r0 + rr < rows) V8<T>::load(x + (r0 + rr) * stride + 8 * j, v[rr][k]);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[rr][k][e] = 0.f;
+        }
+      }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const long long r = r0 + rr;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[rr][k][e];
+      const float mean = warp_sum(s) / (float)c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (lane + 32 * k < nvec) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const float d = v[rr][k][e] - mean; q += d * d; }
+        }
+      const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
+      if (r >= rows) continue;                            // warp-uniform
+      T* yr = y + r * stride;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nvec) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * j)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * j + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + 8 * j)), b1 = __ldg(reinterpret_cast<const float4*>(beta + 8 * j + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (v[rr][k][e] - mean) * rstd * gg[e] + bb[e];
+          V8<T>::store(yr + 8 * j, o);
+        }
+      }
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = nvec + lane; j < svec; j += 32) V8<T>::store(yr + 8 * j, z);
+      if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
+    }
+  }
+}
+
+// backward: d-gamma / d-beta partials of the lane's own channels stay in registers across all its rows.  Rows of up
+// to 1024 channels are held in registers as well (RPW rows per warp iteration: one read of x and dy); wider rows take
+// a second sweep that hits L1, as in the scalar kernel.
+template <typename T, int VPL, int RPW>
+__global__ void __launch_bounds__(256, VPL <= 3 ? 2 : 1)
+ln_bwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float2* __restrict__ stats,
+                  const T* __restrict__ dy, long long rows, int c, int stride, T* __restrict__ dx, int accumulate,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float s_red[];   // [2][c]
+  constexpr bool KEEP = VPL * RPW <= 4;
+  static_assert(KEEP || RPW == 1, "wide rows: one row per iteration");
+  const int lane = threadIdx.x & 31;
+  const int nvec = c >> 3, svec = stride >> 3;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, wstep = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  float pg[VPL][8], pb[VPL][8];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pg[k][e] = pb[k][e] = 0.f;
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long r0 = w0 * RPW; r0 < rows; r0 += wstep * RPW) {
+    float xv[KEEP ? RPW : 1][KEEP ? VPL : 1][8], dv[KEEP ? RPW : 1][KEEP ? VPL : 1][8];
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int j = lane + 32 * k;
+          if (j < nvec && r0 + rr < rows) {
+            V8<T>::load(x + (r0 + rr) * stride + 8 * j, xv[rr][k]);
+            V8<T>::load(dy + (r0 + rr) * stride + 8 * j, dv[rr][k]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xv[rr][k][e] = dv[rr][k][e] = 0.f;
+          }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const long long r = r0 + rr;
+      const bool live = r < rows;                         // warp-uniform
+      const T* xr = x + r * stride;
+      const T* dr = dy + r * stride;
+      const float2 st = live ? stats[r] : make_float2(0.f, 0.f);
+      float sg = 0.f, sgx = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nvec && live) {
+          float xs[8], ds[8];
+          if constexpr (!KEEP) {
+            V8<T>::load(xr + 8 * j, xs);
+            V8<T>::load(dr + 8 * j, ds);
+          }
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * j)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * j + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xe = KEEP ? xv[KEEP ? rr : 0][KEEP ? k : 0][e] : xs[e], de = KEEP ? dv[KEEP ? rr : 0][KEEP ? k : 0][e] : ds[e];
+            const float g = de * gg[e];
+            sg += g;
+            sgx += g * (xe - st.x) * st.y;
+          }
+        }
+      }
+      const float mg = warp_sum(sg) / (float)c, mgx = warp_sum(sgx) / (float)c;
+      if (!live) continue;
+      T* dxr = dx + r * stride;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nvec) {
+          float xs[8], ds[8], o[8];
+          if constexpr (!KEEP) {
+            V8<T>::load(xr + 8 * j, xs);
+            V8<T>::load(dr + 8 * j, ds);
+          }
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * j)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * j + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          if (accumulate) V8<T>::load(dxr + 8 * j, o);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xe = KEEP ? xv[KEEP ? rr : 0][KEEP ? k : 0][e] : xs[e], de = KEEP ? dv[KEEP ? rr : 0][KEEP ? k : 0][e] : ds[e];
+            const float xh = (xe - st.x) * st.y;
+            const float val = st.y * (de * gg[e] - mg - xh * mgx);
+            o[e] = accumulate ? o[e] + val : val;
+            pg[k][e] += de * xh;
+            pb[k][e] += de;
+          }
+          V8<T>::store(dxr + 8 * j, o);
+        }
+      }
+      if (!accumulate)
+        for (int j = nvec + lane; j < svec; j += 32) V8<T>::store(dxr + 8 * j, z);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int j = lane + 32 * k;
+    if (j < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(&s_red[8 * j + e], pg[k][e]); atomicAdd(&s_red[c + 8 * j + e], pb[k][e]); }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
@@ -298,15 +479,22 @@ dw7_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int n, int h
 // mode).  The streaming forward re-reads every input element ~17x through L2 (7 filter rows x overlapping columns, no
 // reuse between output rows) and the streaming weight gradient 7x: both are L2-bound at a few per cent of the HBM
 // roofline.  Here a CTA stages a (16+6) x (16+6) pixel x 64 channel halo tile once (cp.async, zero-filled outside the
-// map, double-buffered against the previous tile's math) and a thread owns TWO channels -- one 32-bit word per pixel,
+// map, double-buffered against the previous tile's math; ONE TMA box load per tile issued by one thread when the map
+// is at least a box wide -- per-thread cp.async had the warps stall on the load/store queue, ncu lg_throttle 1.3 per
+// issue -- and per-thread cp.async for smaller maps) and a thread owns TWO channels -- one 32-bit word per pixel,
 // so a warp reads one conflict-free 128-byte wavefront per pixel -- with those channels' 49 taps (forward / data
 // gradient) or 49 partial sums (weight gradient) held in REGISTERS.  A warp owns two tile rows; a unit of work is
 // 2 rows x 8 pixels (forward: 1568 FMAs per 112 shared loads) or 1 row x 8 pixels (weight gradient: 784 per 106).
 constexpr int kDwT = 16, kDwHalo = kDwT + 6;
 constexpr int kDwXBytes = kDwHalo * kDwHalo * 128, kDwYBytes = kDwT * kDwT * 128;
-constexpr int kDwFwdSmem = 2 * kDwXBytes;
 constexpr int kDwWgScratch = 8 * 7 * 64 * (int)sizeof(float);
-constexpr int kDwWgSmem = 2 * (kDwXBytes + kDwYBytes) + kDwWgScratch;
+constexpr int kDwTail = 16 + 128;                       // two mbarriers + slack to align the tiles to 128 bytes
+constexpr int kDwWBytes = 64 * 49 * (int)sizeof(float);   // one channel block's taps, staged coalesced
+constexpr int kDwFwdSmem = 2 * kDwXBytes + kDwWBytes + kDwTail;
+constexpr int kDwWgSmem = 2 * (kDwXBytes + kDwYBytes) + kDwWgScratch + kDwTail;
+__device__ __forceinline__ unsigned char* dw_align128(unsigned char* p) {
+  return p + ((128u - (smem_u32(p) & 127u)) & 127u);
+}
 
 __device__ __forceinline__ uint32_t dw_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dw_cp_async16(uint32_t dst, const void* src, int bytes) {
@@ -345,47 +533,82 @@ __device__ __forceinline__ DwTile dw_tile(long long t, int n, int tiles_y, int t
   return d;
 }
 
-template <bool FLIP>
+template <bool FLIP, bool TMA>
 __global__ void __launch_bounds__(256, 1)
-dw7_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int n, int h,
-                int wd, int c, int stride, __nv_bfloat16* __restrict__ y, int accumulate) {
-  extern __shared__ __align__(128) unsigned char dw_smem[];
+dw7_tile_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ bias, int n, int h, int wd, int c, int stride, __nv_bfloat16* __restrict__ y,
+                int accumulate) {
+  extern __shared__ unsigned char dw_smem_raw[];
+  unsigned char* dw_smem = dw_align128(dw_smem_raw);
+  float* s_w = reinterpret_cast<float*>(dw_smem + 2 * kDwXBytes);                  // [64][49]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_smem + 2 * kDwXBytes + kDwWBytes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_x = (wd + kDwT - 1) / kDwT, tiles_y = (h + kDwT - 1) / kDwT;
   const long long total = (long long)((stride + 63) / 64) * n * tiles_y * tiles_x;
-  const uint32_t sbase = dw_smem_addr(dw_smem);
-  long long t = blockIdx.x;
-  if (t >= total) return;
+  // a CONTIGUOUS range of tiles per CTA (channel block slowest): the taps in registers change at most once or twice
+  const long long t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
+  if (t0 >= t1) return;
+  const uint32_t sbase = smem_u32(dw_smem);
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+  }
   {
-    const DwTile d = dw_tile(t, n, tiles_y, tiles_x);
-    dw_load_tile(x, sbase, d.img, d.y0 - 3, d.x0 - 3, kDwHalo, kDwHalo, h, wd, d.cb * 64, stride);
-    dw_cp_commit();
+    const DwTile d = dw_tile(t0, n, tiles_y, tiles_x);
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[0], kDwXBytes);
+        tma_load_4d(dw_smem, &tmX, &bars[0], d.cb * 64, d.x0 - 3, d.y0 - 3, d.img);
+      }
+    } else {
+      dw_load_tile(x, sbase, d.img, d.y0 - 3, d.x0 - 3, kDwHalo, kDwHalo, h, wd, d.cb * 64, stride);
+      dw_cp_commit();
+    }
   }
   float2 wreg[49];
   float2 breg = make_float2(0.f, 0.f);
   int cur_cb = -1;
-  for (int it = 0; t < total; t += gridDim.x, ++it) {
+  int it = 0;
+  for (long long t = t0; t < t1; ++t, ++it) {
     const DwTile d = dw_tile(t, n, tiles_y, tiles_x);
-    const long long tn = t + gridDim.x;
-    if (tn < total) {
-      const DwTile e = dw_tile(tn, n, tiles_y, tiles_x);
-      dw_load_tile(x, sbase + ((it + 1) & 1) * kDwXBytes, e.img, e.y0 - 3, e.x0 - 3, kDwHalo, kDwHalo, h, wd, e.cb * 64, stride);
+    if (t + 1 < t1) {
+      const DwTile e = dw_tile(t + 1, n, tiles_y, tiles_x);
+      if (TMA) {
+        if (threadIdx.x == 0) {                           // the buffer was released by the barrier that ended trip it - 1
+          mbar_expect_tx(&bars[(it + 1) & 1], kDwXBytes);
+          tma_load_4d(dw_smem + ((it + 1) & 1) * kDwXBytes, &tmX, &bars[(it + 1) & 1], e.cb * 64, e.x0 - 3, e.y0 - 3, e.img);
+        }
+      } else {
+        dw_load_tile(x, sbase + ((it + 1) & 1) * kDwXBytes, e.img, e.y0 - 3, e.x0 - 3, kDwHalo, kDwHalo, h, wd, e.cb * 64, stride);
+      }
     }
-    dw_cp_commit();
+    if (!TMA) dw_cp_commit();
     const int ch = d.cb * 64 + 2 * lane;
-    if (d.cb != cur_cb) {                                 // the tile index runs channel-block slowest: rare
+    if (d.cb != cur_cb) {                                 // block-uniform
       cur_cb = d.cb;
+      const int c0 = d.cb * 64;
+      for (int i = threadIdx.x; i < 64 * 49; i += 256)    // contiguous in global memory: coalesced
+        s_w[i] = (c0 + i / 49 < c) ? w[(size_t)c0 * 49 + i] : 0.f;
+      __syncthreads();
 #pragma unroll
       for (int tp = 0; tp < 49; ++tp) {
         const int src = FLIP ? 48 - tp : tp;
-        wreg[tp].x = ch < c ? w[(size_t)ch * 49 + src] : 0.f;
-        wreg[tp].y = ch + 1 < c ? w[(size_t)(ch + 1) * 49 + src] : 0.f;
+        wreg[tp] = make_float2(s_w[(2 * lane) * 49 + src], s_w[(2 * lane + 1) * 49 + src]);
       }
       breg.x = (bias && ch < c) ? bias[ch] : 0.f;
       breg.y = (bias && ch + 1 < c) ? bias[ch + 1] : 0.f;
+      // (the next write of s_w is behind at least one end-of-trip barrier)
     }
-    dw_cp_wait<1>();
-    __syncthreads();
+    if (TMA) {
+      mbar_wait(&bars[it & 1], (it >> 1) & 1);
+    } else {
+      dw_cp_wait<1>();
+      __syncthreads();
+    }
     const uint32_t* tile = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kDwXBytes);
 #pragma unroll 1
     for (int u = 0; u < 2; ++u) {
@@ -401,18 +624,19 @@ dw7_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
         float2 f[14];
 #pragma unroll
         for (int j = 0; j < 14; ++j) f[j] = dw_unpack(rowp[j * 32]);
+        // tap-major order: consecutive FMAs go to 16 different accumulators (x 2 channels), never back to back on one
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const int r = i - o;
-          if (r < 0 || r > 6) continue;
+        for (int s7 = 0; s7 < 7; ++s7)
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int o = 0; o < 2; ++o) {
+            const int r = i - o;
+            if (r < 0 || r > 6) continue;
 #pragma unroll
-            for (int s7 = 0; s7 < 7; ++s7) {
+            for (int q = 0; q < 8; ++q) {
               acc[o][q].x = fmaf(f[q + s7].x, wreg[r * 7 + s7].x, acc[o][q].x);
               acc[o][q].y = fmaf(f[q + s7].y, wreg[r * 7 + s7].y, acc[o][q].y);
             }
-        }
+          }
       }
       if (ch < stride) {
 #pragma unroll
@@ -437,16 +661,19 @@ dw7_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
     }
     __syncthreads();                                      // the buffer is refilled by the next iteration's prefetch
   }
-  dw_cp_wait<0>();
+  if (!TMA) dw_cp_wait<0>();
 }
 
 // weight gradient on the same tiles: x halo tile + dy tile in shared memory, 49 x 2 partial sums per thread in
 // registers over a CONTIGUOUS range of tiles; one cross-warp reduction + one atomicAdd per (channel, tap) per channel
 // block the range touches
+template <bool TMA>
 __global__ void __launch_bounds__(256, 1)
-dw7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int n, int h, int wd, int c,
+dw7_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                      const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int n, int h, int wd, int c,
                       int stride, float* __restrict__ dw) {
-  extern __shared__ __align__(128) unsigned char dw_smem[];
+  extern __shared__ unsigned char dw_smem_raw[];
+  unsigned char* dw_smem = dw_align128(dw_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_x = (wd + kDwT - 1) / kDwT, tiles_y = (h + kDwT - 1) / kDwT;
   const long long total = (long long)((stride + 63) / 64) * n * tiles_y * tiles_x;
@@ -455,11 +682,28 @@ dw7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   constexpr int kStage = kDwXBytes + kDwYBytes;
   const uint32_t sbase = dw_smem_addr(dw_smem);
   float* scratch = reinterpret_cast<float*>(dw_smem + 2 * kStage);          // [8 warps][7][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_smem + 2 * kStage + kDwWgScratch);
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+  }
   {
     const DwTile d = dw_tile(t0, n, tiles_y, tiles_x);
-    dw_load_tile(x, sbase, d.img, d.y0 - 3, d.x0 - 3, kDwHalo, kDwHalo, h, wd, d.cb * 64, stride);
-    dw_load_tile(dy, sbase + kDwXBytes, d.img, d.y0, d.x0, kDwT, kDwT, h, wd, d.cb * 64, stride);
-    dw_cp_commit();
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[0], kStage);
+        tma_load_4d(dw_smem, &tmX, &bars[0], d.cb * 64, d.x0 - 3, d.y0 - 3, d.img);
+        tma_load_4d(dw_smem + kDwXBytes, &tmDY, &bars[0], d.cb * 64, d.x0, d.y0, d.img);
+      }
+    } else {
+      dw_load_tile(x, sbase, d.img, d.y0 - 3, d.x0 - 3, kDwHalo, kDwHalo, h, wd, d.cb * 64, stride);
+      dw_load_tile(dy, sbase + kDwXBytes, d.img, d.y0, d.x0, kDwT, kDwT, h, wd, d.cb * 64, stride);
+      dw_cp_commit();
+    }
   }
   float2 acc[49];
 #pragma unroll
@@ -492,17 +736,30 @@ dw7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
     const DwTile d = dw_tile(t, n, tiles_y, tiles_x);
     if (t + 1 < t1) {
       const DwTile e = dw_tile(t + 1, n, tiles_y, tiles_x);
-      const uint32_t dst = sbase + ((it + 1) & 1) * kStage;
-      dw_load_tile(x, dst, e.img, e.y0 - 3, e.x0 - 3, kDwHalo, kDwHalo, h, wd, e.cb * 64, stride);
-      dw_load_tile(dy, dst + kDwXBytes, e.img, e.y0, e.x0, kDwT, kDwT, h, wd, e.cb * 64, stride);
+      if (TMA) {
+        if (threadIdx.x == 0) {
+          unsigned char* dstp = dw_smem + ((it + 1) & 1) * kStage;
+          mbar_expect_tx(&bars[(it + 1) & 1], kStage);
+          tma_load_4d(dstp, &tmX, &bars[(it + 1) & 1], e.cb * 64, e.x0 - 3, e.y0 - 3, e.img);
+          tma_load_4d(dstp + kDwXBytes, &tmDY, &bars[(it + 1) & 1], e.cb * 64, e.x0, e.y0, e.img);
+        }
+      } else {
+        const uint32_t dst = sbase + ((it + 1) & 1) * kStage;
+        dw_load_tile(x, dst, e.img, e.y0 - 3, e.x0 - 3, kDwHalo, kDwHalo, h, wd, e.cb * 64, stride);
+        dw_load_tile(dy, dst + kDwXBytes, e.img, e.y0, e.x0, kDwT, kDwT, h, wd, e.cb * 64, stride);
+      }
     }
-    dw_cp_commit();
+    if (!TMA) dw_cp_commit();
     if (d.cb != cur_cb) {
       flush(cur_cb);
       cur_cb = d.cb;
     }
-    dw_cp_wait<1>();
-    __syncthreads();
+    if (TMA) {
+      mbar_wait(&bars[it & 1], (it >> 1) & 1);
+    } else {
+      dw_cp_wait<1>();
+      __syncthreads();
+    }
     const uint32_t* xt = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kStage);
     const uint32_t* dt = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kStage + kDwXBytes);
 #pragma unroll 1
@@ -517,10 +774,11 @@ dw7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
         float2 f[14];
 #pragma unroll
         for (int j = 0; j < 14; ++j) f[j] = dw_unpack(rowp[j * 32]);
+        // pixel-major order: consecutive FMAs go to 7 different partial sums (x 2 channels)
 #pragma unroll
-        for (int s7 = 0; s7 < 7; ++s7)
+        for (int q = 0; q < 8; ++q)
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int s7 = 0; s7 < 7; ++s7) {
             acc[r * 7 + s7].x = fmaf(g[q].x, f[q + s7].x, acc[r * 7 + s7].x);
             acc[r * 7 + s7].y = fmaf(g[q].y, f[q + s7].y, acc[r * 7 + s7].y);
           }
@@ -528,8 +786,20 @@ dw7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
     }
     __syncthreads();
   }
-  dw_cp_wait<0>();
+  if (!TMA) dw_cp_wait<0>();
   flush(cur_cb);
+}
+
+// (C, W, H, N) view of a channels-last bf16 map with a 64-channel x bw x bh box, linear in shared memory
+int dw_make_map(CUtensorMap* tm, const void* base, int n, int h, int wd, int stride, int bw, int bh) {
+  const uint64_t dims[4] = {(uint64_t)stride, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+  const uint64_t strides[3] = {(uint64_t)stride * 2, (uint64_t)wd * stride * 2, (uint64_t)h * wd * stride * 2};
+  const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  return aldi_make_tmap_bf16_sw(tm, base, 4, dims, strides, box, 0);
+}
+bool dw_tma_ok(const void* a, const void* b, int h, int wd, int stride) {
+  static const bool off = getenv("ALDI_DW7_NO_TMA") != nullptr;
+  return !off && h >= kDwHalo && wd >= kDwHalo && stride >= 64 && ((uintptr_t)a & 15) == 0 && (!b || ((uintptr_t)b & 15) == 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -537,15 +807,53 @@ __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff
 __device__ __forceinline__ float gelu_d(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
 }
+// bf16 activations: Phi(x) from the Abramowitz-Stegun 7.1.26 rational form of erf (|error| <= 1.5e-7, two orders below
+// bf16 rounding), evaluated on the TAIL Phi(-|x|) = poly(t) e^{-x^2/2} / 2 so that negative x has no 1 + erf cancellation;
+// the exponential is shared with the density term of the derivative.  ~14 instructions per element instead of erff's
+// ~25 (+ expf), which had the kernel instruction-bound at the same level as its HBM floor.  fp32 (parity mode) keeps erff.
+__device__ __forceinline__ float dw_ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float dw_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ void gelu_phi_fast(float x, float& Phi, float& e) {
+  e = dw_ex2(x * x * (-0.5f * 1.44269504088896340736f));       // exp(-x^2 / 2): two MUFU ops per element in total
+  const float t = dw_rcp(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float tail = p * t * e;
+  Phi = x >= 0.f ? 1.f - tail : tail;
+}
+template <typename T, bool BWD> __device__ __forceinline__ float gelu_apply(float h, float g) {
+  if constexpr (sizeof(T) == 2) {
+    float Phi, e;
+    gelu_phi_fast(h, Phi, e);
+    return BWD ? g * fmaf(h * 0.39894228040143267794f, e, Phi) : h * Phi;
+  } else {
+    return BWD ? g * gelu_d(h) : gelu_f(h);
+  }
+}
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) gelu_kernel(const T* __restrict__ h, const T* __restrict__ da, T* __restrict__ out, size_t n8) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-    float f[8], g[8];
+  // two vectors per thread per trip (the second one gridDim * blockDim further on): twice the loads in flight
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += 2 * step) {
+    const size_t i2 = i + step;
+    const bool two = i2 < n8;
+    float f[8], g[8], f2[8], g2[8];
     V8<T>::load(h + i * 8, f);
-    if (BWD) V8<T>::load(da + i * 8, g);
+    if (two) V8<T>::load(h + i2 * 8, f2);
+    if (BWD) {
+      V8<T>::load(da + i * 8, g);
+      if (two) V8<T>::load(da + i2 * 8, g2);
+    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = BWD ? g[k] * gelu_d(f[k]) : gelu_f(f[k]);
+    for (int k = 0; k < 8; ++k) f[k] = gelu_apply<T, BWD>(f[k], BWD ? g[k] : 0.f);
     V8<T>::store(out + i * 8, f);
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f2[k] = gelu_apply<T, BWD>(f2[k], BWD ? g2[k] : 0.f);
+      V8<T>::store(out + i2 * 8, f2);
+    }
   }
 }
 
@@ -685,6 +993,29 @@ extern "C" int aldi_layernorm_forward(const void* x, const float* gamma, const f
                                       int stride, int dtype, void* y, float* stats, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(x && gamma && beta && y && rows > 0 && c > 0 && stride >= c, "aldi_layernorm_forward: bad args");
+  static const bool legacy = getenv("ALDI_LN_LEGACY") != nullptr;
+  if (!legacy && c % 8 == 0 && stride % 8 == 0 && c <= 2048) {
+    const int nvec = c / 8;
+#define LN_FWD(TT, VPL, RPW)                                                                                          \
+  ln_fwd_vec_kernel<TT, VPL, RPW><<<blocks_for(rows, 8 * RPW, 8), 256, 0, stream>>>((const TT*)x, gamma, beta, eps, rows, c, \
+                                                                                   stride, (TT*)y, (float2*)stats)
+#define LN_FWD_T(TT)                          \
+  do {                                        \
+    if (nvec <= 32) LN_FWD(TT, 1, 4);         \
+    else if (nvec <= 64) LN_FWD(TT, 2, 2);    \
+    else if (nvec <= 96) LN_FWD(TT, 3, 1);    \
+    else if (nvec <= 128) LN_FWD(TT, 4, 1);   \
+    else if (nvec <= 192) LN_FWD(TT, 6, 1);   \
+    else LN_FWD(TT, 8, 1);                    \
+  } while (0)
+    if (dtype == ALDI_DTYPE_BF16) LN_FWD_T(__nv_bfloat16);
+    else LN_FWD_T(float);
+#undef LN_FWD_T
+#undef LN_FWD
+    ALDI_COUNT_LAUNCH();
+    ALDI_CUDA_LAUNCH_CHECK("aldi_layernorm_forward");
+    return ALDI_OK;
+  }
   const int grid = blocks_for(rows, 8, 8);
   DISPATCH_T(dtype,
              (ln_fwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, gamma, beta, eps, rows, c, stride, (float*)y, (float2*)stats)),
@@ -704,6 +1035,32 @@ extern "C" int aldi_layernorm_backward(const void* x, const float* gamma, const 
   ALDI_CHECK_ARG(c <= 2048, "aldi_layernorm_backward: at most 2048 channels");
   const int grid = blocks_for(rows, 8 * 16, 4);
   const size_t smem = (size_t)2 * c * sizeof(float);
+  static const bool legacy = getenv("ALDI_LN_LEGACY") != nullptr;
+  if (!legacy && c % 8 == 0 && stride % 8 == 0) {
+    const int nvec = c / 8;
+    // enough CTAs to fill the GPU even for a few thousand rows, few enough that the per-CTA d-gamma / d-beta atomics
+    // (2 c each) stay cheap: >= 4 rows per warp, at most two CTAs per SM
+    const int vgrid = blocks_for(rows, 8 * 4, 2);
+#define LN_BWDV(TT, VPL, RPW)                                                                                                  \
+  ln_bwd_vec_kernel<TT, VPL, RPW><<<vgrid, 256, smem, stream>>>((const TT*)x, gamma, (const float2*)stats, (const TT*)dy, rows, c,    \
+                                                               stride, (TT*)dx, accumulate, dgamma, dbeta)
+#define LN_BWDV_T(TT)                         \
+  do {                                        \
+    if (nvec <= 32) LN_BWDV(TT, 1, 4);        \
+    else if (nvec <= 64) LN_BWDV(TT, 2, 1);   \
+    else if (nvec <= 96) LN_BWDV(TT, 3, 1);   \
+    else if (nvec <= 128) LN_BWDV(TT, 4, 1);  \
+    else if (nvec <= 192) LN_BWDV(TT, 6, 1);  \
+    else LN_BWDV(TT, 8, 1);                   \
+  } while (0)
+    if (dtype == ALDI_DTYPE_BF16) LN_BWDV_T(__nv_bfloat16);
+    else LN_BWDV_T(float);
+#undef LN_BWDV_T
+#undef LN_BWDV
+    ALDI_COUNT_LAUNCH();
+    ALDI_CUDA_LAUNCH_CHECK("aldi_layernorm_backward");
+    return ALDI_OK;
+  }
 #define LN_BWD(TT, CPL)                                                                                                    \
   ln_bwd_kernel<TT, CPL><<<grid, 256, smem, stream>>>((const TT*)x, gamma, (const float2*)stats, (const TT*)dy, rows, c, stride, \
                                                       (TT*)dx, accumulate, dgamma, dbeta)
@@ -731,14 +1088,27 @@ extern "C" int aldi_dwconv7(const void* x, const float* w, const float* bias, in
   if (dtype == ALDI_DTYPE_BF16 && !legacy) {
     static bool attr = false;
     if (!attr) {
-      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
-      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwFwdSmem));
       attr = true;
     }
     const long long tiles = (long long)((stride + 63) / 64) * n * ((h + kDwT - 1) / kDwT) * ((wd + kDwT - 1) / kDwT);
     const int tgrid = (int)std::min<long long>(tiles, aldi_num_sms());
-    if (flip) dw7_tile_kernel<true><<<tgrid, 256, kDwFwdSmem, stream>>>((const __nv_bfloat16*)x, w, bias, n, h, wd, c, stride, (__nv_bfloat16*)y, accumulate);
-    else dw7_tile_kernel<false><<<tgrid, 256, kDwFwdSmem, stream>>>((const __nv_bfloat16*)x, w, bias, n, h, wd, c, stride, (__nv_bfloat16*)y, accumulate);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (dw_tma_ok(x, nullptr, h, wd, stride)) {
+      int rc = dw_make_map(&tm, x, n, h, wd, stride, kDwHalo, kDwHalo);
+      if (rc != ALDI_OK) return rc;
+      if (flip) dw7_tile_kernel<true, true><<<tgrid, 256, kDwFwdSmem, stream>>>(tm, xb, w, bias, n, h, wd, c, stride, yb, accumulate);
+      else dw7_tile_kernel<false, true><<<tgrid, 256, kDwFwdSmem, stream>>>(tm, xb, w, bias, n, h, wd, c, stride, yb, accumulate);
+    } else {
+      if (flip) dw7_tile_kernel<true, false><<<tgrid, 256, kDwFwdSmem, stream>>>(tm, xb, w, bias, n, h, wd, c, stride, yb, accumulate);
+      else dw7_tile_kernel<false, false><<<tgrid, 256, kDwFwdSmem, stream>>>(tm, xb, w, bias, n, h, wd, c, stride, yb, accumulate);
+    }
     ALDI_COUNT_LAUNCH();
     ALDI_CUDA_LAUNCH_CHECK("aldi_dwconv7");
     return ALDI_OK;
@@ -764,12 +1134,25 @@ extern "C" int aldi_dwconv7_wgrad(const void* x, const void* dy, int n, int h, i
   if (dtype == ALDI_DTYPE_BF16 && !legacy) {
     static bool attr = false;
     if (!attr) {
-      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwWgSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_wgrad_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwWgSmem));
+      ALDI_CUDA_CHECK(cudaFuncSetAttribute(dw7_wgrad_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwWgSmem));
       attr = true;
     }
     const long long tiles = (long long)((stride + 63) / 64) * n * ((h + kDwT - 1) / kDwT) * ((wd + kDwT - 1) / kDwT);
     const int tgrid = (int)std::min<long long>(tiles, aldi_num_sms());
-    dw7_wgrad_tile_kernel<<<tgrid, 256, kDwWgSmem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, n, h, wd, c, stride, dw);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    const __nv_bfloat16* db = (const __nv_bfloat16*)dy;
+    CUtensorMap tmx, tmd;
+    memset(&tmx, 0, sizeof(tmx));
+    memset(&tmd, 0, sizeof(tmd));
+    if (dw_tma_ok(x, dy, h, wd, stride)) {
+      int rc = dw_make_map(&tmx, x, n, h, wd, stride, kDwHalo, kDwHalo);
+      if (rc == ALDI_OK) rc = dw_make_map(&tmd, dy, n, h, wd, stride, kDwT, kDwT);
+      if (rc != ALDI_OK) return rc;
+      dw7_wgrad_tile_kernel<true><<<tgrid, 256, kDwWgSmem, stream>>>(tmx, tmd, xb, db, n, h, wd, c, stride, dw);
+    } else {
+      dw7_wgrad_tile_kernel<false><<<tgrid, 256, kDwWgSmem, stream>>>(tmx, tmd, xb, db, n, h, wd, c, stride, dw);
+    }
     ALDI_COUNT_LAUNCH();
     ALDI_CUDA_LAUNCH_CHECK("aldi_dwconv7_wgrad");
     return ALDI_OK;
