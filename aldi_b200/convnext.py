@@ -15,6 +15,7 @@ tests/test_gpu_convnext.py) and returns the four normalised stage outputs the re
 (build_convnext_fpn_backbone, aldi/backbone.py:373-392), `B200TrainStep(StepConfig(backbone="convnext", ...))` trains
 it with AdamW and EMA (tests/test_gpu_step_parity.py::test_convnext_*).
 """
+import os
 from collections import OrderedDict
 
 import torch
@@ -133,12 +134,19 @@ class _Linear:
 
     def backward(self, x, dy, want_dx=True):
         G = self.net.grad
-        ops.wgrad(x, dy, self.net.view(self.key + ".weight", G), cout_store=self.cout, cin_store=self.cin)
-        rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
         db = self.net.view(self.key + ".bias", G)
-        flat_dy = dy.view(rows, dy.shape[3])
-        for c0 in range(0, self.cout, 2048):       # aldi_colsum handles up to 2048 channels per launch
-            ops.call("aldi_colsum", flat_dy[:, c0:], self.net.dtc, 1, rows, 0, dy.shape[3], min(2048, self.cout - c0), 1.0, db[c0:])
+        # bf16: the bias gradient rides on the weight-gradient pass (column sums of the dy tiles it already stages in
+        # shared memory) -- the 4x-wide hidden gradient is not read a second time; ALDI_CONVNEXT_COLSUM=1 keeps the
+        # separate aldi_colsum pass (A/B knob), which fp32 parity mode always uses
+        fused = dy.dtype == torch.bfloat16 and os.environ.get("ALDI_CONVNEXT_COLSUM") != "1"
+        ops.wgrad(x, dy, self.net.view(self.key + ".weight", G), cout_store=self.cout, cin_store=self.cin,
+                  dbias=db if fused else None)
+        if not fused:
+            rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
+            flat_dy = dy.view(rows, dy.shape[3])
+            for c0 in range(0, self.cout, 2048):       # aldi_colsum handles up to 2048 channels per launch
+                ops.call("aldi_colsum", flat_dy[:, c0:], self.net.dtc, 1, rows, 0, dy.shape[3], min(2048, self.cout - c0), 1.0,
+                         db[c0:])
         if not want_dx:
             return None
         dx = torch.empty_like(x)

@@ -863,18 +863,31 @@ __global__ void __launch_bounds__(256)
 layerscale_fwd_kernel(const T* __restrict__ u, const T* __restrict__ input, const float* __restrict__ gamma,
                       const float* __restrict__ keep, long long rows, long long rows_per_image, int c, int stride,
                       T* __restrict__ out) {
+  // (row, channel vector, image) advance incrementally: the 64-bit divisions of a flat index cost more instructions
+  // per 16-byte vector than the arithmetic itself
   const int cv = stride / 8;
-  const size_t total = (size_t)rows * cv;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % cv) * 8;
-    const long long r = (long long)(i / cv);
-    const float m = keep ? keep[r / rows_per_image] : 1.f;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long r = id / cv;
+  int col = (int)(id - r * cv);
+  const long long dr = nthreads / cv;
+  const int dc = (int)(nthreads - dr * cv);
+  long long img = r / rows_per_image, rem = r - img * rows_per_image;
+  while (r < rows) {
+    const int ch = col * 8;
+    const float m = keep ? keep[img] : 1.f;
     float a[8], b[8];
     V8<T>::load(u + r * stride + ch, a);
     V8<T>::load(input + r * stride + ch, b);
 #pragma unroll
     for (int k = 0; k < 8; ++k) b[k] += (ch + k < c) ? (gamma ? gamma[ch + k] : 1.f) * a[k] * m : 0.f;
     V8<T>::store(out + r * stride + ch, b);
+    long long step = dr;
+    col += dc;
+    if (col >= cv) { col -= cv; ++step; }
+    r += step;
+    rem += step;
+    while (rem >= rows_per_image) { rem -= rows_per_image; ++img; }
   }
 }
 
@@ -892,8 +905,12 @@ layerscale_bwd_kernel(const T* __restrict__ u, const T* __restrict__ dy, const f
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (ch < stride) {
-    for (long long r = (long long)blockIdx.x * 32 + pl; r < rows; r += (long long)gridDim.x * 32) {
-      const float m = keep ? keep[r / rows_per_image] : 1.f;
+    const long long r_first = (long long)blockIdx.x * 32 + pl, r_step = (long long)gridDim.x * 32;
+    long long img = r_first / rows_per_image, rem = r_first - img * rows_per_image;
+    for (long long r = r_first; r < rows; r += r_step) {
+      const float m = keep ? keep[img] : 1.f;
+      rem += r_step;
+      while (rem >= rows_per_image) { rem -= rows_per_image; ++img; }
       float a[8], d[8], o[8];
       V8<T>::load(u + r * stride + ch, a);
       V8<T>::load(dy + r * stride + ch, d);
@@ -937,6 +954,41 @@ s2d_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int ho, int wo,
     const size_t fine = ((((size_t)img * ho * b + (size_t)y * b + dy) * wo * b) + (size_t)x * b + dx) * in_stride + ch;
     if (INVERSE) out[fine] = in[i];   // here `in` is the (coarse, b*b*c) gradient and `out` the fine map
     else out[i] = in[fine];
+  }
+}
+
+// 8-channel vectors (c, both strides multiples of 8; fewer than 2^31 vectors): one 16-byte (bf16) move and one index
+// decomposition per vector instead of per element
+template <typename T> __device__ __forceinline__ void copy8(const T* src, T* dst);
+template <> __device__ __forceinline__ void copy8<__nv_bfloat16>(const __nv_bfloat16* src, __nv_bfloat16* dst) {
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+}
+template <> __device__ __forceinline__ void copy8<float>(const float* src, float* dst) {
+  reinterpret_cast<float4*>(dst)[0] = reinterpret_cast<const float4*>(src)[0];
+  reinterpret_cast<float4*>(dst)[1] = reinterpret_cast<const float4*>(src)[1];
+}
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(256)
+s2d_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int ho, int wo, int b, int c, int in_stride, int out_stride) {
+  const unsigned kc = b * b * c, cvo = out_stride / 8;
+  const unsigned total = (unsigned)n * ho * wo * cvo;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned k = (i % cvo) * 8;
+    unsigned r = i / cvo;
+    const unsigned x = r % wo;
+    r /= wo;
+    const unsigned y = r % ho, img = r / ho;
+    if (k >= kc) {
+      if (!INVERSE) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        V8<T>::store(out + (size_t)i * 8, z);
+      }
+      continue;
+    }
+    const unsigned ch = k % c, dd = k / c, dx = dd % b, dy = dd / b;
+    const size_t fine = ((((size_t)img * ho * b + (size_t)y * b + dy) * wo * b) + (size_t)x * b + dx) * in_stride + ch;
+    if (INVERSE) copy8<T>(in + (size_t)i * 8, out + fine);
+    else copy8<T>(in + fine, out + (size_t)i * 8);
   }
 }
 
@@ -1219,6 +1271,21 @@ extern "C" int aldi_space_to_depth(const void* in, void* out, int n, int ho, int
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(in && out && n > 0 && ho > 0 && wo > 0 && block >= 1 && c > 0 && in_stride >= c && out_stride >= block * block * c,
                  "aldi_space_to_depth: bad args");
+  const long long nvec = (long long)n * ho * wo * (out_stride / 8);
+  if (c % 8 == 0 && in_stride % 8 == 0 && out_stride % 8 == 0 && nvec < (1LL << 31) && ((uintptr_t)in & 15) == 0 &&
+      ((uintptr_t)out & 15) == 0) {
+    const int vgrid = blocks_for(nvec, 256, 8);
+    if (dtype == ALDI_DTYPE_BF16) {
+      if (inverse) s2d_vec_kernel<__nv_bfloat16, true><<<vgrid, 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n, ho, wo, block, c, in_stride, out_stride);
+      else s2d_vec_kernel<__nv_bfloat16, false><<<vgrid, 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n, ho, wo, block, c, in_stride, out_stride);
+    } else {
+      if (inverse) s2d_vec_kernel<float, true><<<vgrid, 256, 0, stream>>>((const float*)in, (float*)out, n, ho, wo, block, c, in_stride, out_stride);
+      else s2d_vec_kernel<float, false><<<vgrid, 256, 0, stream>>>((const float*)in, (float*)out, n, ho, wo, block, c, in_stride, out_stride);
+    }
+    ALDI_COUNT_LAUNCH();
+    ALDI_CUDA_LAUNCH_CHECK("aldi_space_to_depth");
+    return ALDI_OK;
+  }
   const int grid = blocks_for((long long)n * ho * wo * out_stride, 256, 16);
   if (dtype == ALDI_DTYPE_BF16) {
     if (inverse) s2d_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n, ho, wo, block, c, in_stride, out_stride);

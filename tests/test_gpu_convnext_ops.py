@@ -123,16 +123,18 @@ def test_gelu_and_layerscale(mode):
 def test_space_to_depth_patchify_and_adamw():
     from aldi_b200 import ops
     g = torch.Generator().manual_seed(1)
-    n, h, w, c, b = 2, 12, 20, 24, 2
-    x = torch.randn(n, h, w, 32, generator=g)
-    x[..., c:] = 0
-    out = torch.full((n, h // b, w // b, 128), 7.0, device="cuda")
-    ops.call("aldi_space_to_depth", x.cuda(), out, n, h // b, w // b, b, c, 32, 128, 0, 0)
-    want = x[..., :c].reshape(n, h // b, b, w // b, b, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // b, w // b, b * b * c)
-    assert torch.equal(out.cpu()[..., :b * b * c], want) and float(out[..., b * b * c:].abs().max()) == 0.0
-    back = torch.zeros(n, h, w, 32, device="cuda")
-    ops.call("aldi_space_to_depth", out, back, n, h // b, w // b, b, c, 32, 128, 0, 1)
-    assert torch.equal(back.cpu()[..., :c], x[..., :c])
+    n, h, w, b = 2, 12, 20, 2
+    # c = 24: the 8-channel vector kernel (fp32 and bf16); c = 20: the per-element kernel
+    for c, dt, code in [(24, torch.float32, 0), (24, torch.bfloat16, 1), (20, torch.float32, 0)]:
+        x = torch.randn(n, h, w, 32, generator=g).to(dt)
+        x[..., c:] = 0
+        out = torch.full((n, h // b, w // b, 128), 7.0, device="cuda", dtype=dt)
+        ops.call("aldi_space_to_depth", x.cuda(), out, n, h // b, w // b, b, c, 32, 128, code, 0)
+        want = x[..., :c].reshape(n, h // b, b, w // b, b, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // b, w // b, b * b * c)
+        assert torch.equal(out.cpu()[..., :b * b * c], want) and float(out[..., b * b * c:].float().abs().max()) == 0.0
+        back = torch.zeros(n, h, w, 32, device="cuda", dtype=dt)
+        ops.call("aldi_space_to_depth", out, back, n, h // b, w // b, b, c, 32, 128, code, 1)
+        assert torch.equal(back.cpu()[..., :c], x[..., :c])
     # stem patches: conv2d(k=4, s=4) == patches @ weight(OHWI)
     img = torch.randint(0, 256, (2, 3, 16, 24), generator=g, dtype=torch.uint8)
     sizes = torch.tensor([[16, 24], [13, 21]], dtype=torch.int32)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # ConvNeXt stream kernels: op + model + step tests, per-stage micro-benchmark, ConvNeXt-L step bench with profile
-(timeout 400 python -m pytest tests/test_gpu_convnext_ops.py tests/test_gpu_convnext.py tests/test_gpu_step_parity.py -k "convnext or layernorm or dwconv or gelu" -x -q 2>&1 | tail -15) > gpurun_out/s25_tests.log
-timeout 200 python tools/bench_convnext_ops.py --only dwconv7,dwconv7_wgrad > gpurun_out/s25_ops.jsonl 2> gpurun_out/s25_ops.err
-timeout 150 python tools/bench_convnext.py --size L --ims 2 --steps 3 --profile > gpurun_out/s25_convnext.json 2> gpurun_out/s25_convnext.err
-cat gpurun_out/s25_tests.log gpurun_out/s25_convnext.json; head -12 gpurun_out/s25_convnext.err; tail -3 gpurun_out/s25_ops.err
+(timeout 400 python -m pytest tests/test_gpu_convnext_ops.py tests/test_gpu_convnext.py tests/test_gpu_step_parity.py -k "convnext or layernorm or dwconv or gelu" -x -q 2>&1 | tail -15) > gpurun_out/s26_tests.log
+
+timeout 150 python tools/bench_convnext.py --size L --ims 2 --steps 3 --profile > gpurun_out/s26_convnext.json 2> gpurun_out/s26_convnext.err
+cat gpurun_out/s26_tests.log gpurun_out/s26_convnext.json; head -12 gpurun_out/s26_convnext.err
