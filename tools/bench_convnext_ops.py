@@ -74,6 +74,7 @@ def main():
             "layernorm_forward": (lambda: ops.call("aldi_layernorm_forward", x, gamma, beta, 1e-6, rows, c, c, 1, y, stats), 2 * t, 0),
             "layernorm_backward": (lambda: ops.call("aldi_layernorm_backward", x, gamma, stats, dy, rows, c, c, 1, y, 0, dgam, dbet),
                                    3 * t, 0),
+            "layerscale_forward": (lambda: ops.call("aldi_layerscale_forward", x, dy, gamma, None, rows, h * w, c, c, 1, y), 3 * t, 0),
             "gelu": (lambda: ops.call("aldi_gelu", hid, None, act, hid.numel(), 1), 8 * t, 0),
             "gelu_backward": (lambda: ops.call("aldi_gelu", hid, da, act, hid.numel(), 1), 12 * t, 0),
         }
