@@ -656,12 +656,27 @@ class DefaultAnchorGenerator(nn.Module):
 
 
 class StandardRPNHead(nn.Module):
-    def __init__(self, in_channels=256, num_anchors=3, box_dim=4):
+    def __init__(self, in_channels=256, num_anchors=3, box_dim=4, conv_dims=(-1,)):
+        """conv_dims: MODEL.RPN.CONV_DIMS (-1 = the input width).  One entry: the 3x3 conv is `conv`; several (ViTDet's
+        [-1, -1], configs/Base-RCNN-VitDetB.yaml:13-14): `conv` is a Sequential of `conv0`, `conv1`, ... each + ReLU."""
         super().__init__()
-        self.conv = Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1, activation=nn.ReLU())
-        self.objectness_logits = nn.Conv2d(in_channels, num_anchors, kernel_size=1, stride=1)
-        self.anchor_deltas = nn.Conv2d(in_channels, num_anchors * box_dim, kernel_size=1, stride=1)
-        for layer in [self.conv, self.objectness_logits, self.anchor_deltas]:
+        cur = in_channels
+        if len(conv_dims) == 1:
+            out = cur if conv_dims[0] == -1 else conv_dims[0]
+            self.conv = Conv2d(cur, out, kernel_size=3, stride=1, padding=1, activation=nn.ReLU())
+            convs, cur = [self.conv], out
+        else:
+            self.conv = nn.Sequential()
+            convs = []
+            for k, d in enumerate(conv_dims):
+                out = cur if d == -1 else d
+                c = Conv2d(cur, out, kernel_size=3, stride=1, padding=1, activation=nn.ReLU())
+                self.conv.add_module("conv%d" % k, c)
+                convs.append(c)
+                cur = out
+        self.objectness_logits = nn.Conv2d(cur, num_anchors, kernel_size=1, stride=1)
+        self.anchor_deltas = nn.Conv2d(cur, num_anchors * box_dim, kernel_size=1, stride=1)
+        for layer in convs + [self.objectness_logits, self.anchor_deltas]:
             nn.init.normal_(layer.weight, std=0.01)
             nn.init.constant_(layer.bias, 0)
 
@@ -719,10 +734,10 @@ def find_top_rpn_proposals(proposals, pred_objectness_logits, image_sizes, nms_t
 class RPN(nn.Module):
     def __init__(self, in_features=("p2", "p3", "p4", "p5", "p6"), batch_size_per_image=256, positive_fraction=0.5,
                  pre_nms_topk=(2000, 1000), post_nms_topk=(1000, 1000), nms_thresh=0.7, min_box_size=0.0,
-                 iou_thresholds=(0.3, 0.7), iou_labels=(0, -1, 1), smooth_l1_beta=0.0):
+                 iou_thresholds=(0.3, 0.7), iou_labels=(0, -1, 1), smooth_l1_beta=0.0, conv_dims=(-1,)):
         super().__init__()
         self.in_features = in_features
-        self.rpn_head = StandardRPNHead()
+        self.rpn_head = StandardRPNHead(conv_dims=conv_dims)
         self.anchor_generator = DefaultAnchorGenerator()
         self.anchor_matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches=True)
         self.box2box_transform = Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0))
@@ -864,10 +879,34 @@ class ROIPooler(nn.Module):
         return output
 
 
-class FastRCNNConvFCHead(nn.Sequential):
-    def __init__(self, in_channels=256, size=7, fc_dims=(1024, 1024)):
+class LayerNorm2d(nn.Module):
+    """detectron2.layers.batch_norm.LayerNorm (`get_norm("LN", c)`): over the channel axis of NCHW, eps 1e-6."""
+
+    def __init__(self, c, eps=1e-6):
         super().__init__()
-        dim = in_channels * size * size
+        self.weight, self.bias, self.eps = nn.Parameter(torch.ones(c)), nn.Parameter(torch.zeros(c)), eps
+
+    def forward(self, x):
+        u = x.mean(1, keepdim=True)
+        s = (x - u).pow(2).mean(1, keepdim=True)
+        x = (x - u) / torch.sqrt(s + self.eps)
+        return self.weight[:, None, None] * x + self.bias[:, None, None]
+
+
+class FastRCNNConvFCHead(nn.Sequential):
+    def __init__(self, in_channels=256, size=7, fc_dims=(1024, 1024), conv_dims=(), conv_norm=""):
+        """conv_dims / conv_norm: MODEL.ROI_BOX_HEAD.NUM_CONV x CONV_DIM / NORM -- ViTDet uses four 3x3 convs of 256 with
+        "LN" before one FC (configs/Base-RCNN-VitDetB.yaml:7-12); conv bias is off when a norm follows."""
+        super().__init__()
+        cur = in_channels
+        for k, d in enumerate(conv_dims):
+            assert conv_norm in ("", "LN"), conv_norm
+            conv = Conv2d(cur, d, kernel_size=3, padding=1, bias=not conv_norm,
+                          norm=LayerNorm2d(d) if conv_norm == "LN" else None, activation=nn.ReLU())
+            self.add_module("conv{}".format(k + 1), conv)
+            c2_msra_fill(conv)
+            cur = d
+        dim = cur * size * size
         self.add_module("flatten", nn.Flatten())
         for k, fc_dim in enumerate(fc_dims):
             fc = nn.Linear(dim, fc_dim)
@@ -1018,7 +1057,8 @@ def add_ground_truth_to_proposals(gt, proposals):
 
 class StandardROIHeads(nn.Module):
     def __init__(self, num_classes=8, batch_size_per_image=512, positive_fraction=0.25, iou_thresholds=(0.5,),
-                 iou_labels=(0, 1), proposal_append_gt=True, box_in_features=("p2", "p3", "p4", "p5")):
+                 iou_labels=(0, 1), proposal_append_gt=True, box_in_features=("p2", "p3", "p4", "p5"),
+                 box_fc_dims=(1024, 1024), box_conv_dims=(), box_conv_norm=""):
         super().__init__()
         self.num_classes = num_classes
         self.batch_size_per_image = batch_size_per_image
@@ -1027,8 +1067,8 @@ class StandardROIHeads(nn.Module):
         self.proposal_append_gt = proposal_append_gt
         self.box_in_features = box_in_features
         self.box_pooler = ROIPooler()
-        self.box_head = FastRCNNConvFCHead()
-        self.box_predictor = FastRCNNOutputLayers(num_classes=num_classes)
+        self.box_head = FastRCNNConvFCHead(fc_dims=box_fc_dims, conv_dims=box_conv_dims, conv_norm=box_conv_norm)
+        self.box_predictor = FastRCNNOutputLayers(input_size=box_fc_dims[-1], num_classes=num_classes)
 
     def _sample_proposals(self, matched_idxs, matched_labels, gt_classes):
         has_gt = gt_classes.numel() > 0
@@ -1099,18 +1139,24 @@ class StandardROIHeads(nn.Module):
 # ---------------------------------------------------------------------------------------------------
 class GeneralizedRCNN(nn.Module):
     def __init__(self, num_classes=8, pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0), freeze_at=2,
-                 bottom_up=None, fpn_in_features=None, anchor_sizes=None, **kwargs):
+                 bottom_up=None, fpn_in_features=None, anchor_sizes=None, backbone=None, rpn_conv_dims=(-1,),
+                 box_fc_dims=(1024, 1024), box_conv_dims=(), box_conv_norm="", **kwargs):
         super().__init__()
+        # backbone: a complete pyramid module returning {"p2".."p6"} (oracle/vit_ref.SimpleFeaturePyramid for
+        # build_vitdet_*_backbone, aldi/backbone.py:37-64), used as is instead of FPN(bottom_up)
         # bottom_up: any module exposing _out_feature_strides / _out_feature_channels (e.g. oracle/convnext_ref.ConvNeXt
         # with fpn_in_features (0, 1, 2, 3): build_convnext_fpn_backbone, aldi/backbone.py:373-392)
-        if bottom_up is None:
+        if backbone is not None:
+            self.backbone = backbone
+        elif bottom_up is None:
             self.backbone = FPN(ResNet(freeze_at=freeze_at))
         else:
             self.backbone = FPN(bottom_up, in_features=fpn_in_features)
-        self.proposal_generator = RPN()
+        self.proposal_generator = RPN(conv_dims=rpn_conv_dims)
         if anchor_sizes is not None:
             self.proposal_generator.anchor_generator = DefaultAnchorGenerator(sizes=anchor_sizes)
-        self.roi_heads = StandardROIHeads(num_classes=num_classes)
+        self.roi_heads = StandardROIHeads(num_classes=num_classes, box_fc_dims=box_fc_dims, box_conv_dims=box_conv_dims,
+                                          box_conv_norm=box_conv_norm)
         self.register_buffer("pixel_mean", torch.tensor(pixel_mean).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor(pixel_std).view(-1, 1, 1), False)
 

@@ -141,3 +141,39 @@ def test_builders_and_lr_decay_table():
     assert abs(f("backbone.net.blocks.0.attn.qkv.weight") - 0.7 ** 12) < 1e-12
     assert abs(f("backbone.net.blocks.11.mlp.fc2.bias") - 0.7) < 1e-12
     assert f("backbone.simfp_2.0.weight") == 1.0 and f("roi_heads.box_head.fc1.weight") == 1.0
+
+
+def test_vitdet_detector_heads_and_source_step():
+    """Base-RCNN-VitDetB.yaml on the oracle: the simple feature pyramid AS the backbone (no FPN), RPN.CONV_DIMS [-1, -1],
+    ROI_BOX_HEAD 4 x conv(256, LN) + one FC -- Detectron2's parameter names, one training-mode step with finite gradients."""
+    import random
+
+    from oracle import d2_rcnn as d2
+    torch.manual_seed(3)
+    random.seed(3)
+    net = V.ViT(img_size=64, patch_size=16, embed_dim=32, depth=2, num_heads=2, drop_path_rate=0.0, window_size=2,
+                window_block_indexes=(0,), pretrain_img_size=32)
+    model = d2.GeneralizedRCNN(num_classes=3, pixel_mean=(123.675, 116.28, 103.53), pixel_std=(58.395, 57.12, 57.375),
+                               backbone=V.SimpleFeaturePyramid(net, out_channels=256), rpn_conv_dims=(-1, -1),
+                               box_fc_dims=(64,), box_conv_dims=(256, 256, 256, 256), box_conv_norm="LN")
+    keys = set(model.state_dict())
+    assert {"backbone.net.blocks.1.attn.rel_pos_w", "backbone.simfp_2.4.norm.weight",
+            "proposal_generator.rpn_head.conv.conv0.weight", "proposal_generator.rpn_head.conv.conv1.bias",
+            "roi_heads.box_head.conv1.weight", "roi_heads.box_head.conv4.norm.bias", "roi_heads.box_head.fc1.weight",
+            "roi_heads.box_predictor.cls_score.weight"} <= keys
+    assert "roi_heads.box_head.conv1.bias" not in keys and "roi_heads.box_head.fc2.weight" not in keys
+    assert model.state_dict()["roi_heads.box_head.fc1.weight"].shape == (64, 256 * 7 * 7)
+    assert model.backbone.size_divisibility == 32
+    inst = d2.Instances((64, 96))
+    inst.gt_boxes = d2.Boxes(torch.tensor([[8.0, 8.0, 40.0, 48.0], [50.0, 10.0, 90.0, 60.0]]))
+    inst.gt_classes = torch.tensor([0, 2])
+    batch = [{"image": torch.randint(0, 256, (3, 64, 96)).float(), "instances": inst}]
+    model.train()
+    with d2.EventStorage():
+        losses = model(batch)
+    assert set(losses) == {"loss_cls", "loss_box_reg", "loss_rpn_cls", "loss_rpn_loc"}
+    sum(losses.values()).backward()
+    for n, p in model.named_parameters():
+        assert p.grad is None or torch.isfinite(p.grad).all(), n
+    assert float(model.roi_heads.box_head.conv2.norm.weight.grad.abs().sum()) > 0
+    assert float(model.backbone.net.blocks[0].attn.qkv.weight.grad.abs().sum()) > 0
