@@ -1046,7 +1046,8 @@ extern "C" int aldi_layernorm_forward(const void* x, const float* gamma, const f
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALDI_CHECK_ARG(x && gamma && beta && y && rows > 0 && c > 0 && stride >= c, "aldi_layernorm_forward: bad args");
   static const bool legacy = getenv("ALDI_LN_LEGACY") != nullptr;
-  if (!legacy && c % 8 == 0 && stride % 8 == 0 && c <= 2048) {
+  const bool aligned16 = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  if (!legacy && aligned16 && c % 8 == 0 && stride % 8 == 0 && c <= 2048) {
     const int nvec = c / 8;
 #define LN_FWD(TT, VPL, RPW)                                                                                          \
   ln_fwd_vec_kernel<TT, VPL, RPW><<<blocks_for(rows, 8 * RPW, 8), 256, 0, stream>>>((const TT*)x, gamma, beta, eps, rows, c, \
@@ -1088,7 +1089,8 @@ extern "C" int aldi_layernorm_backward(const void* x, const float* gamma, const 
   const int grid = blocks_for(rows, 8 * 16, 4);
   const size_t smem = (size_t)2 * c * sizeof(float);
   static const bool legacy = getenv("ALDI_LN_LEGACY") != nullptr;
-  if (!legacy && c % 8 == 0 && stride % 8 == 0) {
+  const bool aligned16 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma) & 15) == 0;
+  if (!legacy && aligned16 && c % 8 == 0 && stride % 8 == 0) {
     const int nvec = c / 8;
     // enough CTAs to fill the GPU even for a few thousand rows, few enough that the per-CTA d-gamma / d-beta atomics
     // (2 c each) stay cheap: >= 4 rows per warp, at most two CTAs per SM
