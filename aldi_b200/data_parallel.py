@@ -15,7 +15,6 @@ known point of `Detector.backward`; `GradReducer.ready(tag)` is called there.
 """
 from collections import OrderedDict
 
-import torch
 import torch.distributed as dist
 
 # backward completion order of the buckets (Detector.backward calls ready() with these tags)

@@ -16,7 +16,6 @@ Schedule differences that do not change results: the teacher trunk + RPN head ru
 micro-batches accumulate into one flat buffer that is all-reduced once per step (the reference all-reduces
 per micro-batch backward; averaging is linear).
 """
-import math
 import os
 import random
 

@@ -18,7 +18,7 @@ Module / parameter names follow Detectron2 so that state_dict keys match release
 aldi/ema.py:19-50 and aldi/checkpoint.py:8-31 iterate over.
 """
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn.functional as F

@@ -1,7 +1,6 @@
 """Shared helpers for the GPU parity tests: run the CPU oracle and the B200 step on identical inputs."""
 import random
 
-import numpy as np
 import torch
 
 from aldi_b200 import arch, sampling, synth_data

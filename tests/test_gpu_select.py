@@ -1,6 +1,5 @@
 """Selection kernels against the oracle's Detectron2 primitives on IDENTICAL inputs: index sets must be exact."""
 import ctypes
-import math
 
 import pytest
 import torch
