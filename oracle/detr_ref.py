@@ -1,6 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY — CPU restatement of the Deformable-DETR path downstream of the ResNet trunk (BASELINE
-configs[3]): input projections + fourth level, sine position embedding, deformable encoder /
-decoder, heads, Hungarian matching, set criterion, inference top-k.
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the Deformable-DETR path (BASELINE configs[3], SURVEY §8 f4 /
+Appendix B): torchvision-style ResNet-50 trunk with FrozenBN + padding masks + sine position embedding, input
+projections + fourth level, deformable encoder / decoder, heads, Hungarian matching, set criterion, inference top-k.
 
 Only tests/ may import this module.  Reference files (under
 /root/reference/aldi/detr/libs/DeformableDETRDetectron2/, "DETR/" below) each function follows are cited inline.
@@ -8,7 +8,8 @@ PINNED: tests/golden/make_detr_golden.py executes the reference's own `Deformabl
 `HungarianMatcher` and `SetCriterion` classes in float64 (the CUDA op routed to the reference's pure-PyTorch core, the
 torchvision trunk replaced by fixed feature maps) and stores outputs of every decoder layer, the assignment of every
 layer, all loss entries, the weighted total, a norm + projection of every parameter gradient and the inference top-k;
-tests/test_detr_oracle.py replays them against this file.
+tests/test_detr_oracle.py replays them against this file.  The trunk has its own golden from the reference's
+`Backbone` + `Joiner` classes (`detr_trunk_golden.pt`; weights re-drawn from a seed on both sides).
 
 Functional on purpose: the model is a plain dict of tensors under the reference's state-dict keys
 (`transformer.encoder.layers.0.self_attn.sampling_offsets.weight`, `input_proj.3.0.weight`, `class_embed.0.bias`, ...),
@@ -61,6 +62,74 @@ def _lin(sd, key, x):
 
 def _ln(sd, key, x):
     return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], 1e-5)
+
+
+# --------------------------------------------------------------------------------------------------------------
+RESNET50_BLOCKS = (3, 4, 6, 3)
+
+
+def trunk_shapes(prefix="0.body."):
+    """Key -> shape table of the reference trunk's state dict: torchvision ResNet-50 behind IntermediateLayerGetter (no
+    avgpool / fc), every norm a FrozenBatchNorm2d with four buffers (DETR/deformable_detr/models/backbone.py:25-109)."""
+    shapes = {}
+
+    def bn(k, c):
+        for f in ("weight", "bias", "running_mean", "running_var"):
+            shapes[prefix + k + "." + f] = (c,)
+
+    shapes[prefix + "conv1.weight"] = (64, 3, 7, 7)
+    bn("bn1", 64)
+    cin = 64
+    for li, nblk in enumerate(RESNET50_BLOCKS):
+        mid = 64 * 2 ** li
+        for b in range(nblk):
+            k = "layer%d.%d." % (li + 1, b)
+            shapes[prefix + k + "conv1.weight"] = (mid, cin, 1, 1)
+            bn(k + "bn1", mid)
+            shapes[prefix + k + "conv2.weight"] = (mid, mid, 3, 3)
+            bn(k + "bn2", mid)
+            shapes[prefix + k + "conv3.weight"] = (mid * 4, mid, 1, 1)
+            bn(k + "bn3", mid * 4)
+            if b == 0:
+                shapes[prefix + k + "downsample.0.weight"] = (mid * 4, cin, 1, 1)
+                bn(k + "downsample.1", mid * 4)
+            cin = mid * 4
+    return shapes
+
+
+def trunk_trainable(prefix="0.body."):
+    """BackboneBase.__init__ (:72-75): only parameters of layer2-4 train; FrozenBN has buffers only."""
+    return sorted(k for k in trunk_shapes(prefix) if k.endswith("weight") and "bn" not in k and "downsample.1" not in k
+                  and any(l in k for l in ("layer2", "layer3", "layer4")))
+
+
+def trunk(sd, x, canvas_mask, prefix="0.body.", eps=1e-5):
+    """torchvision-style ResNet-50 (stride on the 3x3, unlike Detectron2's STRIDE_IN_1X1), FrozenBN as x * scale + bias
+    with scale = w * rsqrt(var + eps) (:54-64); returns layer2-4 outputs (strides 8 / 16 / 32), their nearest-resized
+    padding masks (:91) and sine position embeddings (Joiner.forward, :112-129)."""
+    def fbn(k, t):
+        scale = sd[prefix + k + ".weight"] * (sd[prefix + k + ".running_var"] + eps).rsqrt()
+        bias = sd[prefix + k + ".bias"] - sd[prefix + k + ".running_mean"] * scale
+        return t * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+
+    t = F.relu(fbn("bn1", F.conv2d(x, sd[prefix + "conv1.weight"], stride=2, padding=3)))
+    t = F.max_pool2d(t, kernel_size=3, stride=2, padding=1)
+    outs = []
+    for li, nblk in enumerate(RESNET50_BLOCKS):
+        for b in range(nblk):
+            k = "layer%d.%d." % (li + 1, b)
+            stride = 2 if (b == 0 and li > 0) else 1
+            y = F.relu(fbn(k + "bn1", F.conv2d(t, sd[prefix + k + "conv1.weight"])))
+            y = F.relu(fbn(k + "bn2", F.conv2d(y, sd[prefix + k + "conv2.weight"], stride=stride, padding=1)))
+            y = fbn(k + "bn3", F.conv2d(y, sd[prefix + k + "conv3.weight"]))
+            if b == 0:
+                t = fbn(k + "downsample.1", F.conv2d(t, sd[prefix + k + "downsample.0.weight"], stride=stride))
+            t = F.relu(y + t)
+        if li > 0:
+            outs.append(t)
+    masks = [level_mask(canvas_mask, o.shape[-2:]) for o in outs]
+    pos = [sine_position_embedding(m, 128).to(o.dtype) for m, o in zip(masks, outs)]
+    return outs, masks, pos
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -18,7 +18,12 @@ Weights: the reference's own initialisation followed by small noise on the tenso
 offsets' weight, attention weights, the last bbox layer), so no term of the forward or backward is identically zero.
 Dropout 0 (it is a config value; with 0.1 the draws would be the only difference).
 
-    python tests/golden/make_detr_golden.py      ->  tests/golden/detr_golden.pt
+The trunk gets its own small golden (`detr_trunk_golden.pt`): the reference's `Backbone("resnet50", ...)` + `Joiner`
+(models/backbone.py:25-129: torchvision ResNet-50 with the reference's FrozenBatchNorm2d, layer2-4 outputs, interpolated
+masks, sine embeddings) on a 2 x 3 x 64 x 96 batch.  Only `pretrained=` is forced off (no network); the 23.5 M weights are
+not stored but re-drawn from a seed by `trunk_state_dict()`, which the test shares.
+
+    python tests/golden/make_detr_golden.py      ->  tests/golden/detr_golden.pt, tests/golden/detr_trunk_golden.pt
 """
 import os
 import sys
@@ -52,6 +57,33 @@ def detr_inputs(cfg=CFG, dtype=torch.float64):
         targets.append({"labels": torch.randint(0, cfg["classes"], (n,), generator=g),
                         "boxes": torch.cat([cxcy, wh], 1).to(dtype)})
     return feats, mask, targets
+
+
+def trunk_state_dict(shapes, dtype=torch.float64):
+    """Seeded weights for every key of the reference trunk's state dict (sorted key order): convolutions ~ He-scaled
+    normal, FrozenBN weight / var in [0.5, 1.5], bias / mean small."""
+    g = torch.Generator().manual_seed(17)
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        if k.endswith("running_var") or (k.endswith("weight") and len(shp) == 1):
+            v = 0.5 + torch.rand(shp, generator=g, dtype=torch.float64)
+        elif len(shp) == 1:
+            v = 0.1 * torch.randn(shp, generator=g, dtype=torch.float64)
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            v = torch.randn(shp, generator=g, dtype=torch.float64) * (2.0 / fan_in) ** 0.5
+        sd[k] = v.to(dtype)
+    return sd
+
+
+def trunk_inputs(dtype=torch.float64):
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(2, 3, 64, 96, generator=g, dtype=torch.float64).to(dtype)
+    mask = torch.ones(2, 64, 96, dtype=torch.bool)
+    mask[0, :, :] = False
+    mask[1, :40, :72] = False
+    return x, mask
 
 
 def load_reference():
@@ -160,5 +192,36 @@ def main():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(sd), "tensors;", {k: float(v) for k, v in golden["losses"].items()})
 
 
+def main_trunk():
+    import torchvision
+    load_reference()
+    import deformable_detr.models.backbone as bb
+    import deformable_detr.models.position_encoding as pe
+    import deformable_detr.util.misc as misc
+    real = torchvision.models.resnet50
+
+    def no_download(*a, **kw):
+        kw["pretrained"] = False
+        return real(*a, **kw)
+
+    torchvision.models.resnet50 = no_download
+    try:
+        backbone = bb.Backbone("resnet50", True, True, False)
+    finally:
+        torchvision.models.resnet50 = real
+    joiner = bb.Joiner(backbone, pe.PositionEmbeddingSine(128, normalize=True)).double().eval()
+    shapes = {k: tuple(v.shape) for k, v in joiner.state_dict().items()}
+    joiner.load_state_dict(trunk_state_dict(shapes), strict=True)
+    x, mask = trunk_inputs()
+    with torch.no_grad():
+        feats, pos = joiner(misc.NestedTensor(x, mask))
+    golden = {"shapes": shapes, "features": [f.tensors for f in feats], "masks": [f.mask for f in feats], "pos": pos,
+              "trainable": sorted(n for n, p in joiner.named_parameters() if p.requires_grad)}
+    path = os.path.join(HERE, "detr_trunk_golden.pt")
+    torch.save(golden, path)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(shapes), "tensors;", [tuple(f.shape) for f in golden["features"]])
+
+
 if __name__ == "__main__":
     main()
+    main_trunk()

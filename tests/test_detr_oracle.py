@@ -9,7 +9,7 @@ from oracle import detr_ref as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from make_detr_golden import detr_inputs  # noqa: E402
+from make_detr_golden import detr_inputs, trunk_inputs, trunk_state_dict  # noqa: E402
 
 
 def _load():
@@ -78,3 +78,18 @@ def test_position_embedding_ignores_padding_and_empty_targets():
     losses, ind = R.criterion(out, empty, g["cfg"])
     assert all(len(i) == 0 for lay in ind for i, _ in lay)
     assert float(losses["loss_bbox"]) == 0.0 and float(losses["loss_giou_1"]) == 0.0 and float(losses["loss_ce"]) > 0
+
+
+def test_trunk_matches_reference_backbone_and_joiner():
+    g = torch.load(os.path.join(HERE, "golden", "detr_trunk_golden.pt"), weights_only=False)
+    assert R.trunk_shapes() == g["shapes"]                      # every key and shape of the reference trunk's state dict
+    assert R.trunk_trainable() == g["trainable"]                # layer2-4 convolutions only
+    sd = trunk_state_dict(R.trunk_shapes())
+    x, mask = trunk_inputs()
+    with torch.no_grad():
+        feats, masks, pos = R.trunk(sd, x, mask)
+    assert [tuple(f.shape) for f in feats] == [(2, 512, 8, 12), (2, 1024, 4, 6), (2, 2048, 2, 3)]
+    for f, m, p, gf, gm, gpos in zip(feats, masks, pos, g["features"], g["masks"], g["pos"]):
+        assert torch.allclose(f, gf, rtol=1e-9, atol=1e-9 * float(gf.abs().max()))
+        assert torch.equal(m, gm) and torch.allclose(p, gpos, atol=1e-12)
+    assert bool(masks[0][1, 5:, :].all()) and not bool(masks[0][1, :5, :9].any())      # 40 x 72 valid pixels of 64 x 96
