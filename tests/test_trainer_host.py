@@ -1,4 +1,6 @@
 """Host-side mirror of the reference's cfg / dataloader / trainer surface (no GPU needed except where marked)."""
+import os
+
 import pytest
 import torch
 
@@ -132,3 +134,44 @@ def test_trainer_runs_aldi_best_config(tmp_path):
     assert set(sd) == {"model", "ema", "iteration"}
     assert "backbone.bottom_up.res2.0.conv1.weight" in sd["model"] and "roi_heads.box_predictor.cls_score.bias" in sd["ema"]
     assert trainer.step_impl.graph_replays == 0 or trainer.step_impl.cfg.cuda_graph
+
+
+REF_CONFIGS = "/root/reference/configs"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIGS), reason="the reference tree exists in the authoring container only")
+def test_every_shipped_yaml_loads_or_fails_as_documented():
+    """The reference's own test strategy is 'every config starts' (tests/test_all_configs_cityscapes.sh).  Here:
+    every shipped YAML goes through the cfg mirror (`_BASE_` chains, `add_aldi_config` keys); R50-FPN and ConvNeXt-FPN
+    configs map onto a StepConfig; ViTDet configs load and are refused with NotImplementedError (a18, not built);
+    Deformable-DETR / YOLO YAMLs need config keys that the reference's tools/train_net.py itself only registers when the
+    optional sub-library imports (yolo, :37-41) or not at all (detr: commented out, :47-50) -> 'Non-existent config key'."""
+    import glob
+    seen = {"ok": 0, "vit": 0, "detr_yolo": 0, "missing_base": 0}
+    for path in sorted(glob.glob(os.path.join(REF_CONFIGS, "**", "*.yaml"), recursive=True)):
+        name = os.path.relpath(path, REF_CONFIGS)
+        cfg = get_cfg()
+        add_aldi_config(cfg)
+        try:
+            cfg.merge_from_file(path)
+        except KeyError as e:
+            assert ("DETR" in name or "Yolo" in name) and ("DEFORMABLE_DETR" in str(e) or "MODEL.YAML" in str(e)), (name, e)
+            seen["detr_yolo"] += 1
+            continue
+        except FileNotFoundError:
+            assert name == os.path.join("sim10k", "ALDI-Best-Sim10k.yaml"), name     # its _BASE_ is not in the reference tree
+            seen["missing_base"] += 1
+            continue
+        if "VitDet" in name or "ViT" in name:
+            with pytest.raises(NotImplementedError):
+                step_config_from_cfg(cfg)
+            seen["vit"] += 1
+            continue
+        sc = step_config_from_cfg(cfg)
+        assert sc.backbone in ("resnet50", "convnext") and sc.ims_per_gpu >= 1, name
+        if "ConvNeXt" in name:
+            assert sc.backbone == "convnext" and sc.optimizer == "ADAMW" and sc.convnext_dims == (192, 384, 768, 1536)
+        if name.startswith("cityscapes") and "ALDI-Best-Cityscapes" in name:
+            assert sc.distill_enabled and sc.do_cls_dst and sc.do_obj_dst and not sc.do_hard_cls and sc.num_classes == 8
+        seen["ok"] += 1
+    assert seen["ok"] >= 15 and seen["vit"] >= 10 and seen["detr_yolo"] >= 9, seen
