@@ -177,3 +177,50 @@ def test_vitdet_detector_heads_and_source_step():
         assert p.grad is None or torch.isfinite(p.grad).all(), n
     assert float(model.roi_heads.box_head.conv2.norm.weight.grad.abs().sum()) > 0
     assert float(model.backbone.net.blocks[0].attn.qkv.weight.grad.abs().sum()) > 0
+
+
+def test_aldi_distillation_step_on_the_vitdet_oracle():
+    """The ALDI layer (oracle/aldi_ref.py: pseudo-labeler, hooks, soft losses, aldi/distill.py:115-278) over the ViTDet
+    detector variant: eval-mode pseudo-label pass without DropPath, training-mode student / teacher passes with their
+    own DropPath draws, the eight distillation loss keys, gradients into the ViT blocks and relative-position tables."""
+    import copy
+    import random
+
+    from oracle import aldi_ref, d2_rcnn as d2
+    torch.manual_seed(4)
+    random.seed(4)
+
+    def make():
+        net = V.ViT(img_size=64, patch_size=16, embed_dim=32, depth=2, num_heads=2, drop_path_rate=0.2, window_size=2,
+                    window_block_indexes=(0,), pretrain_img_size=32)
+        m = aldi_ref.ALDI(num_classes=3, pixel_mean=(123.675, 116.28, 103.53), pixel_std=(58.395, 57.12, 57.375),
+                          backbone=V.SimpleFeaturePyramid(net, out_channels=256), rpn_conv_dims=(-1, -1), box_fc_dims=(64,),
+                          box_conv_dims=(256, 256), box_conv_norm="LN")
+        return m, net
+
+    student, net_s = make()
+    teacher, net_t = make()
+    teacher.load_state_dict(copy.deepcopy(student.state_dict()))
+    with torch.no_grad():
+        for n, p in list(student.named_parameters()) + list(teacher.named_parameters()):
+            if "rel_pos" in n:
+                p.normal_(std=0.02)
+        teacher.roi_heads.box_predictor.cls_score.bias[0] += 6.0           # a confident teacher: pseudo labels are non-empty
+    student.train()
+    teacher.train()
+    keep = lambda: [torch.tensor([1 / 0.8, 0.0]), torch.tensor([1 / 0.8, 1 / 0.8])]       # noqa: E731  block 1: attn, mlp
+    net_s.keep_queue, net_t.keep_queue = keep(), keep()
+    dist = aldi_ref.ALDIDistiller(teacher, student, do_hard_cls=False, do_hard_obj=False, do_hard_rpn_reg=False,
+                                  do_hard_roi_reg=False, do_cls_dst=True, do_obj_dst=True, do_rpn_reg_dst=True,
+                                  do_roih_reg_dst=True, pseudo_label_threshold=0.5)
+    img = lambda: {"image": torch.randint(0, 256, (3, 64, 96)).float(), "height": 64, "width": 96}   # noqa: E731
+    weak, strong = [img(), img()], [img(), img()]
+    with d2.EventStorage():
+        losses = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, None, weak, strong), 2, False, lambda l: l.backward())
+    assert not net_s.keep_queue and not net_t.keep_queue              # one training-mode pass each; the eval pass draws none
+    assert {"loss_cls_distill", "loss_box_reg_distill", "loss_rpn_cls_distill", "loss_rpn_loc_distill", "loss_obj_bce_distill",
+            "loss_rpn_l1_distill", "loss_cls_ce_distill", "loss_roih_l1_distill"} <= set(losses)
+    assert all(torch.isfinite(torch.as_tensor(v)) for v in losses.values())
+    assert sum(len(d["instances"]) for d in weak) > 0                  # pseudo labels were attached to the weak dicts
+    assert float(net_s.blocks[1].attn.rel_pos_h.grad.abs().sum()) > 0 and float(net_s.patch_embed.proj.weight.grad.abs().sum()) > 0
+    assert all(p.grad is None for p in teacher.parameters())
