@@ -428,6 +428,8 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "parallelism": "dp%d" % world,
                            "global_batch": imgs_per_step,
                            "l2": "inputs larger than L2: 75 MB of uint8 views + >4 GB of activations per micro-batch vs 126 MB L2",
+                           # also report image VIEWS / s (each target image is consumed twice, weak + strong)
+                           "image_views_per_s": value * 1.5,
                            "algorithmic_tflop_per_step_per_gpu": 24.0, "base_lr": cfg.base_lr,
                            "cuda_graph": bool(cfg.cuda_graph), "graph_replays": step.graph_replays,
                            "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)},
