@@ -106,6 +106,18 @@ def to_device(batches, device):
 
 
 # ------------------------------------------------------------------------------------------------------
+def cpu_model_name():
+    """Host CPU model for the cpu_baseline record (SURVEY §8d asks for it next to the thread count)."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_step_factory(threads):
     """The reference path restated on CPU (oracle port): one (source + target) image pair per step."""
     import torch
@@ -163,7 +175,8 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "Detectron2 is not installable offline; the CPU arm is the oracle "
                                                      "restatement of the reference path (SURVEY.md §8c)"},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+                             "cpu_model": cpu_model_name(), "os_cpu_count": os.cpu_count()},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -418,6 +431,7 @@ def run_ours(args):
         n = sum(cstep() for _ in range(k))
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": n / dt, "unit": "images/s", "cores": threads, "kind": "port",
+                        "cpu_model": cpu_model_name(), "os_cpu_count": os.cpu_count(),
                         "sample": "oracle port of the reference step (oracle/aldi_ref.py, torch CPU fp32, %d threads), ONE "
                                   "(source+target) 1024x2048 pair per step: 1 warm-up step (%.1f s) + %d timed step(s) (%.1f s)"
                                   % (threads, t_warm, k, dt)}
