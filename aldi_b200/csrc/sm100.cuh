@@ -54,7 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(addr, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(addr, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > 40000000000LL) {  // ~20 s at 2 GHz: a lost TMA transaction, never a slow neighbour
       printf("aldi_b200: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }

@@ -515,16 +515,21 @@ class B200TrainStep:
         gc.collect()
         cs = self._capture_stream
         cs.wait_stream(torch.cuda.current_stream())
+        # thread-local capture mode: under torch.distributed the NCCL watchdog thread polls its work events with
+        # cudaEventQuery, which the default ("global") mode forbids in EVERY thread while a capture is open -- the
+        # watchdog then dies with "operation not permitted when stream is capturing" and takes the process down
+        # (SIGABRT); the calls of the capturing thread itself are still checked
+        mode = os.environ.get("ALDI_CAPTURE_MODE", "thread_local")
         with torch.cuda.stream(cs):
             seg = torch.cuda.CUDAGraph()
-            seg.capture_begin(pool=self._graph_pool)
+            seg.capture_begin(pool=self._graph_pool, capture_error_mode=mode)
             state = {"seg": seg}
 
             def cut(tag):
                 state["seg"].capture_end()
                 chain.extend([state["seg"], tag])
                 state["seg"] = torch.cuda.CUDAGraph()
-                state["seg"].capture_begin(pool=self._graph_pool)
+                state["seg"].capture_begin(pool=self._graph_pool, capture_error_mode=mode)
 
             self._capture_hook = cut if split else None
             try:

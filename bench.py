@@ -212,11 +212,21 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    diag_dir = os.environ.get("ALDI_BENCH_DIAG_DIR")
+    if diag_dir:
+        # per-rank stderr (Python tracebacks, faulthandler dumps, the C++ terminate message of a dying NCCL watchdog,
+        # device-side printf) into one file per rank: torchrun's exit table alone does not say WHY a rank died
+        os.makedirs(diag_dir, exist_ok=True)
+        fd = os.open(os.path.join(diag_dir, "rank%d.err" % rank), os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        os.dup2(fd, 2)
+    import faulthandler
+    faulthandler.enable(all_threads=True)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     pg = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
         pg = dist.group.WORLD
     lib.load()
     peaks, peak_src = load_peaks()
@@ -227,7 +237,7 @@ def run_ours(args):
                      cuda_graph=not args.no_graph)
     step = B200TrainStep(cfg, arch.synthetic_state_dict(0), device=device, process_group=pg)
     step.debug = None
-    host = make_data(1234 + rank, pinned=True)
+    host = make_data(1234 + rank + args.seed_offset, pinned=True)
     dev = to_device(host, device)
     imgs_per_step = (N_SRC + N_TGT) * world
 
@@ -470,6 +480,8 @@ def main():
                     "in-situ device times here")
     ap.add_argument("--ncu-step", action="store_true", help="debug: warm up, run ONE eager step inside cudaProfilerStart/Stop, exit")
     ap.add_argument("--trace-losses", type=int, default=0, help="debug: run this many steps printing the loss dict, then exit")
+    ap.add_argument("--seed-offset", type=int, default=0, help="debug: data seed = 1234 + rank + this (reproduce another "
+                    "rank's synthetic batch on one GPU)")
     ap.add_argument("--base-lr", type=float, default=None, help="override SOLVER.BASE_LR (default: the reference's 0.06)")
     args = ap.parse_args()
     if args.impl == "reference":
