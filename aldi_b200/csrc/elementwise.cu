@@ -98,8 +98,9 @@ stem_im2col_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes
 // this map, and the four column taps b of one output pixel are 64 CONTIGUOUS values starting at column jp = ox: the
 // conv kernel reads them as one 128-byte TMA row of an overlapping-row view (row stride 16 elements), row taps a by
 // TMA coordinate, zero rows above/below by TMA out-of-bounds fill.
+template <typename T>
 __global__ void __launch_bounds__(256)
-stem_s2d_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes, __nv_bfloat16* __restrict__ out, int n,
+stem_s2d_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes, T* __restrict__ out, int n,
                 int hin, int win, int ho, int wp, Norm3 nm) {
   const size_t total = (size_t)n * ho * wp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -126,12 +127,71 @@ stem_s2d_kernel(const uint8_t* __restrict__ in, const int* __restrict__ sizes, _
         }
       }
     }
-    uint4 q[2];
-    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(q);
+    if constexpr (sizeof(T) == 4) {
+      float4* o = reinterpret_cast<float4*>(out) + i * 4;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-    reinterpret_cast<uint4*>(out)[i * 2] = q[0];
-    reinterpret_cast<uint4*>(out)[i * 2 + 1] = q[1];
+      for (int e = 0; e < 4; ++e) o[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+    } else {
+      uint4 q[2];
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+      reinterpret_cast<uint4*>(out)[i * 2] = q[0];
+      reinterpret_cast<uint4*>(out)[i * 2 + 1] = q[1];
+    }
+  }
+}
+
+// ---- split-bf16 parity mode ("bf16x3" / "bf16x6"): an fp32 tensor as a sum of 2 or 3 bf16 tensors ------------------
+// part[0] = bf16(x), part[1] = bf16(x - part[0]), part[2] = bf16(x - part[0] - part[1]); the tcgen05 kernels then run
+// once per kept product term (hi*hi, lo*hi, hi*lo, ...) into one fp32 accumulation: the SAME tensor-core main loops as
+// the bf16 step, at 2^-16 (two parts) or fp32-level (three parts) relative accuracy, so the whole step can be held to
+// the oracle's 1e-3 bar.  Source: strided channels-last view; parts: contiguous (n, h, w, c), `part_stride` elements apart.
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, long long sn, long long sh, long long sw, int n, int h, int w, int c,
+                  __nv_bfloat16* __restrict__ out, long long part_stride, int parts) {
+  const size_t total = (size_t)n * h * w * c;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    size_t r = i / c;
+    const int xw = (int)(r % w);
+    r /= w;
+    const int y = (int)(r % h);
+    const int b = (int)(r / h);
+    float v = __ldg(x + (long long)b * sn + (long long)y * sh + (long long)xw * sw + ch);
+    for (int p = 0; p < parts; ++p) {
+      const __nv_bfloat16 q = __float2bfloat16_rn(v);
+      out[(long long)p * part_stride + (long long)i] = q;
+      v = __fsub_rn(v, __bfloat162float(q));
+    }
+  }
+}
+
+// The fused epilogue of aldi_conv_tc restated on an fp32 accumulation (the sum of the split-mode launches):
+//   v = raw*scale[co] + bias[co] (+ residual) ; relu ; (* (mask > 0)) ; (+= out)
+__global__ void __launch_bounds__(256)
+conv_epilogue_f32_kernel(const float* __restrict__ raw, int n, int ho, int wo, int cp, const float* __restrict__ scale,
+                         const float* __restrict__ bias, const float* __restrict__ residual, int res_mode, long long res_sn,
+                         long long res_sh, long long res_sw, const float* __restrict__ mask, long long mask_sn,
+                         long long mask_sh, long long mask_sw, int relu, int accumulate, float* __restrict__ out,
+                         long long out_sn, long long out_sh, long long out_sw, int cout_store) {
+  const size_t total = (size_t)n * ho * wo * cout_store;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout_store);
+    size_t r = i / cout_store;
+    const int xw = (int)(r % wo);
+    r /= wo;
+    const int y = (int)(r % ho);
+    const int b = (int)(r / ho);
+    float v = raw[(((size_t)b * ho + y) * wo + xw) * cp + co];
+    if (scale) v = __fmul_rn(v, __ldg(scale + co));
+    if (bias) v = __fadd_rn(v, __ldg(bias + co));
+    if (res_mode == 1) v += residual[(long long)b * res_sn + (long long)y * res_sh + (long long)xw * res_sw + co];
+    else if (res_mode == 2) v += residual[(long long)b * res_sn + (long long)(y >> 1) * res_sh + (long long)(xw >> 1) * res_sw + co];
+    if (relu) v = fmaxf(v, 0.f);
+    if (mask && !(mask[(long long)b * mask_sn + (long long)y * mask_sh + (long long)xw * mask_sw + co] > 0.f)) v = 0.f;
+    float* o = out + (long long)b * out_sn + (long long)y * out_sh + (long long)xw * out_sw + co;
+    *o = accumulate ? *o + v : v;
   }
 }
 
@@ -388,10 +448,51 @@ extern "C" int aldi_stem_s2d(const uint8_t* images, const int* sizes, void* out_
   Norm3 nm;
   for (int i = 0; i < 3; ++i) { nm.mean[i] = h_mean[i]; nm.stdv[i] = h_std[i]; }
   const int ho = hin / 2, wp = win / 2 + 4;
-  stem_s2d_kernel<<<grid_for((size_t)n * ho * wp, 256), 256, 0, stream>>>(images, sizes, (__nv_bfloat16*)out_bf16, n, hin,
-                                                                         win, ho, wp, nm);
+  stem_s2d_kernel<__nv_bfloat16><<<grid_for((size_t)n * ho * wp, 256), 256, 0, stream>>>(images, sizes, (__nv_bfloat16*)out_bf16,
+                                                                                        n, hin, win, ho, wp, nm);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_stem_s2d");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_stem_s2d_f32(const uint8_t* images, const int* sizes, float* out, int n, int hin, int win,
+                                 const float* h_mean, const float* h_std, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(images && sizes && out && h_mean && h_std, "aldi_stem_s2d_f32: null pointer");
+  ALDI_CHECK_ARG(n > 0 && hin % 2 == 0 && win % 2 == 0, "aldi_stem_s2d_f32: canvas must have even height and width");
+  Norm3 nm;
+  for (int i = 0; i < 3; ++i) { nm.mean[i] = h_mean[i]; nm.stdv[i] = h_std[i]; }
+  const int ho = hin / 2, wp = win / 2 + 4;
+  stem_s2d_kernel<float><<<grid_for((size_t)n * ho * wp, 256), 256, 0, stream>>>(images, sizes, out, n, hin, win, ho, wp, nm);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_stem_s2d_f32");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_split_bf16(const float* x, int n, int h, int w, int c, long long sn, long long sh, long long sw,
+                               void* out, long long part_stride, int parts, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(x && out, "aldi_split_bf16: null pointer");
+  ALDI_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && parts >= 1 && parts <= 3, "aldi_split_bf16: bad extents / parts");
+  split_bf16_kernel<<<grid_for((size_t)n * h * w * c, 256), 256, 0, stream>>>(x, sn, sh, sw, n, h, w, c, (__nv_bfloat16*)out,
+                                                                             part_stride, parts);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_split_bf16");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_conv_epilogue_f32(const float* raw, const aldi_conv_params* p, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(raw && p && p->out, "aldi_conv_epilogue_f32: null pointer");
+  ALDI_CHECK_ARG(p->out_dtype == ALDI_DTYPE_F32, "aldi_conv_epilogue_f32: fp32 output only");
+  ALDI_CHECK_ARG(p->cout_store > 0 && p->cout_store <= p->cout_p, "aldi_conv_epilogue_f32: bad cout_store");
+  ALDI_CHECK_ARG(!p->res_mode || p->residual, "aldi_conv_epilogue_f32: res_mode without residual");
+  conv_epilogue_f32_kernel<<<grid_for((size_t)p->n * p->ho * p->wo * p->cout_store, 256), 256, 0, stream>>>(
+      raw, p->n, p->ho, p->wo, p->cout_p, p->scale, p->bias, (const float*)p->residual, p->res_mode, p->res_sn, p->res_sh,
+      p->res_sw, (const float*)p->mask, p->mask_sn, p->mask_sh, p->mask_sw, p->relu, p->accumulate, (float*)p->out,
+      p->out_sn, p->out_sh, p->out_sw, p->cout_store);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_conv_epilogue_f32");
   return ALDI_OK;
 }
 

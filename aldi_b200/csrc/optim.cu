@@ -219,7 +219,6 @@ refresh_kernel(const aldi_refresh_desc* __restrict__ descs, const int* __restric
     else if (d.out_dtype == ALDI_DTYPE_BF16) refresh_pack<__nv_bfloat16>(d, begin, end);
     else refresh_pack<float>(d, begin, end);
   } else if (d.kind == 4) {  // stem 7x7x3 -> 4x4 taps over the 2x2 space-to-depth map: out[co][a][b][dy][dx][c4], bf16
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
     const size_t total = (size_t)d.cout_p * 256;
     for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < total; i += blockDim.x) {
       const int co = (int)(i >> 8), rem = (int)(i & 255);
@@ -227,7 +226,8 @@ refresh_kernel(const aldi_refresh_desc* __restrict__ descs, const int* __restric
       const int r = 2 * a + dy - 1, s = 2 * b + dx - 1;
       float v = 0.f;
       if (co < d.cout && r >= 0 && s >= 0 && c < 3) v = __ldg(d.w + (((size_t)co * 7 + r) * 7 + s) * 3 + c);
-      out[i] = __float2bfloat16_rn(v);
+      if (d.out_dtype == ALDI_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(d.out)[i] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(d.out)[i] = v;   // split-bf16 parity mode: the operand is split afterwards
     }
   } else if (d.kind == 2) {  // FrozenBN fold: scale -> out, shift -> out2
     for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < (size_t)d.cout; i += blockDim.x) {

@@ -122,9 +122,13 @@ class LayerGeom:
 class DetectorWeights:
     """One model's parameters: flat fp32 master + GEMM operands + folded FrozenBN, refreshed by kernels."""
 
-    def __init__(self, layout, flat, dtype, bottom_up=None):
+    def __init__(self, layout, flat, dtype, bottom_up=None, split_parts=0):
+        """split_parts = 2 | 3 (dtype fp32): the split-bf16 parity mode of the tensor-core path -- activations stay fp32,
+        every GEMM runs on the tcgen05 kernels as 3 | 6 bf16 product terms (ops._conv_split)."""
         self.layout, self.flat, self.dtype = layout, flat, dtype
         self.dev = flat.device
+        self.split_parts = int(split_parts)
+        assert not self.split_parts or (dtype == torch.float32 and bottom_up is None)
         # a bottom-up that is not the ResNet-50 of this table (aldi_b200.convnext.ConvNeXtBackbone): own flat buffer,
         # forward(images, sizes, keep_masks, save) -> {0..3: stage outputs}, backward({stage: gradient})
         self.bottom_up = bottom_up
@@ -142,8 +146,9 @@ class DetectorWeights:
             else:
                 self.geom[name] = LayerGeom(name, s.cin, s.cout, s.k, s.pad, s.stride, (name,), s.norm, s.trainable)
         # stem: bf16 path runs it as a GEMM over the fused normalise+im2col buffer (K = 147 -> 192)
-        self.stem_gemm = dtype == torch.bfloat16
+        self.stem_gemm = dtype == torch.bfloat16 or bool(self.split_parts)
         self.fwd, self.dgrad, self.scale, self.shift = {}, {}, {}, {}
+        self.fwd_split, self.dgrad_split = {}, {}
         for name, g in self.geom.items():
             taps = g.k * g.k
             if name == "stem":
@@ -232,6 +237,19 @@ class DetectorWeights:
         trainable_only: the student after an optimizer step — frozen layers and FrozenBN buffers did not move."""
         raw, st, n, tot = self._table(trainable_only)
         ops.call("aldi_refresh_operands", raw, st, n, tot)
+        if self.split_parts:
+            for name, g in self.geom.items():
+                if trainable_only and not g.trainable:
+                    continue
+                self.fwd_split[name] = ops.split_bf16(self.fwd[name], self.split_parts)
+                if name in self.dgrad:
+                    self.dgrad_split[name] = ops.split_bf16(self.dgrad[name], self.split_parts)
+
+    def operand(self, name, dgrad=False):
+        """The GEMM operand a conv call takes: the packed tensor, or its bf16 split in the split parity mode."""
+        if self.split_parts:
+            return (self.dgrad_split if dgrad else self.fwd_split)[name]
+        return (self.dgrad if dgrad else self.fwd)[name]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -277,7 +295,7 @@ class Detector:
         if out is None:
             ho, wo = h + 2 * g.pad - g.k + 1, w + 2 * g.pad - g.k + 1   # stride-2 1x1 convs were turned into views
             out = torch.empty(n, ho, wo, g.cout_p, device=x.device, dtype=out_dtype or x.dtype)
-        ops.conv(xv, W.fwd[name], out, taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad, scale=W.scale.get(name),
+        ops.conv(xv, W.operand(name), out, taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad, scale=W.scale.get(name),
                  bias=W.shift[name], residual=residual, res_mode=res_mode, relu=relu, cout_store=cout_store)
         return out
 
@@ -301,9 +319,11 @@ class Detector:
             # pixel are 64 contiguous values, read through an overlapping-row view (row stride 16) as ONE TMA row
             wpad = wo + 4
             s2d = torch.empty(n, ho, wpad, 16, device=dev, dtype=dt)
-            ops.call("aldi_stem_s2d", images_u8, sizes, s2d, n, hp, wp, mean, std)
+            ops.call("aldi_stem_s2d_f32" if W.split_parts else "aldi_stem_s2d", images_u8, sizes, s2d, n, hp, wp, mean, std)
+            if W.split_parts:
+                s2d = ops.split_bf16(s2d, W.split_parts)     # the overlapping-row view is taken of every part
             view = s2d.as_strided((n, ho, wo, 64), (ho * wpad * 16, wpad * 16, 16, 1))
-            ops.conv(view, W.fwd["stem"], stem_out, taps_h=4, taps_w=1, pad_h=2, pad_w=0, scale=W.scale["stem"],
+            ops.conv(view, W.operand("stem"), stem_out, taps_h=4, taps_w=1, pad_h=2, pad_w=0, scale=W.scale["stem"],
                      bias=W.shift["stem"], relu=True, algo_cin=147 / 4.0)
             del view, s2d
         else:
@@ -520,7 +540,7 @@ class Detector:
         fused_bias = (not g.norm) and dy.dtype == torch.bfloat16 and os.environ.get("ALDI_FUSED_DBIAS") == "1"
         ops.wgrad(xv, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
                   scale=W.scale.get(name), cout_store=g.cout, cin_store=g.cin,
-                  dbias=W.view(name, "bias", G) if fused_bias else None)
+                  dbias=W.view(name, "bias", G) if fused_bias else None, split_parts=W.split_parts)
         if not g.norm and not fused_bias:
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             assert dy.is_contiguous()
@@ -531,7 +551,7 @@ class Detector:
         g = W.geom[name]
         outv = out[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else out
         maskv = mask[:, ::2, ::2, :] if (mask is not None and g.stride == 2 and g.k == 1) else mask
-        ops.conv(dy, W.dgrad[name], outv, taps_h=g.k, taps_w=g.k, pad_h=g.k - 1 - g.pad, pad_w=g.k - 1 - g.pad,
+        ops.conv(dy, W.operand(name, dgrad=True), outv, taps_h=g.k, taps_w=g.k, pad_h=g.k - 1 - g.pad, pad_w=g.k - 1 - g.pad,
                  mask=maskv, residual=residual, res_mode=1 if residual is not None else 0, accumulate=accumulate,
                  cout_store=g.cin)
         return out
@@ -666,7 +686,8 @@ class Detector:
         g = W.geom[name]
         fused_bias = dy.dtype == torch.bfloat16 and os.environ.get("ALDI_FUSED_DBIAS") == "1"
         ops.wgrad(x, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
-                  cout_store=g.cout, cin_store=g.cin, dbias=W.view(name, "bias", G) if fused_bias else None)
+                  cout_store=g.cout, cin_store=g.cin, dbias=W.view(name, "bias", G) if fused_bias else None,
+                  split_parts=W.split_parts)
         if fused_bias:
             return
         n, h, w, c = dy.shape

@@ -119,6 +119,9 @@ SIGNATURES = {
     "aldi_preprocess": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "aldi_stem_im2col": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "aldi_stem_s2d": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
+    "aldi_stem_s2d_f32": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
+    "aldi_split_bf16": (c_int, [P, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, P, c_ll, c_int, P]),
+    "aldi_conv_epilogue_f32": (c_int, [P, ctypes.POINTER(ConvParams), P]),
     "aldi_maxpool3x3s2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_sum2x2_accum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_add_f32": (c_int, [P, c_int, P, c_size_t, P]),

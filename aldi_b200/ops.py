@@ -34,6 +34,15 @@ class KernelProfiler:
 
 
 _PROFILER = None
+_SHADOW = None
+
+
+def set_shadow(fn):
+    """Test seam: fn(kind, run, **call) wraps every tensor-core conv / wgrad call (`kind` = "conv" | "wgrad", `run()`
+    performs the real launch, `call` holds the tensors and keyword arguments) so a test can re-run the SAME call on the
+    fp32 CUDA-core kernels and compare (tests/test_gpu_fullsize.py shadows every launch of a full-size step)."""
+    global _SHADOW
+    _SHADOW = fn
 
 
 def set_profiler(p):
@@ -117,10 +126,115 @@ def pack_weight(w, out, *, dgrad=False, scale=None, cout, taps, cin, cout_p, cin
                                                                      _stream())), "aldi_pack_weight")
 
 
+class Split:
+    """An fp32 tensor written as a sum of 2 or 3 bf16 tensors (aldi_split_bf16): `parts[k]` share the shape (and, for
+    views made by `as_strided`, the strides) of the tensor they stand for.  The split-bf16 parity mode ("bf16x3",
+    "bf16x6") feeds these to the SAME tcgen05 kernels the bf16 step runs."""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+
+    def as_strided(self, size, stride, offset=0):
+        return Split([p.as_strided(size, stride, offset) for p in self.parts])
+
+
+def split_bf16(x, parts):
+    """fp32 channels-last view (1-4 dims, unit last stride) -> Split of contiguous bf16 tensors of the same shape."""
+    assert x.dtype == torch.float32 and x.stride(-1) == 1 and 1 <= x.dim() <= 4
+    shape = tuple(x.shape)
+    lead = (1,) * (4 - x.dim()) + shape[:-1]
+    strides = (0,) * (4 - x.dim()) + tuple(x.stride()[:-1])
+    out = torch.empty((parts,) + shape, device=x.device, dtype=torch.bfloat16)
+    L = _l.load()
+    _l.check(_launch("aldi_split_bf16", lambda: L.aldi_split_bf16(
+        _ptr(x), lead[0], lead[1], lead[2], shape[-1], strides[0], strides[1], strides[2], _ptr(out), out[0].numel(), parts,
+        _stream())), "aldi_split_bf16")
+    return Split([out[k] for k in range(parts)])
+
+
+def split_view(v, parts):
+    """Split that keeps the strides of a non-contiguous view (stride-2 views of 1x1 convs, level slabs of the RPN
+    gradient map): the whole underlying allocation is split and the view re-applied to every part, so the kernels
+    build the SAME strided TMA tensor maps as in the bf16 step."""
+    if v.is_contiguous():
+        return split_bf16(v, parts)
+    st = v.untyped_storage()
+    flat = torch.empty(0, dtype=torch.float32, device=v.device).set_(st, 0, (st.nbytes() // 4,), (1,))
+    s = split_bf16(flat, parts)
+    return s.as_strided(tuple(v.shape), tuple(v.stride()), v.storage_offset())
+
+
+def _split_terms(parts):
+    """Product terms kept by the split mode, most significant first: (0,0), (1,0), (0,1) for two parts (error
+    ~2^-16 per product); three parts add (1,1), (2,0), (0,2) (fp32-level)."""
+    return [(i, j) for t in range(parts) for i in range(t + 1) for j in [t - i]]
+
+
+def _conv_split(x, wp, out, *, taps_h, taps_w, pad_h, pad_w, stride, scale, bias, residual, res_mode, mask, relu,
+                accumulate, cout_store):
+    """aldi_conv_tc once per product term of (split activations) x (split weights) into ONE fp32 accumulation, then the
+    layer's epilogue (aldi_conv_epilogue_f32): the tensor-core main loops of the bf16 step at fp32-level accuracy."""
+    assert stride == 1, "tensor-core path: pass a strided view instead of a stride"
+    parts = len(wp.parts)
+    xs = x if isinstance(x, Split) else split_view(x, parts)
+    x0, w0 = xs.parts[0], wp.parts[0]
+    n, xh, xw, xc, _, _, _ = _cl4(x0, "x")
+    on, oh, ow, oc, o_sn, o_sh, o_sw = _cl4(out, "out")
+    assert on == n and out.dtype == torch.float32
+    cout_p = w0.shape[0]
+    assert w0.numel() == cout_p * taps_h * taps_w * xc, (w0.shape, taps_h, taps_w, xc)
+    raw = torch.empty(n, oh, ow, cout_p, device=out.device, dtype=torch.float32)
+    L = _l.load()
+
+    def params(xa, wa, o, acc):
+        p = _l.ConvParams()
+        if xa is not None:
+            _, _, _, _, a_sn, a_sh, a_sw = _cl4(xa, "x")
+            p.x = xa.data_ptr(); p.x_sw = a_sw; p.x_sh = a_sh; p.x_sn = a_sn
+            p.w = wa.data_ptr()
+        p.x_c = xc; p.x_w = xw; p.x_h = xh; p.x_n = n
+        p.cout_p = cout_p
+        p.taps_h = taps_h; p.taps_w = taps_w; p.pad_h = pad_h; p.pad_w = pad_w; p.stride = 1
+        p.n = n; p.ho = oh; p.wo = ow
+        p.out = o.data_ptr(); p.out_dtype = _l.F32
+        _, _, _, _, q_sn, q_sh, q_sw = _cl4(o, "out")
+        p.out_sw = q_sw; p.out_sh = q_sh; p.out_sn = q_sn
+        p.accumulate = int(acc)
+        return p
+
+    for t, (i, j) in enumerate(_split_terms(parts)):
+        p = params(xs.parts[i], wp.parts[j], raw, t > 0)
+        p.cout_store = cout_p
+        _l.check(_launch("aldi_conv_tc", lambda: L.aldi_conv_tc(ctypes.byref(p), _stream())), "aldi_conv_tc(split)")
+    p = params(None, None, out, accumulate)
+    p.cout_store = int(cout_store if cout_store is not None else min(oc, cout_p))
+    assert p.cout_store <= oc
+    p.scale = scale.data_ptr() if scale is not None else None
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.relu = int(bool(relu))
+    if residual is not None:
+        assert res_mode in (1, 2) and residual.dtype == torch.float32
+        _, _, _, _, r_sn, r_sh, r_sw = _cl4(residual, "residual")
+        p.residual = residual.data_ptr(); p.res_mode = res_mode
+        p.res_sw = r_sw; p.res_sh = r_sh; p.res_sn = r_sn
+    if mask is not None:
+        assert mask.dtype == torch.float32
+        _, mh, mw, _, m_sn, m_sh, m_sw = _cl4(mask, "mask")
+        assert (mh, mw) == (oh, ow)
+        p.mask = mask.data_ptr(); p.mask_sw = m_sw; p.mask_sh = m_sh; p.mask_sn = m_sn
+    _l.check(_launch("aldi_conv_epilogue_f32", lambda: L.aldi_conv_epilogue_f32(_ptr(raw), ctypes.byref(p), _stream())),
+             "aldi_conv_epilogue_f32")
+
+
 def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, bias=None, residual=None,
          res_mode=0, mask=None, relu=False, accumulate=False, cout_store=None, algo_cin=None):
     """Implicit-GEMM conv/linear (forward or data-gradient).  x, out, residual, mask are channels-last
-    (N,H,W,C) views; wp is the packed (cout_p, taps*C) operand.  bf16 inputs -> tcgen05 path, fp32 -> CUDA cores."""
+    (N,H,W,C) views; wp is the packed (cout_p, taps*C) operand.  bf16 inputs -> tcgen05 path, fp32 -> CUDA cores;
+    a `Split` weight operand (fp32 activations) -> the tcgen05 path in split-bf16 parity mode."""
+    if isinstance(wp, Split):
+        return _conv_split(x, wp, out, taps_h=taps_h, taps_w=taps_w, pad_h=pad_h, pad_w=pad_w, stride=stride, scale=scale,
+                           bias=bias, residual=residual, res_mode=res_mode, mask=mask, relu=relu, accumulate=accumulate,
+                           cout_store=cout_store)
     n, xh, xw, xc, x_sn, x_sh, x_sw = _cl4(x, "x")
     on, oh, ow, oc, o_sn, o_sh, o_sw = _cl4(out, "out")
     assert on == n
@@ -165,16 +279,31 @@ def conv(x, wp, out, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
         taps_h, taps_w, xc, p.cout_store, n, oh, ow, " s2" if x_sw != xc else "", " +res%d" % res_mode if res_mode else "",
         " mask" if mask is not None else "", " acc" if accumulate else "")
     if x.dtype == torch.bfloat16:
-        _l.check(_launch("aldi_conv_tc", lambda: L.aldi_conv_tc(ctypes.byref(p), _stream()), flops, nbytes, key),
-                 "aldi_conv_tc")
+        def run():
+            _l.check(_launch("aldi_conv_tc", lambda: L.aldi_conv_tc(ctypes.byref(p), _stream()), flops, nbytes, key),
+                     "aldi_conv_tc")
+        if _SHADOW is not None:
+            return _SHADOW("conv", run, x=x, wp=wp, out=out, key=key(), kw=dict(
+                taps_h=taps_h, taps_w=taps_w, pad_h=pad_h, pad_w=pad_w, stride=stride, scale=scale, bias=bias,
+                residual=residual, res_mode=res_mode, mask=mask, relu=relu, accumulate=accumulate, cout_store=p.cout_store))
+        run()
     else:
         _l.check(_launch("aldi_conv_f32", lambda: L.aldi_conv_f32(ctypes.byref(p), _stream()), flops, nbytes, key),
                  "aldi_conv_f32")
 
 
 def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=None, cout_store=None,
-          cin_store=None, dbias=None):
-    """dw[co, tap, ci] += scale[co] * sum_pixels dy[pixel, co] * x[pixel shifted by tap, ci]  (fp32 atomics)."""
+          cin_store=None, dbias=None, split_parts=0):
+    """dw[co, tap, ci] += scale[co] * sum_pixels dy[pixel, co] * x[pixel shifted by tap, ci]  (fp32 atomics).
+    split_parts = 2 | 3 with fp32 operands: aldi_wgrad_tc once per product term of the split operands (the result is
+    accumulated atomically anyway) -- the split-bf16 parity mode of the tensor-core path."""
+    if split_parts:
+        assert x.dtype == torch.float32 and dy.dtype == torch.float32 and dbias is None
+        xs, ds = split_view(x, split_parts), split_view(dy, split_parts)
+        for i, j in _split_terms(split_parts):
+            wgrad(xs.parts[i], ds.parts[j], dw, taps_h=taps_h, taps_w=taps_w, pad_h=pad_h, pad_w=pad_w, stride=stride,
+                  scale=scale, cout_store=cout_store, cin_store=cin_store)
+        return
     n, xh, xw, xc, x_sn, x_sh, x_sw = _cl4(x, "x")
     dn, oh, ow, dc, d_sn, d_sh, d_sw = _cl4(dy, "dy")
     assert dn == n and dy.dtype == x.dtype and dw.dtype == torch.float32 and dw.is_contiguous()
@@ -196,8 +325,14 @@ def wgrad(x, dy, dw, *, taps_h=1, taps_w=1, pad_h=0, pad_w=0, stride=1, scale=No
     key = lambda: "%dx%d c%d->%d px%dx%dx%d%s" % (taps_h, taps_w, p.cin_store, p.cout_store, n, oh, ow,  # noqa: E731
                                                  " s2" if x_sw != xc else "")
     if x.dtype == torch.bfloat16:
-        _l.check(_launch("aldi_wgrad_tc", lambda: L.aldi_wgrad_tc(ctypes.byref(p), _stream()), flops, nbytes, key),
-                 "aldi_wgrad_tc")
+        def run():
+            _l.check(_launch("aldi_wgrad_tc", lambda: L.aldi_wgrad_tc(ctypes.byref(p), _stream()), flops, nbytes, key),
+                     "aldi_wgrad_tc")
+        if _SHADOW is not None:
+            return _SHADOW("wgrad", run, x=x, dy=dy, dw=dw, key=key(), kw=dict(
+                taps_h=taps_h, taps_w=taps_w, pad_h=pad_h, pad_w=pad_w, stride=stride, scale=scale,
+                cout_store=p.cout_store, cin_store=p.cin_store))
+        run()
     else:
         _l.check(_launch("aldi_wgrad_f32", lambda: L.aldi_wgrad_f32(ctypes.byref(p), _stream()), flops, nbytes, key),
                  "aldi_wgrad_f32")

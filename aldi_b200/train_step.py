@@ -88,7 +88,8 @@ class StepConfig:
         self.optimizer = "SGD"                   # SOLVER.OPTIMIZER: "SGD" | "ADAMW" (aldi/trainer.py:199-208)
         self.adamw_betas = (0.9, 0.999)
         self.adamw_eps = 1e-8
-        self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": parity path
+        self.dtype = "bf16"                      # "bf16": tcgen05 path; "fp32": CUDA-core parity path; "bf16x3" /
+                                                 # "bf16x6": the tcgen05 path in split-bf16 parity mode (fp32-level)
         self.cuda_graph = False                  # replay each micro-batch as a captured CUDA graph (2nd use onwards)
         # run the student on a source micro-batch and a distillation micro-batch as ONE batch (same weights, FrozenBN:
         # no cross-image coupling) -> twice the tiles per launch, half the launches; ALDI_NO_FUSE=1 is the A/B knob
@@ -247,8 +248,12 @@ class B200TrainStep:
     def __init__(self, cfg, state_dict, device="cuda:0", teacher_state_dict=None, process_group=None):
         self.cfg = cfg
         self.device = torch.device(device)
+        if cfg.dtype not in ("bf16", "fp32", "bf16x3", "bf16x6"):
+            raise ValueError("StepConfig.dtype %r: bf16 | fp32 | bf16x3 | bf16x6" % (cfg.dtype,))
         self.dtype = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
         self.dtc = _l.BF16 if cfg.dtype == "bf16" else _l.F32
+        # "bf16x3" / "bf16x6": fp32 activations, every GEMM on the tcgen05 kernels as 3 / 6 bf16 product terms
+        split_parts = {"bf16x3": 2, "bf16x6": 3}.get(cfg.dtype, 0)
         _l.load()  # fail loudly if the CUDA library is missing
         convnext = cfg.backbone == "convnext"
         if cfg.backbone not in ("resnet50", "convnext"):
@@ -272,8 +277,8 @@ class B200TrainStep:
             bu_s, bu_t = bottom_up(state_dict), bottom_up(tsd)
             self.keep_rng = torch.Generator().manual_seed(0)    # DropPath masks (host-drawn, aldi/backbone.py:176-181)
             self.keep_override = None                           # test seam: list of per-forward mask lists
-        self.student = DetectorWeights(self.layout, flat, self.dtype, bottom_up=bu_s)
-        self.teacher = DetectorWeights(self.layout, tflat, self.dtype, bottom_up=bu_t)
+        self.student = DetectorWeights(self.layout, flat, self.dtype, bottom_up=bu_s, split_parts=split_parts)
+        self.teacher = DetectorWeights(self.layout, tflat, self.dtype, bottom_up=bu_t, split_parts=split_parts)
         self.student.enable_dgrad()
         self.nt = self.layout.num_trainable
         self.grad = torch.zeros(self.nt, device=self.device)
@@ -308,6 +313,12 @@ class B200TrainStep:
         # device-computed ones, one GroundTruth per distillation micro-batch
         self.pseudo_override = None
         self.pseudo_log = []
+        # test seam of the same kind for the student's RPN proposals: {pass_id: [(k_i, 4) boxes per image]} to use INSTEAD
+        # of the device-computed ones (which are kept in `proposal_log` for comparison).  Selections are discontinuous: at
+        # 1024x2048 the top-2000 cut falls among ~400k scores a few 1e-6 apart, so two correct implementations differ in
+        # a handful of boxes; everything downstream is then compared on identical inputs.
+        self.proposal_override = None
+        self.proposal_log = {}
         # {"labeled": StrongAugmenter, "unlabeled": StrongAugmenter}: set to derive strong views on the device from
         # items that carry "aug_params" 
         self.augmenters = {}
@@ -482,7 +493,7 @@ class B200TrainStep:
         data parallelism is captured as a CHAIN of graphs cut where a gradient bucket becomes final: the NCCL
         all-reduce of that bucket is issued eagerly between two replays and overlaps the next segment."""
         if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override \
-                or self.student.bottom_up is not None:   # DropPath masks are host-drawn per forward: eager
+                or self.proposal_override or self.student.bottom_up is not None:   # DropPath masks are host-drawn: eager
             if self.profile_spin_cycles:
                 # profiling aid: park the GPU on a spin kernel while the host queues this micro-batch, so the kernels
                 # then run back to back (warm L2, no launch gaps) and per-launch CUDA events time exactly their durations
@@ -588,6 +599,7 @@ class B200TrainStep:
             out["labels"], out["matched"], out["rpn_stats"] = self._label_anchors(lv, b, gt, sampling.SITE_RPN)
         props = det.proposals(rpn_out, lv, b.sizes, cfg.rpn_pre_topk[0], cfg.rpn_post_topk[0], cfg.rpn_nms_thresh,
                               self.err_flag)
+        props = self._override_proposals(props, [(pass_id, n)])
         out["props"] = props
         m = n * cfg.roi_batch
         rois = torch.empty(m, 4, device=self.device)
@@ -603,6 +615,25 @@ class B200TrainStep:
         pred, head_saved = det.box_head(W, feats, rois, roi_batch, save=True)
         out.update(rois=rois, roi_gt=roi_gt, roi_batch=roi_batch, roi_class=roi_class, roi_src=roi_src,
                    roi_count=roi_count, roi_stats=roi_stats, pred=pred, head_saved=head_saved)
+        return out
+
+    def _override_proposals(self, props, passes):
+        """Test seam (see `proposal_override`): log the device's proposals per pass, substitute the given ones.
+        passes: [(pass_id, images)] in row order of `props`."""
+        if self.proposal_override is None:
+            return props
+        boxes, count = props["boxes"].clone(), props["count"].clone()
+        row = 0
+        for pid, k in passes:
+            self.proposal_log[pid] = (props["boxes"][row:row + k].clone(), props["count"][row:row + k].clone())
+            for j in range(k):
+                b = self.proposal_override[pid][j].to(self.device, torch.float32)
+                boxes[row + j].zero_()
+                boxes[row + j, :b.shape[0]] = b
+                count[row + j] = b.shape[0]
+            row += k
+        out = dict(props)
+        out["boxes"], out["count"] = boxes, count
         return out
 
     def _keep_masks(self, W, n):
@@ -727,6 +758,7 @@ class B200TrainStep:
         lv = det.levels(feats)
         rpn_out, rpn_ts = det.rpn_head(W, feats, lv, save=True)
         props = det.proposals(rpn_out, lv, sizes, cfg.rpn_pre_topk[0], cfg.rpn_post_topk[0], cfg.rpn_nms_thresh, self.err_flag)
+        props = self._override_proposals(props, [(pass_src, ns), (pass_dst, nt)])
         m = n * R
         rois = torch.empty(m, 4, device=self.device)
         roi_gt = torch.empty(m, 4, device=self.device)

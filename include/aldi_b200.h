@@ -118,6 +118,20 @@ int aldi_conv_tc(const aldi_conv_params* p, void* stream);
 /* same contract, fp32 activations/weights on CUDA cores (parity mode; also checks the tcgen05 path) */
 int aldi_conv_f32(const aldi_conv_params* p, void* stream);
 
+/* ---- split-bf16 parity mode of the tensor-core path ("bf16x3" / "bf16x6", StepConfig.dtype) -----------------------
+ * Holds the tcgen05 kernels themselves to the reference's fp32 arithmetic (the 1e-3 bar of the parity tests): every
+ * fp32 operand is written as a sum of 2 or 3 bf16 tensors, aldi_conv_tc / aldi_wgrad_tc run once per kept product
+ * term into ONE fp32 accumulation, and the fused epilogue is applied once on that sum.
+ *   aldi_split_bf16: part[0] = bf16(x), part[k] = bf16(x - part[0] - .. - part[k-1]); x: strided channels-last fp32
+ *       view (element strides sn/sh/sw, unit channel stride); parts: contiguous (n,h,w,c) bf16, `part_stride`
+ *       elements apart in `out`.
+ *   aldi_conv_epilogue_f32: the epilogue of aldi_conv_params (scale, bias, residual, relu, mask, accumulate) on the
+ *       contiguous fp32 accumulation `raw` (n, ho, wo, cout_p); residual / mask / out are fp32 views here; x, w and
+ *       the tap fields of `p` are ignored.                                                                          */
+int aldi_split_bf16(const float* x, int n, int h, int w, int c, long long sn, long long sh, long long sw, void* out,
+                    long long part_stride, int parts, void* stream);
+int aldi_conv_epilogue_f32(const float* raw, const aldi_conv_params* p, void* stream);
+
 /* ---- weight gradient: dw[co, r, s, ci] (+)= scale[co] * sum_{n,h,w} dy[n,h,w,co] * x[n,h+r-pad_h,w+s-pad_w,ci]
  * fp32 result accumulated atomically into the flat gradient buffer (split-K over pixels).        */
 typedef struct {
@@ -151,6 +165,9 @@ int aldi_stem_im2col(const uint8_t* images, const int* sizes, void* out_bf16, in
  * (N, hin/2, win/2, 64) with element strides (.., (win/2+4)*16, 16, 1) as a 4x1-tap conv, pad_h 2 */
 int aldi_stem_s2d(const uint8_t* images, const int* sizes, void* out_bf16, int n, int hin, int win,
                   const float* h_mean, const float* h_std, void* stream);
+/* the same map in fp32 (split-bf16 parity mode: split afterwards with aldi_split_bf16) */
+int aldi_stem_s2d_f32(const uint8_t* images, const int* sizes, float* out, int n, int hin, int win,
+                      const float* h_mean, const float* h_std, void* stream);
 int aldi_maxpool3x3s2(const void* in, void* out, int dtype, int n, int h, int w, int c, void* stream);
 /* coarse[n,h,w,c] += sum of the 2x2 block of fine (backward of nearest-2x upsample + add in FPN top-down) */
 int aldi_sum2x2_accum(const void* fine, void* coarse, int dtype, int n, int h, int w, int c, void* stream);

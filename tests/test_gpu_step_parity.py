@@ -1,6 +1,8 @@
-"""Whole-step parity: the B200 path in fp32 parity mode (CUDA-core fp32 convs, same kernels otherwise) against
-the CPU oracle on identical seeded inputs.  Tolerance from BASELINE north_star: 1e-3 relative on floats,
-bit-exact on box-index / NMS / sampling selections."""
+"""Whole-step parity against the CPU oracle on identical seeded inputs, in two arithmetic modes of the B200 path:
+"fp32" (CUDA-core fp32 convs, same kernels otherwise) and the tcgen05 tensor-core kernels in split-bf16 mode ("bf16x3":
+every GEMM as 3 bf16 product terms, ~2^-16 per product; "bf16x6": 6 terms, fp32-level) -- the same aldi_conv_tc /
+aldi_wgrad_tc launches the bf16 benchmark step makes, held to the reference's arithmetic.  Tolerance from BASELINE
+north_star: 1e-3 relative on floats, bit-exact on box-index / NMS / sampling selections."""
 import os
 import random
 
@@ -14,9 +16,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-3
 
 
-def run_device(sd_s, sd_t, data, pseudo_override=None, **cfg_kw):
+TC_MODES = ["fp32", "bf16x3", "bf16x6"]
+
+
+def run_device(sd_s, sd_t, data, pseudo_override=None, dtype="fp32", **cfg_kw):
     from aldi_b200.train_step import B200TrainStep, StepConfig
-    cfg = StepConfig(dtype="fp32", ema_start_iter=-1, **cfg_kw)
+    cfg = StepConfig(dtype=dtype, ema_start_iter=-1, **cfg_kw)
     step = B200TrainStep(cfg, sd_s, teacher_state_dict=sd_t)
     step.pseudo_override = pseudo_override
     random.seed(1234)
@@ -48,10 +53,11 @@ def check_grads(step, student):
     return worst
 
 
-def test_source_only_step_matches_oracle():
+@pytest.mark.parametrize("dtype", TC_MODES)
+def test_source_only_step_matches_oracle(dtype):
     """BASELINE config 1 shape of step: labeled_strong only (burn-in), hard losses."""
     sd_s, sd_t, ls, uw, us = pu.make_inputs(41, 2, 0, 128, 160)
-    step, dev_losses = run_device(sd_s, sd_t, (None, ls, None, None), ims_per_gpu=2)
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, None, None), ims_per_gpu=2, dtype=dtype)
     pu.install_device_sampler(step.seed_log)
     student, teacher = pu.oracle_models(sd_s, sd_t)
     with d2.EventStorage():
@@ -77,8 +83,10 @@ def test_source_only_step_matches_oracle():
         assert torch.allclose(tnew[k], v, rtol=1e-5, atol=1e-7), k
 
 
-@pytest.mark.parametrize("n_l,n_u,mb,h,w", [(2, 2, 2, 128, 160), (3, 3, 2, 96, 96)])
-def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w):
+@pytest.mark.parametrize("n_l,n_u,mb,h,w,dtype", [(2, 2, 2, 128, 160, "fp32"), (3, 3, 2, 96, 96, "fp32"),
+                                                  (2, 2, 2, 128, 160, "bf16x3"), (2, 2, 2, 128, 160, "bf16x6"),
+                                                  (3, 3, 2, 96, 96, "bf16x6")])
+def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w, dtype):
     """ALDI++ step: source + distillation micro-batches (incl. the uneven T9 case)."""
     sd_s, sd_t, ls, uw, us = pu.make_inputs(21 + n_l, n_l, n_u, h, w)
     n_src_mb, n_dst_mb = -(-n_l // mb), -(-n_u // mb)
@@ -95,7 +103,7 @@ def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w):
     # match.  The device computes its own pseudo labels (checked below against the oracle's) but the rest of the
     # step consumes the oracle's boxes so that every downstream selection sees identical inputs.
     override = [pu.pseudo_to_device([d["instances"] for d in uw_o[i:i + mb]], "cuda") for i in range(0, n_u, mb)]
-    step, dev_losses = run_device(sd_s, sd_t, (None, ls, uw, us), pseudo_override=override, ims_per_gpu=mb)
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, uw, us), pseudo_override=override, ims_per_gpu=mb, dtype=dtype)
     assert step.seed_log == pu.predict_seed_log(1234, n_src_mb, n_dst_mb)
     # --- last distillation micro-batch: intermediate tensors, in pipeline order (first mismatch = culprit)
     dbg = step.debug
@@ -136,10 +144,11 @@ def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w):
     print("aldi step: losses", dev_losses, "pseudo counts", cnt, "worst grad rel err", worst)
 
 
-def test_empty_pseudo_labels():
+@pytest.mark.parametrize("dtype", ["fp32", "bf16x6"])
+def test_empty_pseudo_labels(dtype):
     """T2: no detection above the threshold -> 256 negatives per image still feed loss_obj_bce; loss_rpn_l1 == 0."""
     sd_s, sd_t, ls, uw, us = pu.make_inputs(77, 0, 2, 96, 128)
-    step, dev_losses = run_device(sd_s, sd_t, (None, None, uw, us), ims_per_gpu=2, pseudo_threshold=0.9999)
+    step, dev_losses = run_device(sd_s, sd_t, (None, None, uw, us), ims_per_gpu=2, pseudo_threshold=0.9999, dtype=dtype)
     assert step.debug["pseudo"].counts.cpu().tolist() == [0, 0]
     pu.install_device_sampler(step.seed_log)
     student, teacher = pu.oracle_models(sd_s, sd_t)
@@ -153,7 +162,8 @@ def test_empty_pseudo_labels():
     check_grads(step, student)
 
 
-def test_ragged_batch_and_empty_gt_match_oracle():
+@pytest.mark.parametrize("dtype", ["fp32", "bf16x6"])
+def test_ragged_batch_and_empty_gt_match_oracle(dtype):
     """Edge cases of the batch format: images of different sizes share a zero-padded canvas (detectron2 ImageList),
     and one labelled image carries no ground-truth box at all."""
     from aldi_b200 import arch, synth_data
@@ -164,7 +174,7 @@ def test_ragged_batch_and_empty_gt_match_oracle():
     for (h, w, nb) in ((96, 160, 5), (128, 96, 0), (64, 64, 3)):
         img, boxes, classes = synth_data.synth_image(h, w, gen, num_boxes=nb, max_side=48)
         ls.append({"image": img, "boxes": boxes.reshape(-1, 4), "classes": classes.reshape(-1).long(), "height": h, "width": w})
-    step, dev_losses = run_device(sd_s, sd_t, (None, ls, None, None), ims_per_gpu=3)
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, None, None), ims_per_gpu=3, dtype=dtype)
     pu.install_device_sampler(step.seed_log)
     student, _ = pu.oracle_models(sd_s, sd_t)
     with d2.EventStorage():
