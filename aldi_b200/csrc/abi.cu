@@ -27,14 +27,15 @@ int aldi_num_sms() {
   return sms;
 }
 
+static int g_pdl_on = -1;
 bool aldi_pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
+  if (g_pdl_on < 0) {
     const char* e = getenv("ALDI_NO_PDL");
-    on = (e && e[0] == '1') ? 0 : 1;
+    g_pdl_on = (e && e[0] == '1') ? 0 : 1;
   }
-  return on != 0;
+  return g_pdl_on != 0;
 }
+extern "C" void aldi_set_pdl(int on) { g_pdl_on = on ? 1 : 0; }
 
 extern "C" const char* aldi_last_error(void) { return g_err; }
 extern "C" int aldi_abi_version(void) { return 1; }

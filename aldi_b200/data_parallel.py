@@ -56,6 +56,27 @@ class GradReducer:
         self.pending = []
         self.done = set()
         self.collectives = 0
+        if self.active:
+            self.warm_up()
+
+    def warm_up(self):
+        """Run every bucket's all-reduce once on a scratch buffer BEFORE the first kernel of the step exists: NCCL sets up
+        its per-algorithm connections lazily at the first collective of a given size class (runtime connect: cuMem
+        allocations, IPC / multicast mappings, NVLS buffers on 8 GPUs), and the step would otherwise make it do that
+        in the middle of its first backward, concurrently with the persistent tcgen05 kernels, and again between the
+        graph captures of its second.  Ends with a device synchronisation and a barrier: every rank enters its first
+        step with all transports up."""
+        import torch
+        if not self.grad.is_cuda:
+            return
+        scratch = torch.zeros_like(self.grad)
+        for a, b in self.ranges.values():
+            if b > a:
+                dist.all_reduce(scratch[a:b], op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=self.pg)
+        torch.cuda.synchronize(self.grad.device)
+        dist.barrier(group=self.pg)
+        del scratch
 
     @property
     def active(self):

@@ -105,6 +105,7 @@ SIGNATURES = {
     "aldi_abi_version": (c_int, []),
     "aldi_launch_count": (ctypes.c_ulonglong, []),
     "aldi_reset_launch_count": (None, []),
+    "aldi_set_pdl": (None, [c_int]),
     "aldi_ema_update": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p]),
     "aldi_sgd_momentum_step": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
                                        c_void_p, c_double, c_void_p]),
