@@ -557,28 +557,42 @@ class B200TrainStep:
         return chain
 
     def _source_body(self, b, gscale, pass_id, base=SLOT_BASE["source_strong"]):
-        cfg, det, W = self.cfg, self.det, self.student
         fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=True)
+        self._source_finish(fw, b, {k: gscale for k in SRC_KEYS + ("da",)}, self.loss_acc, base, labeled=True)
+
+    def _source_finish(self, fw, b, w, loss_vec, base, labeled=True, do_align=True):
+        """Hard losses of a finished student forward and the explicit backward.  w: weight per loss key (`loss_cls`,
+        `loss_box_reg`, `loss_rpn_cls`, `loss_rpn_loc`, `da`): value written = weight * loss, gradient scaled alike
+        (the step passes 1/num_grad_accum for all of them; the module facade passes what autograd hands back)."""
+        d_rpn, dpred, align = self._source_losses(fw, b, w, loss_vec, base, labeled, do_align, self.grad)
+        self.det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"],
+                          dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), align=align)
+
+    def _source_losses(self, fw, b, w, loss_vec, base, labeled, do_align, G):
+        """-> (d_rpn, dpred, align context); G: where the discriminators' last-layer gradients go (they are produced by
+        the same kernel as the loss)."""
+        cfg, det = self.cfg, self.det
         n = b.n
+        if "labels" not in fw:        # target_weak alignment pass: no detection losses (aldi/trainer.py:107-109)
+            return None, None, (self._align(fw, labeled, w["da"], loss_vec[base:base + 2], G) if do_align else None)
         d_rpn = torch.zeros(n, fw["lv"].total_locs, 64, device=self.device, dtype=self.dtype)
         ops.call("aldi_rpn_loss", fw["rpn_out"], _l.ctypes.byref(fw["lv"]), n, fw["labels"], fw["matched"], b.gt.boxes,
-                 b.gt.counts, b.gt.gmax, cfg.rpn_batch, 1.0, 1.0, gscale, d_rpn, self.dtc, 64, 0,
-                 self.loss_acc[base + 2:base + 4])
+                 b.gt.counts, b.gt.gmax, cfg.rpn_batch, w["loss_rpn_cls"], w["loss_rpn_loc"], 1.0, d_rpn, self.dtc, 64, 0,
+                 loss_vec[base + 2:base + 4])
         m = n * cfg.roi_batch
         dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
         ops.call("aldi_roi_loss", fw["pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"], fw["rois"], fw["roi_gt"],
-                 fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)), 1.0, 1.0, gscale, dpred, self.dtc, 64,
-                 self.loss_acc[base:base + 2])
-        align = self._align(fw, True, gscale, self.loss_acc[base + 4:base + 6])
-        det.backward(W, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"], dpred,
-                     fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), align=align)
+                 fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)), w["loss_cls"], w["loss_box_reg"], 1.0, dpred,
+                 self.dtc, 64, loss_vec[base:base + 2])
+        align = self._align(fw, labeled, w["da"], loss_vec[base + 4:base + 6], G) if do_align else None
+        return d_rpn, dpred, align
 
-    def _align(self, fw, labeled, gscale, loss_out):
+    def _align(self, fw, labeled, gscale, loss_out, G=None):
         """AlignMixin.forward(do_align=True) on a finished student forward (aldi/align.py:74-90)."""
         if not self.cfg.do_align:
             return None
-        saved = self.det.align_forward(self.student, self.grad, fw["feats"], fw["head_saved"][2], fw["roi_count"],
-                                       self.cfg.roi_batch, self.cfg, labeled, gscale, loss_out)
+        saved = self.det.align_forward(self.student, self.grad if G is None else G, fw["feats"], fw["head_saved"][2],
+                                       fw["roi_count"], self.cfg.roi_batch, self.cfg, labeled, gscale, loss_out)
         saved["img_layer"] = self.cfg.img_da_layer
         return saved
 
@@ -586,11 +600,8 @@ class B200TrainStep:
         """aldi/trainer.py:107-109: model(unlabeled_weak, labeled=False, do_align=True) — a training-mode student
         forward on target images with EMPTY ground truth (aldi/dataloader.py:21-30), of which only the `_da_` losses
         are kept and back-propagated (the detection losses are multiplied by 0, aldi/trainer.py:75-77)."""
-        det, W = self.det, self.student
         fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=False)
-        align = self._align(fw, False, gscale, self.loss_acc[base:base + 2])
-        det.backward(W, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], None, fw["lv"], fw["head_saved"], None,
-                     fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), align=align)
+        self._source_finish(fw, b, {"da": gscale}, self.loss_acc, base, labeled=False)
 
     def _student_forward(self, b, gt, pass_id, want_rpn_labels):
         cfg, det, W = self.cfg, self.det, self.student
@@ -828,8 +839,18 @@ class B200TrainStep:
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
     def _distill_body(self, bw, bs, gscale, pass_id, base=SLOT_BASE["distill"]):
+        cfg = self.cfg
+        ctx = self._distill_forward(bw, bs, pass_id)
+        w = {"loss_cls": gscale if cfg.do_hard_cls else 0.0, "loss_box_reg": gscale if cfg.do_hard_roi_reg else 0.0,
+             "loss_rpn_cls": gscale if cfg.do_hard_obj else 0.0, "loss_rpn_loc": gscale if cfg.do_hard_rpn_reg else 0.0,
+             "loss_obj_bce": gscale if cfg.do_obj_dst else 0.0, "loss_rpn_l1": gscale if cfg.do_rpn_reg_dst else 0.0,
+             "loss_cls_ce": gscale if cfg.do_cls_dst else 0.0, "loss_roih_l1": gscale if cfg.do_roih_reg_dst else 0.0}
+        self._distill_finish(ctx, w, self.loss_acc, base)
+
+    def _distill_forward(self, bw, bs, pass_id):
+        """aldi/distill.py:144-168: pseudo-label with the teacher, student forward on the strong views, teacher box
+        head on the student's sampled proposals, fresh teacher anchor sampling on the pseudo labels (T2)."""
         cfg, det = self.cfg, self.det
-        n = bw.n
         t_feats, t_lv, t_rpn_out = self.teacher_forward(bw)
         pseudo, _ = self.pseudo_label(bw, t_feats, t_lv, t_rpn_out)
         self.last_pseudo = pseudo
@@ -846,34 +867,119 @@ class B200TrainStep:
         t_pred, _ = det.box_head(self.teacher, t_feats, fw["rois"], fw["roi_batch"], save=False)
         # fresh anchor sampling by the TEACHER's RPN on the pseudo labels (T2)
         labels, _, stats = self._label_anchors(t_lv, bs, pseudo, sampling.SITE_RPN_DISTILL)
+        self.debug = {"fw": fw, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": labels, "stats": stats,
+                      "pseudo": pseudo} if self.debug is not None else None
+        return {"fw": fw, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": labels, "stats": stats, "pseudo": pseudo,
+                "n": bw.n}
+
+    def _distill_finish(self, ctx, w, loss_vec, base):
+        """Losses of aldi/distill.py:170-278 with one weight per key (0 = the reference's `* 0.0`, T5) and the backward."""
+        fw = ctx["fw"]
+        d_rpn, dpred = self._distill_losses(ctx, w, loss_vec, base)
+        self.det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"],
+                          dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready())
+
+    def _distill_losses(self, ctx, w, loss_vec, base):
+        cfg, det = self.cfg, self.det
+        fw, pseudo, n = ctx["fw"], ctx["pseudo"], ctx["n"]
         lv = fw["lv"]
         d_rpn = torch.zeros(n, lv.total_locs, 64, device=self.device, dtype=self.dtype)
         acc = 0
-        if hard_rpn:
+        if (w["loss_rpn_cls"] or w["loss_rpn_loc"]) and "labels" in fw:
             ops.call("aldi_rpn_loss", fw["rpn_out"], _l.ctypes.byref(lv), n, fw["labels"], fw["matched"], pseudo.boxes,
-                     pseudo.counts, pseudo.gmax, cfg.rpn_batch, 1.0 if cfg.do_hard_obj else 0.0,
-                     1.0 if cfg.do_hard_rpn_reg else 0.0, gscale, d_rpn, self.dtc, 64, 0, self.loss_acc[base + 2:base + 4])
+                     pseudo.counts, pseudo.gmax, cfg.rpn_batch, w["loss_rpn_cls"], w["loss_rpn_loc"], 1.0, d_rpn, self.dtc,
+                     64, 0, loss_vec[base + 2:base + 4])
             acc = 1
-        ops.call("aldi_distill_rpn_loss", fw["rpn_out"], t_rpn_out, _l.ctypes.byref(lv), n, labels, stats,
-                 cfg.obj_temperature, 1.0 if cfg.do_obj_dst else 0.0, 1.0 if cfg.do_rpn_reg_dst else 0.0, gscale, d_rpn,
-                 self.dtc, 64, acc, self.loss_acc[base + 4:base + 6])
+        ops.call("aldi_distill_rpn_loss", fw["rpn_out"], ctx["t_rpn_out"], _l.ctypes.byref(lv), n, ctx["labels"], ctx["stats"],
+                 cfg.obj_temperature, w["loss_obj_bce"], w["loss_rpn_l1"], 1.0, d_rpn, self.dtc, 64, acc,
+                 loss_vec[base + 4:base + 6])
         m = n * cfg.roi_batch
         dpred = torch.zeros(m, 64, device=self.device, dtype=self.dtype)
         acc = 0
-        if cfg.do_hard_cls or cfg.do_hard_roi_reg:
+        if w["loss_cls"] or w["loss_box_reg"]:
             ops.call("aldi_roi_loss", fw["pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"], fw["rois"],
-                     fw["roi_gt"], fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)),
-                     1.0 if cfg.do_hard_cls else 0.0, 1.0 if cfg.do_hard_roi_reg else 0.0, gscale, dpred, self.dtc, 64,
-                     self.loss_acc[base:base + 2])
+                     fw["roi_gt"], fw["roi_count"], n, ops.host_floats((10.0, 10.0, 5.0, 5.0)), w["loss_cls"],
+                     w["loss_box_reg"], 1.0, dpred, self.dtc, 64, loss_vec[base:base + 2])
             acc = 1
-        ops.call("aldi_distill_roi_loss", fw["pred"], t_pred, det.PRED_CH, m, cfg.num_classes, fw["roi_class"],
-                 fw["roi_count"], n, cfg.cls_temperature, 1 if cfg.cls_loss_type == "KL" else 0,
-                 1.0 if cfg.do_cls_dst else 0.0, 1.0 if cfg.do_roih_reg_dst else 0.0, gscale, dpred, self.dtc, 64, acc,
-                 self.loss_acc[base + 6:base + 8])
-        self.debug = {"fw": fw, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": labels, "stats": stats,
-                      "pseudo": pseudo} if self.debug is not None else None
-        det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, lv, fw["head_saved"],
-                     dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready())
+        ops.call("aldi_distill_roi_loss", fw["pred"], ctx["t_pred"], det.PRED_CH, m, cfg.num_classes, fw["roi_class"],
+                 fw["roi_count"], n, cfg.cls_temperature, 1 if cfg.cls_loss_type == "KL" else 0, w["loss_cls_ce"],
+                 w["loss_roih_l1"], 1.0, dpred, self.dtc, 64, acc, loss_vec[base + 6:base + 8])
+        return d_rpn, dpred
+
+    # ---- module-facade seams (aldi_b200/model.py): ONE micro-batch per call, losses first, backward when autograd asks ----
+    def _facade_begin(self):
+        if not getattr(self, "_facade_open", False):
+            self._facade_open, self._facade_pass = True, 0
+            self.seed = random.randint(0, 2 ** 32 - 1)      # aldi/helpers.py:19-23, as run_model draws it
+            self.seed_log = {}
+            self.loss_acc.zero_()
+            self._last_backward = False
+
+    def facade_forward(self, data, labeled=True, do_align=False):
+        """`model(batched_inputs, labeled=, do_align=)` of the reference (aldi/model.py:27-29) for one micro-batch:
+        student forward + loss values now, `finish(weights)` runs the loss gradients and the explicit backward later.
+        -> (keys, values: fp32 device vector of the UNWEIGHTED losses, finish)"""
+        self._facade_begin()
+        pass_id = self._facade_pass
+        self._facade_pass += 1
+        self.seed_log[pass_id] = self.seed
+        kind = "source" if labeled else "target"
+        item = {"keys": [(kind,) + MicroBatch.shape_key(data, labeled)], "parts": [(kind, data, labeled)],
+                "seed": self.seed, "pass_id": pass_id}
+        b, = self._stage(item, None)
+        fw = self._student_forward(b, b.gt, pass_id, want_rpn_labels=labeled)
+        if getattr(self, "_scratch_grad", None) is None and do_align:
+            self._scratch_grad = torch.zeros_like(self.grad)
+        vals = torch.zeros(8, device=self.device)
+        ones = {k: 1.0 for k in SRC_KEYS + ("da",)}
+        # unlabeled (target_weak) passes carry no detection losses: their slots stay 0, the alignment pair lands at 4..5
+        self._source_losses(fw, b, ones, vals, 0 if labeled else 4, labeled, do_align, getattr(self, "_scratch_grad", None))
+        keys = list(SRC_KEYS) + ([k for k, on in zip(DA_KEYS, (self.cfg.img_da_enabled, self.cfg.ins_da_enabled)) if on]
+                                 if do_align else [])
+        idx = list(range(4)) + ([4 + j for j, on in enumerate((self.cfg.img_da_enabled, self.cfg.ins_da_enabled)) if on]
+                                if do_align else [])
+
+        def finish(weights):
+            w = {k: float(weights.get(k, 0.0)) for k in SRC_KEYS}
+            da = [float(weights[k]) for k in DA_KEYS if k in weights]
+            assert len(set(da)) <= 1, "the alignment losses share one weight (aldi/trainer.py:75-79)"
+            w["da"] = da[0] if da else 0.0
+            self._source_finish(fw, b, w, torch.zeros(8, device=self.device), 0, labeled=labeled, do_align=do_align)
+            b.free_event = torch.cuda.Event()
+            b.free_event.record()
+
+        return keys, vals[idx], finish
+
+    def facade_distill(self, teacher_data, student_data):
+        """`distiller(teacher_batched_inputs, student_batched_inputs)` (aldi/distill.py:170-191) for one micro-batch.
+        -> (keys: the 4 hard + the enabled soft loss names, values, finish)"""
+        self._facade_begin()
+        cfg = self.cfg
+        pass_id = 100 + self._facade_pass
+        self._facade_pass += 1
+        seed = random.randint(0, 2 ** 32 - 1)               # seeder.reset_seed(), aldi/distill.py:150
+        self.seed_log[pass_id] = seed
+        self.seed = seed
+        item = {"keys": [("weak",) + MicroBatch.shape_key(teacher_data, False), ("strong",) + MicroBatch.shape_key(student_data, False)],
+                "parts": [("weak", teacher_data, False), ("strong", student_data, False)], "seed": seed, "pass_id": pass_id}
+        bw, bs = self._stage(item, None)
+        ctx = self._distill_forward(bw, bs, pass_id)
+        on = {"loss_cls": cfg.do_hard_cls, "loss_box_reg": cfg.do_hard_roi_reg, "loss_rpn_cls": cfg.do_hard_obj,
+              "loss_rpn_loc": cfg.do_hard_rpn_reg, "loss_obj_bce": cfg.do_obj_dst, "loss_rpn_l1": cfg.do_rpn_reg_dst,
+              "loss_cls_ce": cfg.do_cls_dst, "loss_roih_l1": cfg.do_roih_reg_dst}
+        vals = torch.zeros(8, device=self.device)
+        self._distill_losses(ctx, {k: 1.0 if v else 0.0 for k, v in on.items()}, vals, 0)
+        keys = list(SRC_KEYS) + [k for k in SOFT_KEYS if on[k]]
+        idx = list(range(4)) + [4 + j for j, k in enumerate(SOFT_KEYS) if on[k]]
+
+        def finish(weights):
+            self._distill_finish(ctx, {k: float(weights.get(k, 0.0)) if on[k] else 0.0 for k in on},
+                                 torch.zeros(8, device=self.device), 0)
+            for m in (bw, bs):
+                m.free_event = torch.cuda.Event()
+                m.free_event.record()
+
+        return keys, vals[idx], finish
 
     # ---- aldi/dropin.py:121 optimizer.step() (torch.optim.SGD via D2 build_optimizer) ---------------------
     def lr_at(self, it, warmup_iters=100, warmup_factor=0.01, steps=(), gamma=0.1):
@@ -915,6 +1021,7 @@ class B200TrainStep:
             ops.sgd_momentum_step(p, self.momentum_buf, self.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
             if bu is not None:
                 ops.sgd_momentum_step(bu.flat, self.bu_momentum, bu.grad, lr, self.cfg.weight_decay, self.cfg.momentum, gs)
+        self._facade_open = False
         self.grad.zero_()
         self.student.refresh(trainable_only=True)
         if bu is not None:

@@ -16,7 +16,7 @@ import torch.distributed as dist
 from . import arch, synth_data
 from .config import step_config_from_cfg
 from .data_parallel import reduce_loss_vector
-from .train_step import B200TrainStep
+from .model import EMA, build_aldi, build_distiller
 
 logger = logging.getLogger("aldi_b200")
 
@@ -109,7 +109,6 @@ class ALDITrainer:
         if cfg.MODEL.DEVICE != "cuda" and device is None:
             raise RuntimeError("aldi_b200 runs the train step on a CUDA device only (MODEL.DEVICE=%s): there is no CPU "
                                "fallback; the CPU arm of bench.py is the oracle" % cfg.MODEL.DEVICE)
-        assert cfg.EMA.ENABLED or not cfg.DOMAIN_ADAPT.TEACHER.ENABLED, "Teacher requires EMA.ENABLED"
         scfg = step_config_from_cfg(cfg, dtype=dtype)
         sd = state_dict
         if sd is None:
@@ -120,9 +119,18 @@ class ALDITrainer:
                 from .convnext import synthetic_state_dict as convnext_init
                 sd.update({"backbone.bottom_up." + k: v for k, v in convnext_init(
                     scfg.convnext_depths, scfg.convnext_dims, 0, cfg.MODEL.CONVNEXT.LAYER_SCALE_INIT_VALUE).items()})
-        self.step_impl = B200TrainStep(scfg, sd, device=device or "cuda:%d" % torch.cuda.current_device(),
-                                       process_group=process_group)
-        self.step_impl.debug = None
+        # aldi/trainer.py:139-147,156-160: the model, its EMA teacher and the distiller come from the registries named in cfg
+        # (MODEL.META_ARCHITECTURE, DOMAIN_ADAPT.ALIGN.MIXIN_NAME, DOMAIN_ADAPT.DISTILL.MIXIN_NAME / DISTILLER_NAME); all
+        # three are facades over ONE engine, which is what run_step drives
+        self.model = build_aldi(cfg, state_dict=sd, device=device or "cuda:%d" % torch.cuda.current_device(),
+                                process_group=process_group, dtype=dtype)
+        self.step_impl = self.model.engine
+        self.ema = EMA(self.model, cfg.EMA.ALPHA, cfg.EMA.START_ITER) if cfg.EMA.ENABLED else None
+        if self.ema is None:
+            # aldi/trainer.py:142: without EMA the "teacher" handed to the distiller is the student itself
+            self.step_impl.teacher = self.step_impl.student
+        self.distiller = build_distiller(cfg, teacher=self.ema.model if self.ema is not None else self.model,
+                                         student=self.model)
         self.data_loader = data_loader if data_loader is not None else self.build_train_loader(cfg, image_size, self.rank,
                                                                                                self.world)
         if getattr(self.data_loader, "augmenters", None):
@@ -146,7 +154,7 @@ class ALDITrainer:
     # ---- aldi/trainer.py:242-246 ----------------------------------------------------------------------------
     def before_step(self):
         if self.cfg.EMA.ENABLED:
-            self.step_impl.ema_update(self.iter)
+            self.ema.update_weights(self.model, self.iter)
 
     # ---- aldi/dropin.py:94-121 (SimpleTrainer.run_step with the run_model / do_backward seams) -------------------
     def run_step(self):

@@ -1,11 +1,11 @@
 #!/bin/bash
 # final-settings check at 8 GPUs: the driver's own command (supervised), restart path with an injected failure, DP tests
 O=gpurun_out/n8c; mkdir -p $O
-run() { name=$1; shift; env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+run() { name=$1; shift; env "$@" timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
   --master-port 29571 bench.py --gpus 8 --steps 20 --warmup 5 > $O/$name.out 2> $O/$name.err; echo "$name rc=$?" | tee -a $O/summary.txt; }
 run plain A=1
 run inject ALDI_BENCH_INJECT_FAIL=3:0
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > $O/pytest.out 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
+timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > $O/pytest.out 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
 for n in plain inject; do python - <<PY
 import json
 try:
