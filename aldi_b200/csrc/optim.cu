@@ -218,6 +218,15 @@ refresh_kernel(const aldi_refresh_desc* __restrict__ descs, const int* __restric
     if (refresh_fast_fwd(d)) refresh_pack_fwd_bf16(d, begin, end);
     else if (d.out_dtype == ALDI_DTYPE_BF16) refresh_pack<__nv_bfloat16>(d, begin, end);
     else refresh_pack<float>(d, begin, end);
+  } else if (d.kind == 5) {  // transposed forward operand: out[(t * cin + ci)][co], cout_p columns
+    const size_t total = (size_t)d.taps * d.cin * d.cout_p;
+    for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < total; i += blockDim.x) {
+      const int co = (int)(i % d.cout_p);
+      const size_t k = i / d.cout_p;             // t * cin + ci
+      const float v = co < d.cout ? __ldg(d.w + (size_t)co * d.taps * d.cin + k) : 0.f;
+      if (d.out_dtype == ALDI_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(d.out)[i] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(d.out)[i] = v;
+    }
   } else if (d.kind == 4) {  // stem 7x7x3 -> 4x4 taps over the 2x2 space-to-depth map: out[co][a][b][dy][dx][c4], bf16
     const size_t total = (size_t)d.cout_p * 256;
     for (size_t i = begin + threadIdx.x; i < begin + kRefreshChunk && i < total; i += blockDim.x) {
@@ -288,6 +297,7 @@ extern "C" int aldi_refresh_blocks(const aldi_refresh_desc* d) {
   if (d->kind == 0) total = (size_t)d->cout_p * d->taps * d->cin_p;
   else if (d->kind == 1) total = (size_t)d->cin_p * d->taps * d->cout_p;
   else if (d->kind == 4) total = (size_t)d->cout_p * 256;
+  else if (d->kind == 5) total = (size_t)d->taps * d->cin * d->cout_p;
   else total = (size_t)d->cout;
   return (int)((total + kRefreshChunk - 1) / kRefreshChunk);
 }

@@ -149,6 +149,7 @@ class DetectorWeights:
         self.stem_gemm = dtype == torch.bfloat16 or bool(self.split_parts)
         self.fwd, self.dgrad, self.scale, self.shift = {}, {}, {}, {}
         self.fwd_split, self.dgrad_split = {}, {}
+        self.scat, self.scat_split = {}, {}
         for name, g in self.geom.items():
             taps = g.k * g.k
             if name == "stem":
@@ -176,6 +177,10 @@ class DetectorWeights:
         for name, g in self.geom.items():
             if g.trainable and name not in self.no_dgrad and name not in self.dgrad:
                 self.dgrad[name] = torch.zeros(g.cin_p, g.k * g.k * g.cout_p, device=self.dev, dtype=self.dtype)
+        # sparse RPN backward (csrc/rpn_sparse.cu): [(tap, cin)][cout] operand that turns gathered hidden-gradient rows
+        # into the 3x3 neighbourhood rows scattered back onto the FPN feature gradient
+        g = self.geom["rpn_conv"]
+        self.scat["rpn_conv"] = torch.zeros(g.k * g.k * g.cin_p, g.cout_p, device=self.dev, dtype=self.dtype)
         self._tables = {}
 
     # ---- operand refresh: ONE launch per table (csrc/optim.cu refresh_kernel) ------------------------------------
@@ -215,6 +220,9 @@ class DetectorWeights:
                 desc(0, w=w, out=self.fwd[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
             if name in self.dgrad:
                 desc(1, w=w, out=self.dgrad[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p, **bn)
+            if name in self.scat:
+                assert g.cin == g.cin_p and not g.norm
+                desc(5, w=w, out=self.scat[name], cout=g.cout, taps=taps, cin=g.cin, cout_p=g.cout_p, cin_p=g.cin_p)
         return out
 
     def _table(self, trainable_only):
@@ -244,12 +252,14 @@ class DetectorWeights:
                 self.fwd_split[name] = ops.split_bf16(self.fwd[name], self.split_parts)
                 if name in self.dgrad:
                     self.dgrad_split[name] = ops.split_bf16(self.dgrad[name], self.split_parts)
+                if name in self.scat:
+                    self.scat_split[name] = ops.split_bf16(self.scat[name], self.split_parts)
 
-    def operand(self, name, dgrad=False):
+    def operand(self, name, dgrad=False, scatter=False):
         """The GEMM operand a conv call takes: the packed tensor, or its bf16 split in the split parity mode."""
         if self.split_parts:
-            return (self.dgrad_split if dgrad else self.fwd_split)[name]
-        return (self.dgrad if dgrad else self.fwd)[name]
+            return (self.scat_split if scatter else self.dgrad_split if dgrad else self.fwd_split)[name]
+        return (self.scat if scatter else self.dgrad if dgrad else self.fwd)[name]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -556,8 +566,54 @@ class Detector:
                  cout_store=g.cin)
         return out
 
+    def _rpn_backward_sparse(self, W, G, feats, rpn_ts, d_rpn, lv, dfeat, rows_per_image, err_flag):
+        """RPN head backward on the non-zero rows of d_rpn only (csrc/rpn_sparse.cu): compact, gather, four GEMMs on the
+        gathered rows, scatter-add into the fp32 feature-gradient maps `dfeat` (p2..p5; p6 rows land in p5's map)."""
+        L = _l.load()
+        n, dt, dev = d_rpn.shape[0], W.dtype, d_rpn.device
+        dtc = _l.BF16 if dt == torch.bfloat16 else _l.F32
+        gc, gh = W.geom["rpn_conv"], W.geom["rpn_head"]
+        C = gc.cin_p
+        cap = n * rows_per_image
+        idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        ops.call("aldi_rpn_sparse_compact", d_rpn, dtc, n, lv.total_locs, 64, gh.cout, cap, idx, count)
+        dy_g = torch.empty(1, 1, cap, 64, device=dev, dtype=dt)
+        t_g = torch.empty(1, 1, cap, C, device=dev, dtype=dt)
+        x_g = torch.empty(1, 1, cap, 9 * C, device=dev, dtype=dt)
+        p = _l.RpnSparseParams()
+        p.levels = _l.ctypes.cast(_l.ctypes.pointer(lv), _l.ctypes.c_void_p)
+        p.dtype, p.channels = dtc, C
+        maps = list(dfeat) + [dfeat[3][:, ::2, ::2, :]]
+        for i, l in enumerate((2, 3, 4, 5, 6)):
+            f, t, d = feats["p%d" % l], rpn_ts[i], maps[i]
+            assert t.is_contiguous() and f.stride(3) == 1 and d.stride(3) == 1 and f.shape[1:3] == d.shape[1:3]
+            p.feat[i], p.feat_sn[i], p.feat_sh[i], p.feat_sw[i] = f.data_ptr(), f.stride(0), f.stride(1), f.stride(2)
+            p.hidden[i] = t.data_ptr()
+            p.dfeat[i], p.dfeat_sn[i], p.dfeat_sh[i], p.dfeat_sw[i] = d.data_ptr(), d.stride(0), d.stride(1), d.stride(2)
+        p.drpn, p.dstride, p.idx, p.count, p.cap = d_rpn.data_ptr(), 64, idx.data_ptr(), count.data_ptr(), cap
+        p.dy_g, p.t_g, p.x_g = dy_g.data_ptr(), t_g.data_ptr(), x_g.data_ptr()
+        p.err_flag = err_flag.data_ptr() if err_flag is not None else None
+        _l.check(ops._launch("aldi_rpn_sparse_gather", lambda: L.aldi_rpn_sparse_gather(_l.ctypes.byref(p), ops._stream())),
+                 "aldi_rpn_sparse_gather")
+        # 1x1 objectness / delta heads: dW += dy^T t, db += colsum(dy), dt = (W^T dy) * (t > 0)
+        ops.wgrad(t_g, dy_g, W.view("rpn_head", "weight", G), cout_store=gh.cout, cin_store=gh.cin, split_parts=W.split_parts)
+        ops.call("aldi_colsum", dy_g, dtc, 1, cap, 0, 64, gh.cout, 1.0, W.view("rpn_head", "bias", G))
+        dt_g = torch.empty_like(t_g)
+        self._dgrad(W, "rpn_head", dy_g, dt_g, mask=t_g)
+        # 3x3 conv: dW[co][tap][ci] += dt^T x_g (a 1x1 layer over the 9 x C gathered columns), db += colsum(dt),
+        # feature-gradient rows dx_g[k][tap][ci] = sum_co dt[k][co] w[co][tap][ci], scattered to (y + r - 1, x + s - 1)
+        ops.wgrad(x_g, dt_g, W.view("rpn_conv", "weight", G), cout_store=gc.cout, cin_store=9 * gc.cin,
+                  split_parts=W.split_parts)
+        ops.call("aldi_colsum", dt_g, dtc, 1, cap, 0, C, gc.cout, 1.0, W.view("rpn_conv", "bias", G))
+        dx_g = torch.empty_like(x_g)
+        ops.conv(dt_g, W.operand("rpn_conv", scatter=True), dx_g, cout_store=9 * C)
+        _l.check(ops._launch("aldi_rpn_sparse_scatter",
+                             lambda: L.aldi_rpn_sparse_scatter(_l.ctypes.byref(p), ops._ptr(dx_g), ops._stream())),
+                 "aldi_rpn_sparse_scatter")
+
     def backward(self, W, G, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch, on_ready=None,
-                 align=None, groups=None):
+                 align=None, groups=None, rpn_rows_per_image=1024, err_flag=None):
         """Accumulate d(loss)/d(params) into the flat gradient buffer G.
         d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64).
         on_ready(tag): called when a bucket of G ("heads", "fpn", "res5", "res4", "res3") has received its last
@@ -570,9 +626,16 @@ class Detector:
         # ---- box head: predictor -> fc2 -> fc1 -> RoIAlign scatter
         dP = {}
         ins = (align or {}).get("ins")
+        # the RPN losses touch only the sampled anchors: run the head's backward on those rows (ALDI_DENSE_RPN_BWD=1: the
+        # dense convolutions over all five levels, as cuDNN does under detectron2 -- kept as the A/B and test reference)
+        sparse_rpn = d_rpn is not None and os.environ.get("ALDI_SPARSE_RPN_BWD", "0") == "1" and W.bottom_up is None
+        dfeat = None
         if dpred is None and ins is None:
-            for l in (2, 3, 4, 5):
-                dP[l] = torch.zeros_like(feats["p%d" % l])
+            if sparse_rpn:
+                dfeat = [torch.zeros(feats["p%d" % l].shape, device=dev, dtype=torch.float32) for l in (2, 3, 4, 5)]
+            else:
+                for l in (2, 3, 4, 5):
+                    dP[l] = torch.zeros_like(feats["p%d" % l])
         else:
             x, f1, f2 = head_saved
             m = f2.shape[2]
@@ -599,13 +662,17 @@ class Detector:
                 ops.roi_align([p[i0:i0 + ni] for p in plv], rois[r0:r0 + rows], roi_batch[r0:r0 + rows],
                               dout=dxv[r0:r0 + rows], dfeats=[d[i0:i0 + ni] for d in dfeat],
                               scales=[1.0 / s for s in FPN_STRIDES[:4]])
+            del dx, df1, df2
+        if sparse_rpn:
+            self._rpn_backward_sparse(W, G, feats, rpn_ts, d_rpn, lv, dfeat, rpn_rows_per_image, err_flag)
+        if dfeat is not None:
             for l, d in zip((2, 3, 4, 5), dfeat):
                 # first writer of dP[l]: the fp32 scatter map becomes the activation-dtype gradient (no memset + add)
                 dP[l] = torch.empty_like(feats["p%d" % l])
                 ops.call("aldi_cast_f32", dP[l], dtc, d, d.numel())
-            del dfeat, dx, df1, df2
-        # ---- RPN head (weights shared over the 5 levels)
-        if d_rpn is not None:
+            del dfeat
+        # ---- RPN head, dense form (weights shared over the 5 levels)
+        if d_rpn is not None and not sparse_rpn:
             for i, l in enumerate((2, 3, 4, 5, 6)):
                 p = feats["p%d" % l]
                 h, w = p.shape[1], p.shape[2]

@@ -86,6 +86,17 @@ class AugParams(ctypes.Structure):
     ]
 
 
+class RpnSparseParams(ctypes.Structure):
+    _fields_ = [
+        ("levels", c_void_p), ("dtype", c_int), ("channels", c_int),
+        ("feat", c_void_p * 5), ("feat_sn", c_ll * 5), ("feat_sh", c_ll * 5), ("feat_sw", c_ll * 5),
+        ("hidden", c_void_p * 5),
+        ("dfeat", c_void_p * 5), ("dfeat_sn", c_ll * 5), ("dfeat_sh", c_ll * 5), ("dfeat_sw", c_ll * 5),
+        ("drpn", c_void_p), ("dstride", c_int), ("idx", c_void_p), ("count", c_void_p), ("cap", c_int),
+        ("dy_g", c_void_p), ("t_g", c_void_p), ("x_g", c_void_p), ("err_flag", c_void_p),
+    ]
+
+
 class RpnLevels(ctypes.Structure):
     _fields_ = [
         ("num_levels", c_int), ("num_anchors", c_int),
@@ -150,6 +161,9 @@ SIGNATURES = {
     "aldi_roi_inference_candidates": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, c_float, P, c_float, P, P, P, P,
                                               P, c_int, P]),
     "aldi_pseudo_label_threshold": (c_int, [P, P, P, P, c_int, c_int, c_float, P, P, P, P, c_int, P]),
+    "aldi_rpn_sparse_compact": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "aldi_rpn_sparse_gather": (c_int, [ctypes.POINTER(RpnSparseParams), P]),
+    "aldi_rpn_sparse_scatter": (c_int, [ctypes.POINTER(RpnSparseParams), P, P]),
     "aldi_rpn_loss": (c_int, [P, ctypes.POINTER(RpnLevels), c_int, P, P, P, P, c_int, c_int, c_float, c_float, c_float,
                               P, c_int, c_int, c_int, P, P]),
     "aldi_roi_loss": (c_int, [P, c_int, c_int, c_int, P, P, P, P, c_int, P, c_float, c_float, c_float, P, c_int, c_int,

@@ -135,7 +135,8 @@ class Split:
         self.parts = list(parts)
 
     def as_strided(self, size, stride, offset=0):
-        return Split([p.as_strided(size, stride, offset) for p in self.parts])
+        """`offset` is relative to the start of each part (torch's as_strided takes an absolute storage offset)."""
+        return Split([p.as_strided(size, stride, p.storage_offset() + offset) for p in self.parts])
 
 
 def split_bf16(x, parts):

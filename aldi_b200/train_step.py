@@ -445,7 +445,11 @@ class B200TrainStep:
 
     def losses_to_host(self, out_keys=None):
         vals = self.loss_acc.cpu()  # one D2H read of the step's loss vector (the reference syncs per loss)
-        if int(self.err_flag.item()):
+        flag = int(self.err_flag.item())
+        if flag & 2:
+            raise _l.AldiError("sparse RPN backward: more non-zero head-gradient rows than its capacity (4 x RPN.BATCH_SIZE_PER_IMAGE "
+                               "per image); run with ALDI_SPARSE_RPN_BWD=0")
+        if flag:
             raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
         return {k: float(vals[j]) for k, j in (out_keys or self._out_keys)}
 
@@ -566,7 +570,7 @@ class B200TrainStep:
         (the step passes 1/num_grad_accum for all of them; the module facade passes what autograd hands back)."""
         d_rpn, dpred, align = self._source_losses(fw, b, w, loss_vec, base, labeled, do_align, self.grad)
         self.det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"],
-                          dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), align=align)
+                          dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), **self._bwd_kw(), align=align)
 
     def _source_losses(self, fw, b, w, loss_vec, base, labeled, do_align, G):
         """-> (d_rpn, dpred, align context); G: where the discriminators' last-layer gradients go (they are produced by
@@ -835,7 +839,7 @@ class B200TrainStep:
             self.debug = {"fw": fw_t, "t_pred": t_pred, "t_rpn_out": t_rpn_out, "labels": dlabels, "stats": dstats,
                           "pseudo": pseudo}
         det.backward(W, self.grad, feats, saved, rpn_ts, d_rpn, lv, head_saved, dpred, rois, roi_batch,
-                     on_ready=self._bucket_ready(), groups=groups)
+                     on_ready=self._bucket_ready(), **self._bwd_kw(), groups=groups)
 
     # ---- one distillation micro-batch (aldi/distill.py:144-278) ------------------------------------------
     def _distill_body(self, bw, bs, gscale, pass_id, base=SLOT_BASE["distill"]):
@@ -877,7 +881,7 @@ class B200TrainStep:
         fw = ctx["fw"]
         d_rpn, dpred = self._distill_losses(ctx, w, loss_vec, base)
         self.det.backward(self.student, self.grad, fw["feats"], fw["saved"], fw["rpn_ts"], d_rpn, fw["lv"], fw["head_saved"],
-                          dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready())
+                          dpred, fw["rois"], fw["roi_batch"], on_ready=self._bucket_ready(), **self._bwd_kw())
 
     def _distill_losses(self, ctx, w, loss_vec, base):
         cfg, det = self.cfg, self.det
@@ -989,6 +993,11 @@ class B200TrainStep:
             a = it / warmup_iters
             lr *= warmup_factor * (1 - a) + a
         return lr
+
+    def _bwd_kw(self):
+        # sparse RPN backward: a strict bound on the locations with a non-zero head gradient per image -- 256 sampled
+        # anchors of the hard loss + 256 valid entries and 128 x 4 flat delta entries of the distillation loss (T1)
+        return {"rpn_rows_per_image": 4 * self.cfg.rpn_batch, "err_flag": self.err_flag}
 
     def _bucket_ready(self):
         """Gradient buckets become final only in the step's LAST backward; earlier micro-batches just accumulate."""

@@ -70,6 +70,8 @@ int aldi_pack_weight(const float* w, const float* scale, void* out, int out_dtyp
  *   kind 1: data-gradient operand pack, FrozenBN scale derived in place from bn_w / bn_var (NULL: no scale)
  *   kind 2: FrozenBN fold: out[i] = bn_w*rsqrt(bn_var+eps) (scale), out2[i] = bn_b - bn_mean*scale (shift), i < cout
  *   kind 3: out2[i] = w[i], i < cout (conv bias -> epilogue shift)
+ *   kind 5: transposed forward operand out[(t*cin + ci)][co] = w[co][t][ci], zero padded to cout_p columns (the
+ *           "scatter" operand of the sparse RPN backward: a 1x1 conv from cout channels to taps*cin outputs)
  *   kind 4: stem weights (cout,7,7,3) -> bf16 [cout_p][4][4][2][2][4] taps over the space-to-depth map
  *           of aldi_stem_s2d (row tap a, column tap b, r+1 = 2a+dy, s+1 = 2b+dx, zero where r/s = -1, c = 3) */
 typedef struct {
@@ -275,6 +277,41 @@ int aldi_distill_rpn_loss(const float* student_rpn_out, const float* teacher_rpn
                           int n_images, const signed char* labels, const int* stats, float obj_temperature,
                           float w_obj, float w_reg, float gscale, void* drpn, int dtype, int dstride, int accumulate,
                           float* loss_out, void* stream);
+/* ---- sparse backward of the RPN head (csrc/rpn_sparse.cu) ---------------------------------------------------------
+ * The gradient RPN.losses (detectron2) and aldi/distill.py:193-229 send into the head outputs is non-zero only at the
+ * anchors `subsample_labels` picked (256 per image): the non-zero rows of `drpn` (n_images * total_locs rows) are
+ * compacted, the operands of the head's two layers gathered for those locations, the GEMMs run on the gathered rows
+ * (aldi_conv_tc / aldi_wgrad_tc on a 1 x 1 x cap x C image) and the feature-gradient rows scattered back.
+ *   compact: idx[cap] <- row indices with a non-zero among the first `channels` columns (-1 beyond *count)
+ *   gather : dy_g[cap][64] = drpn rows, t_g[cap][C] = hidden rows, x_g[cap][9][C] = 3x3 neighbourhoods of the FPN
+ *            feature (zeros outside the map = the conv's padding; all-zero rows beyond *count); sets bit 1 of
+ *            *err_flag if *count > cap (rows would be lost)
+ *   scatter: dfeat[img, y+r-1, x+s-1, :] += dx_g[k][r*3+s][:]   (fp32 atomics; the map RoIAlign backward adds into)
+ * Per level: `feat` the layer input p_l (strided channels-last view: p6 is p5[:, ::2, ::2]), `hidden` the ReLU'd 3x3
+ * output (contiguous), `dfeat` the fp32 gradient map of p_l (p6: the strided view of p5's).                          */
+typedef struct {
+  const aldi_rpn_levels* levels;
+  int dtype, channels;                   /* activation dtype of feat / hidden / drpn / *_g; C (multiple of 8) */
+  const void* feat[5];
+  long long feat_sn[5], feat_sh[5], feat_sw[5];
+  const void* hidden[5];
+  float* dfeat[5];
+  long long dfeat_sn[5], dfeat_sh[5], dfeat_sw[5];
+  const void* drpn;
+  int dstride;                           /* 64 */
+  const int* idx;
+  const int* count;
+  int cap;
+  void* dy_g;
+  void* t_g;
+  void* x_g;
+  int* err_flag;                         /* nullable */
+} aldi_rpn_sparse_params;
+int aldi_rpn_sparse_compact(const void* drpn, int dtype, int n_images, int total_locs, int dstride, int channels, int cap,
+                            int* idx, int* count, void* stream);
+int aldi_rpn_sparse_gather(const aldi_rpn_sparse_params* p, void* stream);
+int aldi_rpn_sparse_scatter(const aldi_rpn_sparse_params* p, const void* dx_g, void* stream);
+
 /* aldi/distill.py:231-278: loss_out[0] += loss_cls_ce (CE or KL), loss_out[1] += loss_roih_l1 */
 int aldi_distill_roi_loss(const float* student_pred, const float* teacher_pred, int pred_stride, int m,
                           int num_classes, const int* row_class, const int* counts, int n_images,
