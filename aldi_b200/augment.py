@@ -117,10 +117,14 @@ class StrongAugmenter:
             q.mic_mask, q.mic_h, q.mic_w = keep.data_ptr(), int(keep.shape[0]), int(keep.shape[1])
         L = _l.load()
         nbytes = int(L.aldi_strong_augment_workspace_bytes(q.h, q.w))
-        ws = self._ws.get((src.device, nbytes))
+        # one workspace per (device, size, STREAM): apply() is called from the compute stream and from the copy stream
+        # (prefetch of the next micro-batch), and two streams must not share the blur scratch planes
+        cur = torch.cuda.current_stream()
+        key = (src.device, nbytes, cur.cuda_stream)
+        ws = self._ws.get(key)
         if ws is None:
-            ws = self._ws[(src.device, nbytes)] = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            ws = self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+        stream = ctypes.c_void_p(cur.cuda_stream)
         _l.check(L.aldi_strong_augment(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), ctypes.byref(q),
                                        ctypes.c_void_p(ws.data_ptr()), nbytes, stream), "aldi_strong_augment")
         return dst

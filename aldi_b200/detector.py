@@ -292,9 +292,12 @@ class Detector:
     RPN_CH = 16    # fp32 head output row: 3 logits + 12 deltas (+1 pad)
     PRED_CH = 64   # fp32 predictor row: K+1 logits + 4K deltas, padded
 
-    def __init__(self, num_classes=8, anchor_sizes=None):
+    def __init__(self, num_classes=8, anchor_sizes=None, pixel_mean=None, pixel_std=None):
         self.K = num_classes
         self.cells = cell_anchors(anchor_sizes)
+        # MODEL.PIXEL_MEAN / PIXEL_STD of the cfg (detectron2 GeneralizedRCNN.preprocess_image)
+        self.pixel_mean = tuple(pixel_mean) if pixel_mean is not None else PIXEL_MEAN
+        self.pixel_std = tuple(pixel_std) if pixel_std is not None else PIXEL_STD
 
     # ---- generic layer ------------------------------------------------------------------------------
     @staticmethod
@@ -320,7 +323,7 @@ class Detector:
             outs = W.bottom_up.forward(images_u8, sizes, keep_masks=keep_masks, save=save)
             feats = {"res%d" % (i + 2): outs[i] for i in range(4)}
             return self._fpn_forward(W, feats, {} if save else None, save)
-        mean, std = ops.host_floats(PIXEL_MEAN), ops.host_floats(PIXEL_STD)
+        mean, std = ops.host_floats(self.pixel_mean), ops.host_floats(self.pixel_std)
         g = W.geom["stem"]
         ho, wo = hp // 2, wp // 2
         stem_out = torch.empty(n, ho, wo, 64, device=dev, dtype=dt)
@@ -628,7 +631,7 @@ class Detector:
         ins = (align or {}).get("ins")
         # the RPN losses touch only the sampled anchors: run the head's backward on those rows (ALDI_DENSE_RPN_BWD=1: the
         # dense convolutions over all five levels, as cuDNN does under detectron2 -- kept as the A/B and test reference)
-        sparse_rpn = d_rpn is not None and os.environ.get("ALDI_SPARSE_RPN_BWD", "0") == "1" and W.bottom_up is None
+        sparse_rpn = d_rpn is not None and os.environ.get("ALDI_DENSE_RPN_BWD") != "1" and W.bottom_up is None
         dfeat = None
         if dpred is None and ins is None:
             if sparse_rpn:

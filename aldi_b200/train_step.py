@@ -189,6 +189,10 @@ class MicroBatch:
                 else:
                     assert weak_source is not None, "an image-less strong item needs its weak micro-batch"
                     src = weak_source.images[i]
+                    if weak_source._copied is not None:
+                        # the weak images may have been staged on ANOTHER stream (this load can be a prefetch on the copy
+                        # stream): derive the strong view only after their copies have landed
+                        torch.cuda.current_stream().wait_event(weak_source._copied)
                 augmenter.apply(src, self.images[i], params, valid_hw=(hs[i], ws[i]))
             if img is not None and not img.is_cuda:
                 nbytes += img.numel()
@@ -260,7 +264,7 @@ class B200TrainStep:
             raise NotImplementedError("MODEL.BACKBONE %s: ResNet-50-FPN and ConvNeXt-FPN are built" % cfg.backbone)
         self.layout = FlatLayout(cfg.num_classes, align=cfg.align_spec(),
                                  bottom_up_channels=tuple(cfg.convnext_dims) if convnext else None)
-        self.det = Detector(cfg.num_classes, cfg.anchor_sizes)
+        self.det = Detector(cfg.num_classes, cfg.anchor_sizes, cfg.pixel_mean, cfg.pixel_std)
         flat = self.layout.pack_state_dict(state_dict).to(self.device)
         tsd = state_dict if teacher_state_dict is None else teacher_state_dict
         tflat = flat.clone() if teacher_state_dict is None else self.layout.pack_state_dict(tsd).to(self.device)
@@ -275,7 +279,9 @@ class B200TrainStep:
                                         device=self.device, pixel_mean=cfg.pixel_mean, pixel_std=cfg.pixel_std)
 
             bu_s, bu_t = bottom_up(state_dict), bottom_up(tsd)
-            self.keep_rng = torch.Generator().manual_seed(0)    # DropPath masks (host-drawn, aldi/backbone.py:176-181)
+            # DropPath masks (host-drawn, aldi/backbone.py:176-181): every data-parallel rank draws its own
+            rank = dist.get_rank(process_group) if process_group is not None else 0
+            self.keep_rng = torch.Generator().manual_seed(rank)
             self.keep_override = None                           # test seam: list of per-forward mask lists
         self.student = DetectorWeights(self.layout, flat, self.dtype, bottom_up=bu_s, split_parts=split_parts)
         self.teacher = DetectorWeights(self.layout, tflat, self.dtype, bottom_up=bu_t, split_parts=split_parts)
@@ -327,6 +333,7 @@ class B200TrainStep:
         # items that carry "aug_params" 
         self.augmenters = {}
         self._teacher_out = None   # outputs of the last teacher pass, consumed by the fused student pass
+        self._teacher_outs = {}    # ... per captured teacher graph: a replay writes into THAT capture's tensors
 
     # ---- aldi/ema.py:52-57 -------------------------------------------------------------------------
     def ema_update(self, it):
@@ -513,6 +520,12 @@ class B200TrainStep:
             return fn()
         if chain is None:
             chain = self._graphs[key] = self._capture(fn)
+            if key[0] == "teacher":
+                self._teacher_outs[key] = self._teacher_out
+        if key[0] == "teacher":
+            # the fused student pass that follows reads `_teacher_out`: point it at the tensors THIS graph writes (another
+            # shape's teacher pass may have run, eagerly or captured, in between)
+            self._teacher_out = self._teacher_outs[key]
         for seg in chain:
             if isinstance(seg, str):
                 self.reducer.ready(seg)
@@ -1086,12 +1099,60 @@ class B200TrainStep:
         w.refresh()
         return missing + bad_shape, unexpected
 
+    _OPT_BUFFERS = ("momentum_buf", "exp_avg_sq", "bu_momentum", "bu_exp_avg", "bu_exp_avg_sq")
+
     def optimizer_state(self):
-        """SGD momentum buffer keyed like the parameters (the `optimizer` checkpointable of the reference trainer)."""
-        return {"momentum_buffer": self.momentum_buf.detach().cpu().clone(), "iteration": self.iter}
+        """Everything the optimizer needs to resume (the `optimizer` checkpointable of the reference trainer): the
+        iteration and EVERY flat state buffer -- SGD momentum / AdamW first moment (`momentum_buf`), AdamW second moment,
+        and the ConvNeXt bottom-up's own buffers.  `state` repeats the detector's buffers per parameter under the
+        Detectron2 key names (torch.optim naming: momentum_buffer | exp_avg, exp_avg_sq) for tools that read those."""
+        adamw = self.cfg.optimizer.upper() == "ADAMW"
+        out = {"format": "aldi_b200.flat.v2", "optimizer": self.cfg.optimizer.upper(), "iteration": self.iter, "buffers": {}}
+        for name in self._OPT_BUFFERS:
+            t = getattr(self, name, None)
+            if t is not None:
+                out["buffers"][name] = t.detach().cpu().clone()
+        names = {"momentum_buf": "exp_avg" if adamw else "momentum_buffer", "exp_avg_sq": "exp_avg_sq"}
+        state = {}
+        for buf, tname in names.items():
+            t = out["buffers"].get(buf)
+            if t is None:
+                continue
+            for (layer, field), (off, n, key, shape) in self.layout.entries.items():
+                if off < self.nt and field in ("weight", "bias"):
+                    state.setdefault(key, {})[tname] = self.layout.from_internal(layer, field, t[off:off + n], shape)
+        out["state"] = state
+        out["momentum_buffer"] = out["buffers"]["momentum_buf"]        # v1 readers
+        return out
 
     def load_optimizer_state(self, state):
-        self.momentum_buf.copy_(state["momentum_buffer"].to(self.momentum_buf.device))
+        """Accepts what `optimizer_state` writes (v2; v1 files with only `momentum_buffer` + `iteration` load what they
+        hold).  A torch.optim state_dict (index-keyed `state` + `param_groups`, what the reference writes) cannot be
+        mapped onto the flat buffers without the reference's parameter order: it is skipped with a warning and the
+        optimizer restarts from zero moments at the stored iteration."""
+        import logging
+        log = logging.getLogger("aldi_b200")
+        if not isinstance(state, dict) or ("param_groups" in state and "buffers" not in state):
+            log.warning("optimizer state in torch.optim format: not loadable into the flat buffers, optimizer state reset")
+            return
+        bufs = dict(state.get("buffers") or {})
+        if not bufs and "momentum_buffer" in state:
+            bufs["momentum_buf"] = state["momentum_buffer"]
+        if state.get("optimizer") and state["optimizer"] != self.cfg.optimizer.upper():
+            log.warning("optimizer state was written by %s, this step runs %s: state reset", state["optimizer"],
+                        self.cfg.optimizer.upper())
+            bufs = {}
+        for name in self._OPT_BUFFERS:
+            dst = getattr(self, name, None)
+            if dst is None:
+                continue
+            src = bufs.get(name)
+            if src is None or src.numel() != dst.numel():
+                if bufs:
+                    log.warning("optimizer state: buffer %s missing or of another size in the checkpoint; zeroed", name)
+                dst.zero_()
+                continue
+            dst.copy_(src.to(dst.device).reshape(dst.shape))
         self.iter = int(state.get("iteration", self.iter))
 
 

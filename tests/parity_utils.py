@@ -114,3 +114,19 @@ def pseudo_to_device(insts, device):
         sc[i, :k] = inst.scores
         cnt[i] = k
     return GroundTruth(b.to(device), c.to(device), cnt.to(device), gmax, sc.to(device))
+
+
+def log_student_proposals(student):
+    """Forward hook on the oracle student's RPN: one entry per forward = [proposal boxes per image]."""
+    log = []
+    student.proposal_generator.register_forward_hook(
+        lambda m, i, o: log.append([p.proposal_boxes.tensor.detach().clone() for p in o[0]]))
+    return log
+
+
+def proposal_override(log, n_source_mb, n_distill_mb, n_align_mb=0):
+    """-> B200TrainStep.proposal_override: the oracle's proposals keyed by the step's pass ids (student forwards run in
+    plan order: source micro-batches, alignment passes, then the distillation micro-batches as 100 + index)."""
+    ids = list(range(n_source_mb + n_align_mb)) + [100 + n_source_mb + n_align_mb + j for j in range(n_distill_mb)]
+    assert len(log) == len(ids), (len(log), ids)
+    return dict(zip(ids, log))

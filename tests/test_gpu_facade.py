@@ -21,6 +21,9 @@ def _cfg(opts=(), distiller="ALDIDistiller"):
     from aldi_b200.config import add_aldi_config, get_cfg
     cfg = get_cfg()
     add_aldi_config(cfg)
+    # the RPN top-k values of configs/detectron2/Base-RCNN-FPN.yaml:14-20 (the bare defaults are the C4 model's 12000 / 6000)
+    cfg.merge_from_list(["MODEL.RPN.PRE_NMS_TOPK_TRAIN", 2000, "MODEL.RPN.PRE_NMS_TOPK_TEST", 1000,
+                         "MODEL.RPN.POST_NMS_TOPK_TRAIN", 1000, "MODEL.RPN.POST_NMS_TOPK_TEST", 1000])
     cfg.merge_from_list(["MODEL.ROI_HEADS.NUM_CLASSES", 8, "SOLVER.IMS_PER_GPU", 2, "EMA.ENABLED", True, "EMA.START_ITER", -1,
                          "DOMAIN_ADAPT.DISTILL.DISTILLER_NAME", distiller, "MODEL.DEVICE", "cuda"] + list(opts))
     return cfg

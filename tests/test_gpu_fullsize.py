@@ -121,7 +121,8 @@ def test_every_tensor_core_launch_of_a_full_size_step_is_within_one_bf16_ulp():
             got, want = out[..., :cs].float(), ref[..., :cs]
             rms = float(want.pow(2).mean().sqrt())
             rel = 2.0 ** -8 if out.dtype == torch.bfloat16 else 1e-4
-            ratio = float(((got - want).abs() / (rel * want.abs() + 2e-5 * rms + 1e-30)).max())
+            # + the fp32 summation-order noise of the two kernels (K up to 12544 products per output): 1e-4 of the rms
+            ratio = float(((got - want).abs() / (rel * want.abs() + 1e-4 * rms + 1e-30)).max())
         else:
             dw = c["dw"]
             before = dw.clone()

@@ -16,14 +16,15 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-3
 
 
-TC_MODES = ["fp32", "bf16x3", "bf16x6"]
+TC_MODES = ["fp32", "bf16x6"]
 
 
-def run_device(sd_s, sd_t, data, pseudo_override=None, dtype="fp32", **cfg_kw):
+def run_device(sd_s, sd_t, data, pseudo_override=None, dtype="fp32", proposal_override=None, **cfg_kw):
     from aldi_b200.train_step import B200TrainStep, StepConfig
     cfg = StepConfig(dtype=dtype, ema_start_iter=-1, **cfg_kw)
     step = B200TrainStep(cfg, sd_s, teacher_state_dict=sd_t)
     step.pseudo_override = pseudo_override
+    step.proposal_override = proposal_override
     random.seed(1234)
     losses = step.run_model(data)
     losses = dict(losses.items())
@@ -84,8 +85,7 @@ def test_source_only_step_matches_oracle(dtype):
 
 
 @pytest.mark.parametrize("n_l,n_u,mb,h,w,dtype", [(2, 2, 2, 128, 160, "fp32"), (3, 3, 2, 96, 96, "fp32"),
-                                                  (2, 2, 2, 128, 160, "bf16x3"), (2, 2, 2, 128, 160, "bf16x6"),
-                                                  (3, 3, 2, 96, 96, "bf16x6")])
+                                                  (2, 2, 2, 128, 160, "bf16x6"), (3, 3, 2, 96, 96, "bf16x6")])
 def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w, dtype):
     """ALDI++ step: source + distillation micro-batches (incl. the uneven T9 case)."""
     sd_s, sd_t, ls, uw, us = pu.make_inputs(21 + n_l, n_l, n_u, h, w)
@@ -94,6 +94,7 @@ def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w, dtype):
     pu.install_device_sampler(pu.predict_seed_log(1234, n_src_mb, n_dst_mb))
     student, teacher = pu.oracle_models(sd_s, sd_t)
     dist = aldi_ref.ALDIDistiller(teacher, student, **pu.SOFT)
+    prop_log = pu.log_student_proposals(student)
     uw_o, us_o = pu.to_d2(uw, False), pu.to_d2(us, False)
     with d2.EventStorage():
         ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, pu.to_d2(ls, True), uw_o, us_o), mb, False,
@@ -103,8 +104,16 @@ def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w, dtype):
     # match.  The device computes its own pseudo labels (checked below against the oracle's) but the rest of the
     # step consumes the oracle's boxes so that every downstream selection sees identical inputs.
     override = [pu.pseudo_to_device([d["instances"] for d in uw_o[i:i + mb]], "cuda") for i in range(0, n_u, mb)]
-    step, dev_losses = run_device(sd_s, sd_t, (None, ls, uw, us), pseudo_override=override, ims_per_gpu=mb, dtype=dtype)
+    # ... and likewise the student's RPN proposals (the device's own are compared with the oracle's right below)
+    step, dev_losses = run_device(sd_s, sd_t, (None, ls, uw, us), pseudo_override=override, ims_per_gpu=mb, dtype=dtype,
+                                  proposal_override=pu.proposal_override(prop_log, n_src_mb, n_dst_mb))
     assert step.seed_log == pu.predict_seed_log(1234, n_src_mb, n_dst_mb)
+    for pid, want in step.proposal_override.items():
+        boxes, count = step.proposal_log[pid]
+        for i, wb in enumerate(want):
+            got = boxes[i, :int(count[i])].cpu()
+            same = got.shape == wb.shape and bool(torch.isclose(got, wb, rtol=1e-4, atol=1e-2).all(dim=1).float().mean() > 0.98)
+            assert abs(got.shape[0] - wb.shape[0]) <= 2 and (same or got.shape != wb.shape), ("RPN proposals", pid, i)
     # --- last distillation micro-batch: intermediate tensors, in pipeline order (first mismatch = culprit)
     dbg = step.debug
     n_last = len(uw) - (len(uw) - 1) // mb * mb
@@ -148,15 +157,18 @@ def test_aldi_step_matches_oracle(n_l, n_u, mb, h, w, dtype):
 def test_empty_pseudo_labels(dtype):
     """T2: no detection above the threshold -> 256 negatives per image still feed loss_obj_bce; loss_rpn_l1 == 0."""
     sd_s, sd_t, ls, uw, us = pu.make_inputs(77, 0, 2, 96, 128)
-    step, dev_losses = run_device(sd_s, sd_t, (None, None, uw, us), ims_per_gpu=2, pseudo_threshold=0.9999, dtype=dtype)
-    assert step.debug["pseudo"].counts.cpu().tolist() == [0, 0]
-    pu.install_device_sampler(step.seed_log)
+    pu.install_device_sampler(pu.predict_seed_log(1234, 0, 1))
     student, teacher = pu.oracle_models(sd_s, sd_t)
     dist = aldi_ref.ALDIDistiller(teacher, student, pseudo_label_threshold=0.9999, **pu.SOFT)
+    prop_log = pu.log_student_proposals(student)
     with d2.EventStorage():
         ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, None, pu.to_d2(uw, False), pu.to_d2(us, False)), 2,
                                                    False, lambda l: l.backward())
     d2.set_sample_chooser(None)
+    step, dev_losses = run_device(sd_s, sd_t, (None, None, uw, us), ims_per_gpu=2, pseudo_threshold=0.9999, dtype=dtype,
+                                  proposal_override=pu.proposal_override(prop_log, 0, 1))
+    assert step.seed_log == pu.predict_seed_log(1234, 0, 1)
+    assert step.debug["pseudo"].counts.cpu().tolist() == [0, 0]
     check_losses(dev_losses, ora)
     assert dev_losses["loss_rpn_l1_distill"] == 0.0
     check_grads(step, student)
@@ -414,3 +426,14 @@ def test_convnext_trainer_runs():
         DetectionCheckpointerWithEMA(other.step_impl, tmp).resume_or_load("", resume=True)
         for a, b in ((other.step_impl.student, trainer.step_impl.student), (other.step_impl.teacher, trainer.step_impl.teacher)):
             assert torch.equal(a.flat, b.flat) and torch.equal(a.bottom_up.flat, b.bottom_up.flat)
+        # ... and EVERY optimizer buffer (AdamW moments of the detector and of the bottom-up) plus the iteration: a resume
+        # that dropped the second moments would restart at bias-correction ~1 with v = 0 and take huge first steps
+        a, b = other.step_impl, trainer.step_impl
+        assert a.iter == b.iter == 3
+        for name in ("momentum_buf", "exp_avg_sq", "bu_exp_avg", "bu_exp_avg_sq"):
+            assert float(getattr(b, name).abs().max()) > 0, name
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        st = b.optimizer_state()
+        assert set(st["state"]["roi_heads.box_head.fc1.weight"]) == {"exp_avg", "exp_avg_sq"}
+        assert st["state"]["roi_heads.box_head.fc1.weight"]["exp_avg"].shape == sd["model"]["roi_heads.box_head.fc1.weight"].shape
+        a.load_optimizer_state({"state": {0: {}}, "param_groups": [{}]})      # torch.optim format: skipped, not a KeyError
