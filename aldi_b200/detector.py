@@ -543,33 +543,7 @@ class Detector:
         self._dgrad(W, "img_align.conv0", ndh, dP_layer, accumulate=True)
 
     # ---- backward -------------------------------------------------------------------------------------
-    # ---- weight gradients on a second stream (ALDI_WGRAD_STREAM=1) --------------------------------------------------------
-    # A layer's weight gradient needs only (x, dy) and nothing in the backward waits for it, while the data gradient that
-    # continues the chain is a short persistent kernel whose drain leaves SMs idle: issued on a side stream, the weight
-    # gradient's CTAs fill those SMs.  The operands are held until the streams join (the caching allocator would otherwise
-    # hand a freed dy to the next main-stream kernel while the side stream still reads it).
-    def _side_begin(self, dev):
-        if os.environ.get("ALDI_WGRAD_STREAM") != "1" or dev.type != "cuda":
-            return None
-        if getattr(self, "_side", None) is None:
-            self._side, self._held = torch.cuda.Stream(device=dev), []
-        return self._side
-
-    def _side_join(self):
-        if getattr(self, "_side", None) is not None and self._held:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._held = []
-
     def _wgrad(self, W, G, name, x, dy):
-        side = self._side_begin(dy.device)
-        if side is None:
-            return self._wgrad_now(W, G, name, x, dy)
-        side.wait_stream(torch.cuda.current_stream())
-        self._held.append((x, dy))
-        with torch.cuda.stream(side):
-            self._wgrad_now(W, G, name, x, dy)
-
-    def _wgrad_now(self, W, G, name, x, dy):
         g = W.geom[name]
         xv = x[:, ::2, ::2, :] if (g.stride == 2 and g.k == 1) else x
         # bias gradient: aldi_wgrad_tc can sum the dy tiles it already holds in shared memory (dbias=).  Measured: the
@@ -647,12 +621,7 @@ class Detector:
         d_rpn: (N, total_locs, 64) activation-dtype gradient of the RPN head outputs; dpred: (M, 64).
         on_ready(tag): called when a bucket of G ("heads", "fpn", "res5", "res4", "res3") has received its last
         contribution of this backward (data_parallel.GradReducer starts that bucket's all-reduce)."""
-        user_ready = on_ready or (lambda tag: None)
-
-        def on_ready(tag):
-            self._side_join()          # the bucket is final only when its side-stream weight gradients have landed
-            user_ready(tag)
-
+        on_ready = on_ready or (lambda tag: None)
         dt = W.dtype
         dtc = _l.BF16 if dt == torch.bfloat16 else _l.F32
         dev = feats["p2"].device

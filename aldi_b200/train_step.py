@@ -303,7 +303,7 @@ class B200TrainStep:
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pg = process_group
         self.reducer = GradReducer(self.layout, self.grad, process_group)
-        if self.reducer.active and os.environ.get("ALDI_NO_PDL") is None:
+        if self.reducer.active:
             # under data parallelism NCCL kernels share the SMs with the step: early-launched dependents only park there
             # (measured at 8 GPUs: 2103 images/s without programmatic dependent launch, 2095 with)
             _l.load().aldi_set_pdl(0)

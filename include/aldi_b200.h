@@ -36,8 +36,9 @@ int aldi_abi_version(void);
 /* number of kernels of THIS library launched since load / since the last reset */
 unsigned long long aldi_launch_count(void);
 void aldi_reset_launch_count(void);
-/* programmatic dependent launch of the library's kernels (default on; ALDI_NO_PDL=1 in the environment turns it off).
- * The data-parallel step turns it off: with NCCL kernels sharing the SMs, early-launched dependents only park on them. */
+/* programmatic dependent launch of the library's kernels: off by default (ALDI_PDL=1 in the environment turns it on --
+ * measured neutral on the graph-replayed step); the data-parallel step keeps it off explicitly: with NCCL kernels
+ * sharing the SMs, early-launched dependents only park on them. */
 void aldi_set_pdl(int on);
 
 /* ---- EMA teacher update: aldi/ema.py:32-57 (EMA._update_ema / _init_ema_weights) -------------
