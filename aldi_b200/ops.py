@@ -351,7 +351,15 @@ def _arg(a):
 def call(name, *args):
     L = _l.load()
     cargs = [_arg(a) for a in args]
-    _l.check(_launch(name, lambda: getattr(L, name)(*cargs, _stream())), name)
+    nbytes = 0.0
+    if _PROFILER is not None:
+        # algorithmic bytes of an elementwise / gather kernel ~ every distinct tensor argument touched once
+        seen = set()
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.data_ptr() not in seen:
+                seen.add(a.data_ptr())
+                nbytes += a.numel() * a.element_size()
+    _l.check(_launch(name, lambda: getattr(L, name)(*cargs, _stream()), 0.0, nbytes), name)
 
 
 def host_floats(vals):

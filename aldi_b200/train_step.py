@@ -279,10 +279,9 @@ class B200TrainStep:
                                         device=self.device, pixel_mean=cfg.pixel_mean, pixel_std=cfg.pixel_std)
 
             bu_s, bu_t = bottom_up(state_dict), bottom_up(tsd)
-            # DropPath masks (host-drawn, aldi/backbone.py:176-181): every data-parallel rank draws its own
-            rank = dist.get_rank(process_group) if process_group is not None else 0
-            self.keep_rng = torch.Generator().manual_seed(rank)
-            self.keep_override = None                           # test seam: list of per-forward mask lists
+        # DropPath masks (host-drawn, aldi/backbone.py:176-181): every data-parallel rank draws its own
+        self.keep_rng = torch.Generator().manual_seed(dist.get_rank(process_group) if process_group is not None else 0)
+        self.keep_override = None                               # test seam: list of per-forward mask lists
         self.student = DetectorWeights(self.layout, flat, self.dtype, bottom_up=bu_s, split_parts=split_parts)
         self.teacher = DetectorWeights(self.layout, tflat, self.dtype, bottom_up=bu_t, split_parts=split_parts)
         self.student.enable_dgrad()
@@ -334,6 +333,8 @@ class B200TrainStep:
         self.augmenters = {}
         self._teacher_out = None   # outputs of the last teacher pass, consumed by the fused student pass
         self._teacher_outs = {}    # ... per captured teacher graph: a replay writes into THAT capture's tensors
+        self._mask_slots, self._mask_events = {}, {}     # DropPath mask blocks per micro-batch body (see _keep_masks)
+        self._mask_key, self._mask_idx = None, 0
 
     # ---- aldi/ema.py:52-57 -------------------------------------------------------------------------
     def ema_update(self, it):
@@ -507,8 +508,9 @@ class B200TrainStep:
         sampling seed and salts included, so a replay sees the new step's data.  The step's LAST backward under
         data parallelism is captured as a CHAIN of graphs cut where a gradient bucket becomes final: the NCCL
         all-reduce of that bucket is issued eagerly between two replays and overlaps the next segment."""
+        self._mask_key, self._mask_idx = key, 0
         if not (self.cfg.cuda_graph and self.device.type == "cuda") or self.debug is not None or self.pseudo_override \
-                or self.proposal_override or self.student.bottom_up is not None:   # DropPath masks are host-drawn: eager
+                or self.proposal_override or self.keep_override is not None:
             if self.profile_spin_cycles:
                 # profiling aid: park the GPU on a spin kernel while the host queues this micro-batch, so the kernels
                 # then run back to back (warm L2, no launch gaps) and per-launch CUDA events time exactly their durations
@@ -526,12 +528,16 @@ class B200TrainStep:
             # the fused student pass that follows reads `_teacher_out`: point it at the tensors THIS graph writes (another
             # shape's teacher pass may have run, eagerly or captured, in between)
             self._teacher_out = self._teacher_outs[key]
+        self._redraw_masks(key)
         for seg in chain:
             if isinstance(seg, str):
                 self.reducer.ready(seg)
             else:
                 seg.replay()
                 self.graph_replays += 1
+        if key in self._mask_slots:
+            self._mask_events[key] = torch.cuda.Event()
+            self._mask_events[key].record()
 
     def _capture(self, fn):
         import gc
@@ -669,12 +675,44 @@ class B200TrainStep:
         return out
 
     def _keep_masks(self, W, n):
-        """DropPath factors of one training-mode forward of a ConvNeXt bottom-up (None for the ResNet)."""
+        """DropPath factors of one training-mode forward of a ConvNeXt bottom-up (None for the ResNet).
+        Drawn on the host like `torch.bernoulli_` in the reference (aldi/backbone.py:176-181) but DEVICE-RESIDENT: every
+        mask request of a micro-batch body owns a pinned host block and a device block; the body copies one onto the
+        other (a memcpy node when the body is captured), and `_redraw_masks` refreshes the pinned blocks before each graph
+        replay -- so a replayed ConvNeXt step sees fresh masks and nothing about DropPath forces eager execution."""
         if W.bottom_up is None:
             return None
         if self.keep_override is not None:
             return self.keep_override.pop(0)
-        return W.bottom_up.draw_keep_masks(n, self.keep_rng)
+        rates = W.bottom_up.drop_rates
+        slots = self._mask_slots.setdefault(self._mask_key, [])
+        i = self._mask_idx
+        self._mask_idx += 1
+        if i == len(slots):
+            host = torch.zeros(len(rates), n)
+            slots.append((host.pin_memory() if self.device.type == "cuda" else host,
+                          torch.zeros(len(rates), n, device=self.device), rates))
+        host, dev, _ = slots[i]
+        self._draw_into(host, rates)
+        dev.copy_(host, non_blocking=True)
+        return [None if r <= 0 else dev[b] for b, r in enumerate(rates)]
+
+    def _draw_into(self, host, rates):
+        n = host.shape[1]
+        for b, r in enumerate(rates):
+            if r > 0:
+                host[b] = (torch.rand(n, generator=self.keep_rng) < (1 - r)).float() / (1 - r)
+
+    def _redraw_masks(self, key):
+        """Before a graph replay: new DropPath draws into the pinned blocks the captured copies read."""
+        slots = self._mask_slots.get(key)
+        if not slots:
+            return
+        ev = self._mask_events.get(key)
+        if ev is not None:
+            ev.synchronize()          # the previous replay's copies have read the pinned blocks
+        for host, _, rates in slots:
+            self._draw_into(host, rates)
 
     def _label_anchors(self, lv, b, gt, site):
         cfg, n = self.cfg, b.n
