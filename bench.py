@@ -491,9 +491,9 @@ def run_ours(args):
         # `ncu --metrics ...dram__bytes_{read,write}.sum` over `bench.py --ncu-step`); algorithmic bytes beside it
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_traffic.json")))
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_step_traffic.json")))
             traffic = tj["kernels"]["conv_tc"]["dram_bytes_per_launch"]
-            traffic_src = "profiles/r01_step_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d launches)" \
+            traffic_src = "profiles/r02_step_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d launches)" \
                 % tj["kernels"]["conv_tc"]["launches"]
         except Exception:
             pass

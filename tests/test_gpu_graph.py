@@ -81,3 +81,32 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     DetectionCheckpointerWithEMA(c, str(tmp_path / "fresh")).resume_or_load(path, resume=False)
     nt = c.layout.numel
     assert torch.equal(c.student.flat[:nt], saved_teacher[:nt])
+
+
+def test_convnext_step_replays_as_graphs_with_fresh_droppath_masks():
+    """BASELINE configs[4] inside the graph machinery: the DropPath factors are drawn on the host per forward (as
+    torch.bernoulli_ does in the reference, aldi/backbone.py:176-181) but live in device blocks refreshed from pinned
+    memory by a captured copy, so the ConvNeXt bodies replay as CUDA graphs and every replay sees NEW masks."""
+    from aldi_b200 import arch, synth_data
+    from aldi_b200.convnext import synthetic_state_dict as convnext_init
+    from aldi_b200.train_step import B200TrainStep, StepConfig
+    depths, dims = (1, 1, 2, 1), (32, 64, 96, 128)
+    sd = arch.synthetic_state_dict(3, bottom_up_channels=dims)
+    sd.update({"backbone.bottom_up." + k: v for k, v in convnext_init(depths, dims, 3, 1.0).items()})
+    ls, uw, us = synth_data.synthetic_batch(3, 2, 2, 96, 128)
+    cfg = StepConfig(dtype="bf16", ims_per_gpu=2, ema_start_iter=-1, backbone="convnext", convnext_depths=depths,
+                     convnext_dims=dims, convnext_drop_path=0.5, optimizer="ADAMW", base_lr=1e-5, cuda_graph=True)
+    step = B200TrainStep(cfg, sd)
+    step.debug = None
+    random.seed(5)
+    seen, losses = [], []
+    for _ in range(5):
+        losses.append(dict(step.step((None, ls, uw, us)).items()))
+        torch.cuda.synchronize()
+        seen.append(torch.cat([dev.flatten() for slots in step._mask_slots.values() for _, dev, _ in slots]).cpu())
+    assert step.graph_replays > 0 and len(step._mask_slots) >= 2          # source body + distillation body
+    assert all(v == v and abs(v) < 1e6 for l in losses for v in l.values()), losses[-1]
+    # replays (steps 3..5) drew new masks each time; values are 0 or 1 / keep_prob
+    assert not torch.equal(seen[2], seen[3]) or not torch.equal(seen[3], seen[4])
+    vals = set(torch.cat(seen).unique().tolist())
+    assert len(vals) > 1 and 0.0 in vals and all(v == 0.0 or v > 1.0 for v in vals), vals
