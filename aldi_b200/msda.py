@@ -18,6 +18,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import lib as _l
+from . import ops
 
 _DT = {torch.float32: 0, torch.float64: 2}
 
@@ -84,6 +85,69 @@ class MSDeformAttnFunction(Function):
         return grad_value, None, None, grad_loc, grad_attn, None
 
 
+class _LinearFunction(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM kernels (aldi_conv_tc / aldi_wgrad_tc as a 1x1 layer over a 1 x 1 x M x C image)
+    with fp32 operands split into `parts` bf16 tensors: 3 = fp32-level (the module is an fp32 module in the reference),
+    1 = plain bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, parts):
+        cout, cin = weight.shape
+        cout_p = (cout + 63) // 64 * 64
+        m = x.numel() // cin
+        x2 = x.reshape(1, 1, m, cin).contiguous().float()
+        wp = torch.empty(cout_p, cin, device=x.device)
+        ops.pack_weight(weight.detach().contiguous().float(), wp, cout=cout, taps=1, cin=cin, cout_p=cout_p, cin_p=cin)
+        bp = torch.zeros(cout_p, device=x.device)
+        bp[:cout] = bias.detach()
+        out = torch.empty(1, 1, m, cout, device=x.device)
+        ops.conv(x2, ops.split_bf16(wp, parts), out, bias=bp, cout_store=cout)
+        ctx.save_for_backward(x2, weight)
+        ctx.parts, ctx.shape = parts, x.shape
+        return out.view(*x.shape[:-1], cout)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        x2, weight = ctx.saved_tensors
+        parts = ctx.parts
+        cout, cin = weight.shape
+        cout_p = (cout + 63) // 64 * 64
+        m = x2.shape[2]
+        g2 = torch.zeros(1, 1, m, cout_p, device=grad.device)
+        g2[..., :cout] = grad.reshape(1, 1, m, cout)
+        wt = torch.empty(cin, cout_p, device=grad.device)          # [cin][cout_p] = W^T, zero padded
+        ops.pack_weight(weight.detach().contiguous().float(), wt, dgrad=True, cout=cout, taps=1, cin=cin, cout_p=cout_p, cin_p=cin)
+        dx = torch.empty(1, 1, m, cin, device=grad.device)
+        ops.conv(g2, ops.split_bf16(wt, parts), dx, cout_store=cin)
+        dw = torch.zeros(cout, cin, device=grad.device)
+        ops.wgrad(x2, g2, dw.view(-1), cout_store=cout, cin_store=cin, split_parts=parts)
+        db = torch.zeros(cout, device=grad.device)
+        ops.call("aldi_colsum", g2, _l.F32, 1, m, 0, cout_p, cout, 1.0, db)
+        return dx.view(ctx.shape), dw, db, None
+
+
+class Linear(nn.Module):
+    """nn.Linear's parameters (`weight`, `bias`: the reference's checkpoints load) over `_LinearFunction`."""
+
+    def __init__(self, in_features, out_features, parts=3):
+        super().__init__()
+        if in_features % 64:
+            raise ValueError("aldi_b200.msda.Linear: in_features must be a multiple of 64 (tensor-core K blocks), got %d"
+                             % in_features)
+        self.in_features, self.out_features, self.parts = in_features, out_features, parts
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(in_features)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise _l.AldiError("aldi_b200.msda.Linear runs on the GPU only (there is no CPU fallback)")
+        return _LinearFunction.apply(x, self.weight, self.bias, self.parts)
+
+
 def _is_power_of_2(n):
     if (not isinstance(n, int)) or (n < 0):
         raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
@@ -91,8 +155,9 @@ def _is_power_of_2(n):
 
 
 class MSDeformAttn(nn.Module):
-    """modules/ms_deform_attn.py:31-115.  The four projections are plain library GEMMs (nn.Linear); the sampling
-    itself is MSDeformAttnFunction above.  Parameter names match the reference so its checkpoints load."""
+    """modules/ms_deform_attn.py:31-115.  The four projections run on this library's tcgen05 GEMM kernels (`Linear`
+    above: split-bf16, fp32-level; no cuBLAS), the sampling itself is MSDeformAttnFunction.  Parameter names match the
+    reference so its checkpoints load."""
 
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
@@ -102,10 +167,10 @@ class MSDeformAttn(nn.Module):
             warnings.warn("MSDeformAttn: a power-of-2 head dimension keeps every bilinear tap one aligned line")
         self.im2col_step = 64
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
-        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
-        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
-        self.value_proj = nn.Linear(d_model, d_model)
-        self.output_proj = nn.Linear(d_model, d_model)
+        self.sampling_offsets = Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = Linear(d_model, d_model)
+        self.output_proj = Linear(d_model, d_model)
         self._reset_parameters()
 
     def _reset_parameters(self):

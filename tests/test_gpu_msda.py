@@ -125,3 +125,27 @@ def test_errors_mirror_reference():
         MSDeformAttnFunction.apply(v, [(2, 3)], [0], loc, at, 64)
     with pytest.raises(AssertionError):                               # batch must divide im2col_step
         MSDeformAttnFunction.apply(v.cuda(), [(2, 3)], [0], loc.cuda(), at.cuda(), 2)
+
+
+def test_module_projections_run_on_the_library_gemms_and_match_nn_linear():
+    """The four projections of MSDeformAttn are `aldi_b200.msda.Linear` (tcgen05 GEMMs, split-bf16 at fp32 level, no cuBLAS):
+    forward and every gradient against torch.nn.functional.linear on the same parameters."""
+    from aldi_b200 import lib
+    from aldi_b200.msda import Linear, MSDeformAttn
+    assert all(isinstance(getattr(MSDeformAttn(64, 2, 4, 2), n), Linear)
+               for n in ("sampling_offsets", "attention_weights", "value_proj", "output_proj"))
+    torch.manual_seed(1)
+    lin = Linear(256, 96).cuda()
+    x = torch.randn(3, 50, 256, device="cuda", requires_grad=True)
+    g = torch.randn(3, 50, 96, device="cuda")
+    lib.reset_launch_count()
+    y = lin(x)
+    y.backward(g)
+    assert lib.launch_count() > 0
+    xr = x.detach().clone().requires_grad_(True)
+    wr, br = lin.weight.detach().clone().requires_grad_(True), lin.bias.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.linear(xr.double(), wr.double(), br.double())
+    yr.backward(g.double())
+    for name, a, b in (("y", y, yr), ("dx", x.grad, xr.grad), ("dw", lin.weight.grad, wr.grad), ("db", lin.bias.grad, br.grad)):
+        err = float((a.double() - b.double()).abs().max() / b.double().abs().max())
+        assert err < 2e-5, (name, err)
