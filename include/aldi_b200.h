@@ -414,6 +414,63 @@ int aldi_patchify_image(const unsigned char* images, const int* sizes, void* out
 int aldi_adamw_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, size_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- ViTDet backbone (BASELINE configs[2]; aldi/backbone.py:21-64 -> detectron2 modeling/backbone/vit.py + utils.py) ------
+ * Everything the plain ViT + SimpleFeaturePyramid needs beyond the GEMM / LayerNorm / GELU kernels above.               */
+/* window_partition / window_unpartition (vit utils): x (n, h, w, C) <-> win (n * ceil(h/ws) * ceil(w/ws), ws, ws, C), `stride` =
+ * elements per token row in both.  inverse = 0: x -> win, bottom / right padding tokens written as ZEROS (they are keys of
+ * their window, detectron2 does not mask them); inverse = 1: win -> x (padding tokens dropped).  The gradient of one
+ * direction is the other.                                                                                              */
+int aldi_window_partition(const void* in, void* out, int n, int h, int w, int ws, int stride, int dtype, int inverse,
+                          void* stream);
+/* x[img, r, :] += pos[r, :] (absolute position embedding, broadcast over the batch); pos fp32 with the same row stride */
+int aldi_add_rows_bcast(void* x, const float* pos, int n, long long rows_per_image, int stride, int dtype, void* stream);
+/* out[r, :] += sum over images of dx[img, r, :]  (gradient of the broadcast add); out fp32 */
+int aldi_sum_over_batch(const void* dx, int n, long long rows_per_image, int stride, int dtype, float* out, void* stream);
+/* get_abs_pos: F.interpolate(mode="bicubic", align_corners=False) of a channels-last fp32 (sh, sw, c) table to (dh, dw, c)
+ * rows of `dst_stride` floats (A = -0.75, border indices clamped, as ATen upsample_bicubic2d).  backward = 1: the transpose,
+ * src[...] += taps * dst[...] (src is the pos_embed gradient).                                                          */
+int aldi_bicubic_resize(float* src, int sh, int sw, float* dst, int dh, int dw, int c, int dst_stride, int backward,
+                        void* stream);
+/* get_rel_pos: F.interpolate(mode="linear") of a (rows_in, c) fp32 table to (rows_out, c); backward = 1: transpose into src */
+int aldi_linear_resize_rows(float* src, int rows_in, float* dst, int rows_out, int c, int backward, void* stream);
+/* nn.MaxPool2d(2, 2) of SimpleFeaturePyramid's scale-0.5 branch; backward routes dy to the first maximum of each 2x2 block */
+int aldi_maxpool2x2(const void* x, void* out, int dtype, int n, int h, int w, int stride, void* stream);
+int aldi_maxpool2x2_backward(const void* x, const void* dy, void* dx, int dtype, int n, int h, int w, int stride,
+                             void* stream);
+
+/* Multi-head attention with MViTv2's decomposed relative position term (detectron2 vit.Attention + add_decomposed_rel_pos),
+ * head dim 64, flash-style (the (tokens x tokens) matrix is never materialised):
+ *   S[q, k] = scale * q.k + relpos[q, gh-1 + qh-kh] + relpos[q, 2gh-1 + gw-1 + qw-kw],   out = softmax_k(S) v
+ * qkv: (batch, gh*gw tokens, ...) rows of `row_stride` elements = [q | k | v], each dim = heads*64 wide (the output of the
+ * qkv Linear as it stands); relpos (nullable): fp32 (batch, tokens, heads, rp_stride), the product of the UNSCALED q with
+ * the concatenated tables [Rh (2gh-1 rows); Rw (2gw-1 rows)] -- one plain GEMM of the q view (aldi_conv_tc / aldi_conv_f32),
+ * so the tables' gradients and the term's part of dq are again plain GEMMs on `drelpos`.
+ * dtype BF16: tcgen05 kernels (QK^T, PV, and in the backward dO V^T, dS K, P^T dO, dS^T Q as 128 x N x 16 UMMA tiles with
+ * TMEM accumulators, 16 x 8-token TMA patches as tiles); dtype F32 or impl = 1: CUDA-core fp32 kernels (parity mode / the
+ * cross-check of the tensor-core path).
+ * forward writes out (batch, tokens, heads*64) rows of out_stride and lse (batch, heads, tokens) fp32;
+ * backward reads out / dout / lse and writes dqkv (same layout as qkv, all three thirds), drelpos (every column) and the
+ * delta workspace (batch, heads, tokens).                                                                               */
+typedef struct {
+  const void* qkv;
+  int batch, gh, gw, heads;
+  long long row_stride, batch_stride;     /* elements */
+  const float* relpos;
+  int rp_stride;
+  float scale;
+  int dtype;
+  void* out;
+  long long out_stride, out_batch_stride;
+  float* lse;
+  const void* dout;                       /* backward only from here */
+  void* dqkv;
+  float* drelpos;
+  float* delta;
+  int impl;
+} aldi_attn_params;
+int aldi_attention_forward(const aldi_attn_params* p, void* stream);
+int aldi_attention_backward(const aldi_attn_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
