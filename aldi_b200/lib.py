@@ -97,6 +97,16 @@ class RpnSparseParams(ctypes.Structure):
     ]
 
 
+class AttnParams(ctypes.Structure):
+    _fields_ = [
+        ("qkv", c_void_p), ("batch", c_int), ("gh", c_int), ("gw", c_int), ("heads", c_int),
+        ("row_stride", c_ll), ("batch_stride", c_ll),
+        ("relpos", c_void_p), ("rp_stride", c_int), ("scale", c_float), ("dtype", c_int),
+        ("out", c_void_p), ("out_stride", c_ll), ("out_batch_stride", c_ll), ("lse", c_void_p),
+        ("dout", c_void_p), ("dqkv", c_void_p), ("drelpos", c_void_p), ("delta", c_void_p), ("impl", c_int),
+    ]
+
+
 class RpnLevels(ctypes.Structure):
     _fields_ = [
         ("num_levels", c_int), ("num_anchors", c_int),
@@ -187,6 +197,15 @@ SIGNATURES = {
     "aldi_adamw_step": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
     "aldi_msda_forward": (c_int, [ctypes.POINTER(MsdaParams), P]),
     "aldi_msda_backward": (c_int, [ctypes.POINTER(MsdaParams), P]),
+    "aldi_window_partition": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_add_rows_bcast": (c_int, [P, P, c_int, c_ll, c_int, c_int, P]),
+    "aldi_sum_over_batch": (c_int, [P, c_int, c_ll, c_int, c_int, P, P]),
+    "aldi_bicubic_resize": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_linear_resize_rows": (c_int, [P, c_int, P, c_int, c_int, c_int, P]),
+    "aldi_maxpool2x2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_maxpool2x2_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_attention_forward": (c_int, [ctypes.POINTER(AttnParams), P]),
+    "aldi_attention_backward": (c_int, [ctypes.POINTER(AttnParams), P]),
 }
 
 
