@@ -11,9 +11,10 @@ import torch
 class ConvSpec:
     """One conv / linear layer: Detectron2 key prefix and geometry."""
 
-    def __init__(self, key, cin, cout, k=1, stride=1, pad=0, bias=False, norm=False, trainable=True, linear=False):
+    def __init__(self, key, cin, cout, k=1, stride=1, pad=0, bias=False, norm=False, trainable=True, linear=False, ln=False):
         self.key, self.cin, self.cout, self.k, self.stride, self.pad = key, cin, cout, k, stride, pad
         self.bias, self.norm, self.trainable, self.linear = bias, norm, trainable, linear
+        self.ln = ln      # a trainable channel LayerNorm follows (detectron2 get_norm("LN")): `<key>.norm.{weight,bias}`
 
 
 RES_DEPTHS = (3, 4, 6, 3)
@@ -64,19 +65,35 @@ def align_specs(align):
     return specs
 
 
-def rcnn_specs(num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
+VITDET_HEADS = dict(pyramid=True, rpn_convs=2, box_convs=4, box_fcs=1)   # configs/Base-RCNN-VitDetB.yaml:7-14
+
+
+def rcnn_specs(num_classes=8, freeze_at=2, align=None, bottom_up_channels=None, pyramid=False, rpn_convs=1, box_convs=0,
+               box_fcs=2):
     """bottom_up_channels: None -> ResNet-50 bottom-up in this table; a 4-tuple -> another bottom-up (ConvNeXt:
-    aldi_b200/convnext.py keeps its own parameter buffer) whose stage widths feed the FPN laterals."""
-    specs = resnet_specs(freeze_at) if bottom_up_channels is None else OrderedDict()
-    for lvl, c in zip((2, 3, 4, 5), bottom_up_channels or (256, 512, 1024, 2048)):
-        specs["fpn_lateral%d" % lvl] = ConvSpec("backbone.fpn_lateral%d" % lvl, c, 256, 1, 1, 0, bias=True)
-        specs["fpn_output%d" % lvl] = ConvSpec("backbone.fpn_output%d" % lvl, 256, 256, 3, 1, 1, bias=True)
+    aldi_b200/convnext.py keeps its own parameter buffer) whose stage widths feed the FPN laterals.
+    pyramid: the backbone returns p2..p5 itself (ViTDet's SimpleFeaturePyramid, aldi_b200/vit.py): no ResNet, no FPN here.
+    rpn_convs / box_convs / box_fcs: MODEL.RPN.CONV_DIMS ([-1] * k: k 3x3 convs, named conv | conv.conv{i} as
+    StandardRPNHead does) and MODEL.ROI_BOX_HEAD.NUM_CONV (3x3 256 + "LN") / NUM_FC of FastRCNNConvFCHead."""
+    specs = resnet_specs(freeze_at) if (bottom_up_channels is None and not pyramid) else OrderedDict()
+    if not pyramid:
+        for lvl, c in zip((2, 3, 4, 5), bottom_up_channels or (256, 512, 1024, 2048)):
+            specs["fpn_lateral%d" % lvl] = ConvSpec("backbone.fpn_lateral%d" % lvl, c, 256, 1, 1, 0, bias=True)
+            specs["fpn_output%d" % lvl] = ConvSpec("backbone.fpn_output%d" % lvl, 256, 256, 3, 1, 1, bias=True)
     rp = "proposal_generator.rpn_head."
-    specs["rpn_conv"] = ConvSpec(rp + "conv", 256, 256, 3, 1, 1, bias=True)
+    if rpn_convs == 1:
+        specs["rpn_conv"] = ConvSpec(rp + "conv", 256, 256, 3, 1, 1, bias=True)
+    else:
+        for k in range(rpn_convs):
+            specs["rpn_conv%d" % k] = ConvSpec(rp + "conv.conv%d" % k, 256, 256, 3, 1, 1, bias=True)
     specs["rpn_obj"] = ConvSpec(rp + "objectness_logits", 256, 3, 1, 1, 0, bias=True)
     specs["rpn_delta"] = ConvSpec(rp + "anchor_deltas", 256, 12, 1, 1, 0, bias=True)
+    for k in range(box_convs):
+        specs["box_conv%d" % (k + 1)] = ConvSpec("roi_heads.box_head.conv%d" % (k + 1), 256, 256, 3, 1, 1, ln=True)
+    assert box_fcs in (1, 2)
     specs["fc1"] = ConvSpec("roi_heads.box_head.fc1", 256 * 7 * 7, 1024, bias=True)
-    specs["fc2"] = ConvSpec("roi_heads.box_head.fc2", 1024, 1024, bias=True)
+    if box_fcs == 2:
+        specs["fc2"] = ConvSpec("roi_heads.box_head.fc2", 1024, 1024, bias=True)
     specs["cls_score"] = ConvSpec("roi_heads.box_predictor.cls_score", 1024, num_classes + 1, bias=True)
     specs["bbox_pred"] = ConvSpec("roi_heads.box_predictor.bbox_pred", 1024, num_classes * 4, bias=True)
     specs.update(align_specs(align))
@@ -94,27 +111,30 @@ def d2_shape(name, s):
     return (s.cout, s.cin, s.k, s.k)
 
 
-def state_dict_entries(num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
+def state_dict_entries(num_classes=8, freeze_at=2, align=None, bottom_up_channels=None, **head):
     """[(d2_key, shape, layer_name, field)] in a fixed order; field in {weight,bias,norm.<f>}."""
     out = []
-    for name, s in rcnn_specs(num_classes, freeze_at, align, bottom_up_channels).items():
+    for name, s in rcnn_specs(num_classes, freeze_at, align, bottom_up_channels, **head).items():
         out.append((s.key + ".weight", d2_shape(name, s), name, "weight"))
         if s.bias:
             out.append((s.key + ".bias", (s.cout,), name, "bias"))
+        if s.ln:
+            out.append((s.key + ".norm.weight", (s.cout,), name, "norm.weight"))
+            out.append((s.key + ".norm.bias", (s.cout,), name, "norm.bias"))
         if s.norm:
             for f in NORM_FIELDS:
                 out.append(("%s.norm.%s" % (s.key, f), (s.cout,), name, "norm." + f))
     return out
 
 
-def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
+def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None, bottom_up_channels=None, **head):
     """Deterministic CPU-generated weights with O(1) activations (stands in for a burn-in checkpoint).
 
     Scales are chosen so that a bf16 trunk stays in range, RPN logits are well separated and the
     box classifier is confident enough (>0.8) on some RoIs for the pseudo-label path to be non-empty.
     """
     sd = OrderedDict()
-    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at, align, bottom_up_channels)):
+    for idx, (key, shape, name, field) in enumerate(state_dict_entries(num_classes, freeze_at, align, bottom_up_channels, **head)):
         g = torch.Generator().manual_seed(seed * 100003 + idx)
         if field == "weight":
             fan_in = 1
@@ -123,7 +143,7 @@ def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None, bottom_
             fan_out = shape[0] * (shape[2] * shape[3] if len(shape) == 4 else 1)
             if name == "stem" or name.startswith("res"):
                 t = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
-            elif name.startswith("fpn") or name in ("fc1", "fc2") or "_align." in name:
+            elif name.startswith("fpn") or name.startswith("box_conv") or name in ("fc1", "fc2") or "_align." in name:
                 bound = (3.0 / fan_in) ** 0.5
                 t = (torch.rand(shape, generator=g) * 2 - 1) * bound
             elif name.startswith("rpn"):
@@ -134,6 +154,8 @@ def synthetic_state_dict(seed=0, num_classes=8, freeze_at=2, align=None, bottom_
                 t = torch.randn(shape, generator=g) * 0.02
         elif field == "bias":
             t = torch.randn(shape, generator=g) * 0.01
+        elif field == "norm.weight" and name.startswith("box_conv"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif field == "norm.weight":
             base = 0.05 if name == "stem" else 0.4 if name.endswith("conv3") else 0.8 if name.endswith("shortcut") else 1.0
             t = base * (1.0 + 0.1 * torch.randn(shape, generator=g))

@@ -203,11 +203,21 @@ def add_aldi_config(cfg):
 def step_config_from_cfg(cfg, dtype=None):
     """cfg (reference key names) -> the StepConfig the B200 step consumes."""
     D = cfg.DOMAIN_ADAPT.DISTILL
-    backbones = {"build_resnet_fpn_backbone": "resnet50", "build_convnext_fpn_backbone": "convnext"}
+    backbones = {"build_resnet_fpn_backbone": "resnet50", "build_convnext_fpn_backbone": "convnext",
+                 "build_vitdet_b_backbone": "vitdet_b", "build_vitdet_l_backbone": "vitdet_l"}
     if cfg.MODEL.META_ARCHITECTURE != "GeneralizedRCNN" or cfg.MODEL.BACKBONE.NAME not in backbones:
-        raise NotImplementedError("Faster R-CNN on ResNet-50-FPN (BASELINE configs[0-1]) and ConvNeXt-FPN (configs[4]) are "
-                                  "built; got %s / %s" % (cfg.MODEL.META_ARCHITECTURE, cfg.MODEL.BACKBONE.NAME))
+        raise NotImplementedError("Faster R-CNN on ResNet-50-FPN (BASELINE configs[0-1]), ViTDet-B/L (configs[2]) and "
+                                  "ConvNeXt-FPN (configs[4]) are built; got %s / %s"
+                                  % (cfg.MODEL.META_ARCHITECTURE, cfg.MODEL.BACKBONE.NAME))
     backbone = backbones[cfg.MODEL.BACKBONE.NAME]
+    B, R = cfg.MODEL.ROI_BOX_HEAD, cfg.MODEL.RPN
+    if backbone.startswith("vitdet"):
+        # configs/Base-RCNN-VitDetB.yaml:7-14: two-conv RPN head, four 3x3 convs + "LN" and one FC in the box head
+        if list(R.CONV_DIMS) != [-1, -1] or (B.NUM_CONV, B.CONV_DIM, B.NORM, B.NUM_FC, B.FC_DIM) != (4, 256, "LN", 1, 1024):
+            raise NotImplementedError("ViTDet heads: MODEL.RPN.CONV_DIMS [-1, -1] and ROI_BOX_HEAD NUM_CONV 4 / CONV_DIM 256 / "
+                                      "NORM LN / NUM_FC 1 / FC_DIM 1024 (Base-RCNN-VitDetB.yaml) are built")
+    elif list(R.CONV_DIMS) != [-1] or (B.NUM_CONV, B.NUM_FC, B.FC_DIM) != (0, 2, 1024):
+        raise NotImplementedError("FPN detectors: the standard RPN head (CONV_DIMS [-1]) and the 2-FC box head are built")
     optimizer = (cfg.SOLVER.OPTIMIZER or "SGD").upper()
     if optimizer not in ("SGD", "ADAMW"):                       # aldi/trainer.py:207-208
         raise ValueError("Unsupported optimizer/backbone combination {} {}.".format(cfg.SOLVER.OPTIMIZER,

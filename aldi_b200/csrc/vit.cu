@@ -183,6 +183,16 @@ maxpool2x2_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restri
   }
 }
 
+// da == NULL: out = max(x, 0); else out = da * (x > 0)   (the ReLU after the LayerNorm of ViTDet's 4-conv box head)
+template <typename T>
+__global__ void __launch_bounds__(256)
+relu_kernel(const T* __restrict__ x, const T* __restrict__ da, T* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = to_f32<T>(x[i]);
+    out[i] = da ? (v > 0.f ? da[i] : from_f32<T>(0.f)) : from_f32<T>(fmaxf(v, 0.f));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // CUDA-core attention (fp32 arithmetic), head dim 64.  Tokens in raster order; keys in tiles of 32 staged in shared memory.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -524,6 +534,18 @@ extern "C" int aldi_maxpool2x2_backward(const void* x, const void* dy, void* dx,
                (maxpool2x2_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
                                                                                (__nv_bfloat16*)dx, n, h, w, stride)),
                "aldi_maxpool2x2_backward");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_relu(const void* x, const void* da, void* out, size_t n, int dtype, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(x && out, "aldi_relu: null pointer");
+  if (n == 0) return ALDI_OK;
+  const int grid = blocks_for((long long)n, 256, 8);
+  VIT_DISPATCH(dtype, (relu_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)da, (float*)out, n)),
+               (relu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)da,
+                                                                    (__nv_bfloat16*)out, n)),
+               "aldi_relu");
   return ALDI_OK;
 }
 

@@ -31,11 +31,13 @@ def _pad64(c):
 class FlatLayout:
     """Detectron2 state_dict keys <-> ranges of one flat fp32 buffer (trainable range first)."""
 
-    def __init__(self, num_classes=8, freeze_at=2, align=None, bottom_up_channels=None):
+    def __init__(self, num_classes=8, freeze_at=2, align=None, bottom_up_channels=None, head=None):
+        """head: keyword arguments of arch.rcnn_specs selecting the head variant (arch.VITDET_HEADS for ViTDet)."""
         self.num_classes = num_classes
         self.align = align
         self.bottom_up_channels = bottom_up_channels
-        self.specs = arch.rcnn_specs(num_classes, freeze_at, align, bottom_up_channels)
+        self.head = dict(head or {})
+        self.specs = arch.rcnn_specs(num_classes, freeze_at, align, bottom_up_channels, **self.head)
         member_of = {m: g for g, ms in FUSED.items() for m in ms}
         train, frozen, buffers = [], [], []
         done = set()
@@ -48,6 +50,9 @@ class FlatLayout:
             dst.append([(g, "weight") for g in group])
             if s.bias:
                 dst.append([(g, "bias") for g in group])
+            if s.ln:
+                dst.append([(name, "norm.weight")])
+                dst.append([(name, "norm.bias")])
             if s.norm:
                 for f in arch.NORM_FIELDS:
                     buffers.append([(name, "norm." + f)])
@@ -113,9 +118,10 @@ class FlatLayout:
 class LayerGeom:
     """Geometry of one executed GEMM layer (after head fusion)."""
 
-    def __init__(self, name, cin, cout, k, pad, stride, members, norm, trainable):
+    def __init__(self, name, cin, cout, k, pad, stride, members, norm, trainable, bias=True, ln=False):
         self.name, self.cin, self.cout, self.k, self.pad, self.stride = name, cin, cout, k, pad, stride
         self.members, self.norm, self.trainable = members, norm, trainable
+        self.bias, self.ln = bias, ln     # has a bias vector / is followed by a trainable channel LayerNorm
         self.cin_p, self.cout_p = _pad64(cin), _pad64(cout)
 
 
@@ -144,7 +150,12 @@ class DetectorWeights:
                 self.geom[g] = LayerGeom(g, s.cin, sum(sp[m].cout for m in ms), s.k, s.pad, s.stride, ms, False,
                                          s.trainable)
             else:
-                self.geom[name] = LayerGeom(name, s.cin, s.cout, s.k, s.pad, s.stride, (name,), s.norm, s.trainable)
+                self.geom[name] = LayerGeom(name, s.cin, s.cout, s.k, s.pad, s.stride, (name,), s.norm, s.trainable,
+                                            bias=s.bias or s.norm, ln=s.ln)
+        # head variants (arch.rcnn_specs): hidden 3x3 convs of the RPN head, 3x3 + LayerNorm convs of the box head
+        self.rpn_convs = [n for n in self.geom if n.startswith("rpn_conv")]
+        self.box_convs = [n for n in self.geom if n.startswith("box_conv")]
+        self.pyramid = bottom_up is not None and getattr(bottom_up, "is_pyramid", False)
         # stem: bf16 path runs it as a GEMM over the fused normalise+im2col buffer (K = 147 -> 192)
         self.stem_gemm = dtype == torch.bfloat16 or bool(self.split_parts)
         self.fwd, self.dgrad, self.scale, self.shift = {}, {}, {}, {}
@@ -179,8 +190,9 @@ class DetectorWeights:
                 self.dgrad[name] = torch.zeros(g.cin_p, g.k * g.k * g.cout_p, device=self.dev, dtype=self.dtype)
         # sparse RPN backward (csrc/rpn_sparse.cu): [(tap, cin)][cout] operand that turns gathered hidden-gradient rows
         # into the 3x3 neighbourhood rows scattered back onto the FPN feature gradient
-        g = self.geom["rpn_conv"]
-        self.scat["rpn_conv"] = torch.zeros(g.k * g.k * g.cin_p, g.cout_p, device=self.dev, dtype=self.dtype)
+        if "rpn_conv" in self.geom:
+            g = self.geom["rpn_conv"]
+            self.scat["rpn_conv"] = torch.zeros(g.k * g.k * g.cin_p, g.cout_p, device=self.dev, dtype=self.dtype)
         self._tables = {}
 
     # ---- operand refresh: ONE launch per table (csrc/optim.cu refresh_kernel) ------------------------------------
@@ -207,7 +219,7 @@ class DetectorWeights:
                 # FrozenBN buffers / biases of frozen layers only move for the EMA teacher (aldi/ema.py covers buffers, T7)
                 if g.norm:
                     desc(2, out=self.scale[name], out2=self.shift[name], cout=g.cout, **bn)
-            if not g.norm and (g.trainable or not trainable_only):
+            if not g.norm and g.bias and (g.trainable or not trainable_only):
                 desc(3, w=self.view(name, "bias"), out2=self.shift[name], cout=g.cout)
             if trainable_only and not g.trainable:
                 continue
@@ -319,6 +331,11 @@ class Detector:
         n, _, hp, wp = images_u8.shape
         assert hp % 32 == 0 and wp % 32 == 0
         dev, dt = images_u8.device, W.dtype
+        if W.pyramid:
+            # ViTDet: the backbone IS the pyramid (SimpleFeaturePyramid); p6 = LastLevelMaxPool(kernel 1, stride 2) of p5
+            feats = dict(W.bottom_up.forward(images_u8, sizes, keep_masks=keep_masks, save=save))
+            feats["p6"] = feats["p5"][:, ::2, ::2, :]
+            return feats, ({} if save else None)
         if W.bottom_up is not None:
             outs = W.bottom_up.forward(images_u8, sizes, keep_masks=keep_masks, save=save)
             feats = {"res%d" % (i + 2): outs[i] for i in range(4)}
@@ -388,13 +405,17 @@ class Detector:
         ts = []
         for i, l in enumerate((2, 3, 4, 5, 6)):
             p = feats["p%d" % l]
-            t = self.conv(W, "rpn_conv", p, relu=True)
+            hidden = []
+            t = p
+            for name in W.rpn_convs:                      # one 3x3 conv + ReLU, or ViTDet's two (RPN.CONV_DIMS [-1, -1])
+                t = self.conv(W, name, t, relu=True)
+                hidden.append(t)
             h, w = p.shape[1], p.shape[2]
             view = rpn_out.as_strided((n, h, w, self.RPN_CH),
                                       (lv.total_locs * self.RPN_CH, w * self.RPN_CH, self.RPN_CH, 1),
                                       lv.loc_off[i] * self.RPN_CH)
             self.conv(W, "rpn_head", t, out=view, cout_store=15)
-            ts.append(t if save else None)
+            ts.append((hidden[0] if len(hidden) == 1 else tuple(hidden)) if save else None)
         return rpn_out, ts
 
     def proposals(self, rpn_out, lv, sizes, pre_topk, post_topk, nms_thresh=0.7, err_flag=None):
@@ -465,12 +486,28 @@ class Detector:
         for r0, rows, i0, ni in self._roi_groups(groups, m, plv[0].shape[0]):
             ops.roi_align([p[i0:i0 + ni] for p in plv], rois[r0:r0 + rows], roi_batch[r0:r0 + rows],
                           out=pooled[r0:r0 + rows], scales=[1.0 / s for s in FPN_STRIDES[:4]])
-        x = pooled.view(1, 1, m, 7 * 7 * 256)
+        convs = []
+        a = pooled
+        dtc = _l.BF16 if dt == torch.bfloat16 else _l.F32
+        for name in W.box_convs:
+            # FastRCNNConvFCHead with NORM "LN": 3x3 conv (no bias) -> channel LayerNorm -> ReLU on the 7x7 RoI maps
+            u = self.conv(W, name, a)
+            y = torch.empty_like(u)
+            stats = torch.empty(m * 49, 2, device=dev)
+            ops.call("aldi_layernorm_forward", u, W.view(name, "norm.weight"), W.view(name, "norm.bias"), 1e-6, m * 49, 256, 256,
+                     dtc, y, stats)
+            r = torch.empty_like(y)
+            ops.call("aldi_relu", y, None, r, y.numel(), dtc)
+            convs.append((a, u, stats, y))
+            a = r
+        x = a.view(1, 1, m, 7 * 7 * 256)
         f1 = self.conv(W, "fc1", x, relu=True)
-        f2 = self.conv(W, "fc2", f1, relu=True)
+        f2 = self.conv(W, "fc2", f1, relu=True) if "fc2" in W.geom else f1
         pred = torch.zeros(1, 1, m, self.PRED_CH, device=dev, dtype=torch.float32)
         self.conv(W, "predictor", f2, out=pred, cout_store=5 * self.K + 1)
-        return pred.view(m, self.PRED_CH), ((x, f1, f2) if save else None)
+        if not save:
+            return pred.view(m, self.PRED_CH), None
+        return pred.view(m, self.PRED_CH), ((x, f1, f2, convs) if W.box_convs else (x, f1, f2))
 
     def detections(self, pred, props, sizes, score_thresh, nms_thresh=0.5, topk=100):
         """FastRCNNOutputLayers.inference on (N*P) predictions -> per-image detections (score order)."""
@@ -550,11 +587,12 @@ class Detector:
         # four extra warps' shared-memory reads slow the MMA pipeline by as much as the 21 aldi_colsum launches cost
         # (wgrad 6.83 -> 7.36 ms, colsum 0.75 -> 0 ms per step: 30.79 vs 30.77 ms), so the separate kernel stays the
         # default; ALDI_FUSED_DBIAS=1 selects the fused path.
-        fused_bias = (not g.norm) and dy.dtype == torch.bfloat16 and os.environ.get("ALDI_FUSED_DBIAS") == "1"
+        has_bias = g.bias and not g.norm
+        fused_bias = has_bias and dy.dtype == torch.bfloat16 and os.environ.get("ALDI_FUSED_DBIAS") == "1"
         ops.wgrad(xv, dy, W.view(name, "weight", G), taps_h=g.k, taps_w=g.k, pad_h=g.pad, pad_w=g.pad,
                   scale=W.scale.get(name), cout_store=g.cout, cin_store=g.cin,
                   dbias=W.view(name, "bias", G) if fused_bias else None, split_parts=W.split_parts)
-        if not g.norm and not fused_bias:
+        if has_bias and not fused_bias:
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             assert dy.is_contiguous()
             ops.call("aldi_colsum", dy, _l.BF16 if dy.dtype == torch.bfloat16 else _l.F32, 1, rows, 0, dy.shape[3], g.cout,
@@ -640,7 +678,8 @@ class Detector:
                 for l in (2, 3, 4, 5):
                     dP[l] = torch.zeros_like(feats["p%d" % l])
         else:
-            x, f1, f2 = head_saved
+            x, f1, f2 = head_saved[:3]
+            box_convs = head_saved[3] if len(head_saved) > 3 else []
             m = f2.shape[2]
             df2 = torch.empty_like(f2)
             if dpred is not None:
@@ -652,15 +691,30 @@ class Detector:
                 _, dh, ndh = ins
                 self._wgrad(W, G, "ins_align.fc0", f2, dh)
                 self._dgrad(W, "ins_align.fc0", ndh, df2, mask=f2, accumulate=dpred is not None)
-            self._wgrad(W, G, "fc2", f1, df2)
-            df1 = torch.empty_like(f1)
-            self._dgrad(W, "fc2", df2, df1, mask=f1)
+            if "fc2" in W.geom:
+                self._wgrad(W, G, "fc2", f1, df2)
+                df1 = torch.empty_like(f1)
+                self._dgrad(W, "fc2", df2, df1, mask=f1)
+            else:
+                df1 = df2                                      # NUM_FC 1 (ViTDet): the predictor reads fc1's output
             self._wgrad(W, G, "fc1", x, df1)
             dx = torch.empty_like(x)
             self._dgrad(W, "fc1", df1, dx)
+            dxv = dx.view(m, 7, 7, 256)
+            for name, (a, u, stats, y) in reversed(list(zip(W.box_convs, box_convs))):
+                # conv -> LayerNorm -> ReLU, backwards
+                dyl = torch.empty_like(y)
+                ops.call("aldi_relu", y, dxv, dyl, y.numel(), dtc)
+                du = torch.empty_like(u)
+                ops.call("aldi_layernorm_backward", u, W.view(name, "norm.weight"), stats, dyl, m * 49, 256, 256, dtc, du, 0,
+                         W.view(name, "norm.weight", G), W.view(name, "norm.bias", G))
+                self._wgrad(W, G, name, a, du)
+                da = torch.empty_like(a)
+                self._dgrad(W, name, du, da)
+                dxv = da
+                del dyl, du
             plv = [feats["p%d" % l] for l in (2, 3, 4, 5)]
             dfeat = [torch.zeros(p.shape, device=dev, dtype=torch.float32) for p in plv]
-            dxv = dx.view(m, 7, 7, 256)
             for r0, rows, i0, ni in self._roi_groups(groups, m, n):
                 ops.roi_align([p[i0:i0 + ni] for p in plv], rois[r0:r0 + rows], roi_batch[r0:r0 + rows],
                               dout=dxv[r0:r0 + rows], dfeats=[d[i0:i0 + ni] for d in dfeat],
@@ -679,20 +733,34 @@ class Detector:
             for i, l in enumerate((2, 3, 4, 5, 6)):
                 p = feats["p%d" % l]
                 h, w = p.shape[1], p.shape[2]
-                t = rpn_ts[i]
+                hidden = rpn_ts[i] if isinstance(rpn_ts[i], tuple) else (rpn_ts[i],)
                 dy = d_rpn.as_strided((n, h, w, 64), (lv.total_locs * 64, w * 64, 64, 1), lv.loc_off[i] * 64)
-                self._wgrad_strided_bias(W, G, "rpn_head", t, dy)
-                dt_ = torch.empty_like(t)
-                self._dgrad(W, "rpn_head", dy, dt_, mask=t)
-                self._wgrad(W, G, "rpn_conv", p, dt_)
-                tgt = dP[l] if l < 6 else dP[5][:, ::2, ::2, :]
-                self._dgrad(W, "rpn_conv", dt_, tgt, accumulate=True)
+                self._wgrad_strided_bias(W, G, "rpn_head", hidden[-1], dy)
+                dt_ = torch.empty_like(hidden[-1])
+                self._dgrad(W, "rpn_head", dy, dt_, mask=hidden[-1])
+                for k in reversed(range(len(W.rpn_convs))):
+                    name = W.rpn_convs[k]
+                    xin = hidden[k - 1] if k > 0 else p
+                    self._wgrad(W, G, name, xin, dt_)
+                    if k > 0:
+                        dprev = torch.empty_like(xin)
+                        self._dgrad(W, name, dt_, dprev, mask=xin)
+                        dt_ = dprev
+                    else:
+                        tgt = dP[l] if l < 6 else dP[5][:, ::2, ::2, :]
+                        self._dgrad(W, name, dt_, tgt, accumulate=True)
                 del dt_
         if align and "img" in align:
             lname = align["img_layer"]
             tgt = dP[int(lname[1])] if lname != "p6" else dP[5][:, ::2, ::2, :]
             self._align_img_backward(W, G, align["img"], tgt)
         on_ready("heads")
+        if W.pyramid:
+            # ViTDet: p2..p5 are the backbone's own outputs (p6's gradient has been accumulated into p5's even positions)
+            W.bottom_up.backward({"p%d" % l: dP[l] for l in (2, 3, 4, 5)})
+            for tag in ("fpn", "res5", "res4", "res3"):
+                on_ready(tag)
+            return
         # ---- FPN: p_l = output_l(prev_l); prev_l = lateral_l(res_l) + up2(prev_{l+1})
         dprev, dres = {}, {}
         for l in (2, 3, 4, 5):

@@ -204,6 +204,7 @@ SIGNATURES = {
     "aldi_linear_resize_rows": (c_int, [P, c_int, P, c_int, c_int, c_int, P]),
     "aldi_maxpool2x2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_maxpool2x2_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "aldi_relu": (c_int, [P, P, P, c_size_t, c_int, P]),
     "aldi_attention_forward": (c_int, [ctypes.POINTER(AttnParams), P]),
     "aldi_attention_backward": (c_int, [ctypes.POINTER(AttnParams), P]),
 }

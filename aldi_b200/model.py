@@ -80,7 +80,8 @@ class GeneralizedRCNN:
             from .config import step_config_from_cfg
             scfg = step_config_from_cfg(cfg, dtype=dtype)
             if state_dict is None:
-                state_dict = arch.synthetic_state_dict(0, scfg.num_classes, align=scfg.align_spec())
+                from .train_step import synthetic_state_dict_for
+                state_dict = synthetic_state_dict_for(scfg)
             dev = device or (cfg.MODEL.DEVICE if cfg.MODEL.DEVICE != "cuda" else "cuda:%d" % torch.cuda.current_device())
             engine = B200TrainStep(scfg, state_dict, device=dev, process_group=process_group)
             engine.debug = None

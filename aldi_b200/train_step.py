@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import lib as _l
-from . import ops, sampling
+from . import arch, ops, sampling
 from .data_parallel import GradReducer
 from .detector import Detector, DetectorWeights, FlatLayout
 
@@ -82,6 +82,10 @@ class StepConfig:
         self.convnext_depths = (3, 3, 27, 3)
         self.convnext_dims = (192, 384, 768, 1536)
         self.convnext_drop_path = 0.2
+        # "vitdet_b" / "vitdet_l" (BASELINE configs[2]; build_vitdet_{b,l}_backbone, aldi/backbone.py:37-64): plain ViT +
+        # SimpleFeaturePyramid with the two-conv RPN head and the 4-conv LayerNorm box head of Base-RCNN-VitDetB.yaml
+        self.vit_img_size = 1024                 # ViT(img_size=...) of mask_rcnn_vitdet.py: sizes the global rel-pos tables
+        self.vit_overrides = None                # test seam: ViT(...) keyword overrides (embed_dim, depth, ...)
         self.anchor_sizes = None                 # MODEL.ANCHOR_GENERATOR.SIZES (None: detectron2's 32..512)
         self.pixel_mean = (103.530, 116.280, 123.675)
         self.pixel_std = (1.0, 1.0, 1.0)
@@ -113,6 +117,27 @@ class StepConfig:
     def distill_enabled(self):                   # aldi/distill.py:140-142
         return any([self.do_hard_cls, self.do_hard_obj, self.do_hard_rpn_reg, self.do_hard_roi_reg, self.do_cls_dst,
                     self.do_obj_dst, self.do_rpn_reg_dst, self.do_roih_reg_dst])
+
+
+def synthetic_state_dict_for(cfg, seed=0, convnext_layer_scale=1e-6, rel_pos_std=0.02):
+    """Deterministic random-init weights of the detector a StepConfig describes, under Detectron2 key names (there is no
+    network for the reference's checkpoints): heads / FPN / ResNet from arch.synthetic_state_dict plus the ConvNeXt or
+    ViTDet backbone's own initialisation."""
+    convnext, vitdet = cfg.backbone == "convnext", cfg.backbone in ("vitdet_b", "vitdet_l")
+    sd = arch.synthetic_state_dict(seed, cfg.num_classes, align=cfg.align_spec(),
+                                   bottom_up_channels=tuple(cfg.convnext_dims) if convnext else None,
+                                   **(arch.VITDET_HEADS if vitdet else {}))
+    if convnext:
+        from .convnext import synthetic_state_dict as convnext_init
+        sd.update({"backbone.bottom_up." + k: v for k, v in convnext_init(cfg.convnext_depths, cfg.convnext_dims, seed,
+                                                                          convnext_layer_scale).items()})
+    if vitdet:
+        from . import vit
+        vc = dict(vit.vit_config(cfg.backbone[-1]))
+        vc.update(cfg.vit_overrides or {})
+        layout = vit.ViTLayout(img_size=cfg.vit_img_size, **vc)
+        sd.update({"backbone." + k: v for k, v in vit.synthetic_state_dict(layout, seed, rel_pos_std=rel_pos_std).items()})
+    return sd
 
 
 class MicroBatch:
@@ -260,10 +285,17 @@ class B200TrainStep:
         split_parts = {"bf16x3": 2, "bf16x6": 3}.get(cfg.dtype, 0)
         _l.load()  # fail loudly if the CUDA library is missing
         convnext = cfg.backbone == "convnext"
-        if cfg.backbone not in ("resnet50", "convnext"):
-            raise NotImplementedError("MODEL.BACKBONE %s: ResNet-50-FPN and ConvNeXt-FPN are built" % cfg.backbone)
+        vitdet = cfg.backbone in ("vitdet_b", "vitdet_l")
+        if cfg.backbone not in ("resnet50", "convnext", "vitdet_b", "vitdet_l"):
+            raise NotImplementedError("MODEL.BACKBONE %s: ResNet-50-FPN, ConvNeXt-FPN and ViTDet-B/L are built" % cfg.backbone)
+        if vitdet:
+            if cfg.do_align:
+                raise NotImplementedError("domain-alignment discriminators on the ViTDet heads are not built")
+            if cfg.dtype not in ("bf16", "fp32"):
+                raise NotImplementedError("ViTDet runs in bf16 (tcgen05) or fp32 (parity mode)")
         self.layout = FlatLayout(cfg.num_classes, align=cfg.align_spec(),
-                                 bottom_up_channels=tuple(cfg.convnext_dims) if convnext else None)
+                                 bottom_up_channels=tuple(cfg.convnext_dims) if convnext else None,
+                                 head=arch.VITDET_HEADS if vitdet else None)
         self.det = Detector(cfg.num_classes, cfg.anchor_sizes, cfg.pixel_mean, cfg.pixel_std)
         flat = self.layout.pack_state_dict(state_dict).to(self.device)
         tsd = state_dict if teacher_state_dict is None else teacher_state_dict
@@ -279,6 +311,16 @@ class B200TrainStep:
                                         device=self.device, pixel_mean=cfg.pixel_mean, pixel_std=cfg.pixel_std)
 
             bu_s, bu_t = bottom_up(state_dict), bottom_up(tsd)
+        if vitdet:
+            from .vit import ViTDetBackbone
+            pre = "backbone."
+
+            def pyramid(sd):
+                return ViTDetBackbone({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, size=cfg.backbone[-1],
+                                      dtype=cfg.dtype, device=self.device, pixel_mean=cfg.pixel_mean, pixel_std=cfg.pixel_std,
+                                      img_size=cfg.vit_img_size, **(cfg.vit_overrides or {}))
+
+            bu_s, bu_t = pyramid(state_dict), pyramid(tsd)
         # DropPath masks (host-drawn, aldi/backbone.py:176-181): every data-parallel rank draws its own
         self.keep_rng = torch.Generator().manual_seed(dist.get_rank(process_group) if process_group is not None else 0)
         self.keep_override = None                               # test seam: list of per-forward mask lists
@@ -1074,7 +1116,13 @@ class B200TrainStep:
             b1, b2 = self.cfg.adamw_betas
             ops.call("aldi_adamw_step", p, self.momentum_buf, self.exp_avg_sq, self.grad, self.nt, lr, b1, b2, self.cfg.adamw_eps,
                      self.cfg.weight_decay, self.iter + 1, gs)
-            if bu is not None:
+            if bu is not None and hasattr(bu, "opt_segments"):
+                # ViTDet (aldi/backbone.py:66-84): layer-wise lr decay, no decay on torch.nn.LayerNorm weights and pos_embed
+                for off, n, factor, no_wd in bu.opt_segments():
+                    ops.call("aldi_adamw_step", bu.flat[off:off + n], self.bu_exp_avg[off:off + n], self.bu_exp_avg_sq[off:off + n],
+                             bu.grad[off:off + n], n, lr * factor, b1, b2, self.cfg.adamw_eps,
+                             0.0 if no_wd else self.cfg.weight_decay, self.iter + 1, gs)
+            elif bu is not None:
                 ops.call("aldi_adamw_step", bu.flat, self.bu_exp_avg, self.bu_exp_avg_sq, bu.grad, bu.flat.numel(), lr, b1, b2,
                          self.cfg.adamw_eps, self.cfg.weight_decay, self.iter + 1, gs)
         else:
@@ -1100,7 +1148,8 @@ class B200TrainStep:
         w = self.student if which == "student" else self.teacher
         out = self.layout.unpack_state_dict(w.flat)
         if w.bottom_up is not None:
-            out.update({"backbone.bottom_up." + k: v for k, v in w.bottom_up.state_dict().items()})
+            pre = getattr(w.bottom_up, "prefix", "backbone.bottom_up.")
+            out.update({pre + k: v for k, v in w.bottom_up.state_dict().items()})
         return out
 
     def load_state_dict(self, sd, which="student", strict=True):
@@ -1112,14 +1161,16 @@ class B200TrainStep:
         bu_missing = []
         if w.bottom_up is not None:
             # the ConvNeXt bottom-up keeps its own flat buffer under the "backbone.bottom_up." prefix
-            pre, lay = "backbone.bottom_up.", w.bottom_up.layout
+            pre, lay = getattr(w.bottom_up, "prefix", "backbone.bottom_up."), w.bottom_up.layout
+            keyed = getattr(w.bottom_up, "keyed_layout", False)
             host = w.bottom_up.flat.detach().cpu()
             for k, (off, n, shape) in lay.entries.items():
                 t = sd.get(pre + k)
                 if t is None or tuple(t.shape) != tuple(shape):
                     bu_missing.append(pre + k)
                 else:
-                    host[off:off + n] = lay.to_internal(torch.as_tensor(t).detach().to("cpu", torch.float32))
+                    t = torch.as_tensor(t).detach().to("cpu", torch.float32)
+                    host[off:off + n] = lay.to_internal(k, t) if keyed else lay.to_internal(t)
             w.bottom_up.flat.copy_(host)
             w.bottom_up.refresh()
             sd = {k: v for k, v in sd.items() if not (k.startswith(pre) and k[len(pre):] in lay.entries)}

@@ -112,13 +112,8 @@ class ALDITrainer:
         scfg = step_config_from_cfg(cfg, dtype=dtype)
         sd = state_dict
         if sd is None:
-            convnext = scfg.backbone == "convnext"
-            sd = arch.synthetic_state_dict(0, cfg.MODEL.ROI_HEADS.NUM_CLASSES, align=scfg.align_spec(),
-                                           bottom_up_channels=tuple(scfg.convnext_dims) if convnext else None)
-            if convnext:
-                from .convnext import synthetic_state_dict as convnext_init
-                sd.update({"backbone.bottom_up." + k: v for k, v in convnext_init(
-                    scfg.convnext_depths, scfg.convnext_dims, 0, cfg.MODEL.CONVNEXT.LAYER_SCALE_INIT_VALUE).items()})
+            from .train_step import synthetic_state_dict_for
+            sd = synthetic_state_dict_for(scfg, 0, cfg.MODEL.CONVNEXT.LAYER_SCALE_INIT_VALUE)
         # aldi/trainer.py:139-147,156-160: the model, its EMA teacher and the distiller come from the registries named in cfg
         # (MODEL.META_ARCHITECTURE, DOMAIN_ADAPT.ALIGN.MIXIN_NAME, DOMAIN_ADAPT.DISTILL.MIXIN_NAME / DISTILLER_NAME); all
         # three are facades over ONE engine, which is what run_step drives

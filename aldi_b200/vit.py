@@ -249,6 +249,8 @@ class ViTDetBackbone:
     backward({"p2".."p5": gradients}).  `is_pyramid`: the detector uses the maps as they are (no FPN on top)."""
 
     is_pyramid = True
+    prefix = "backbone."          # state_dict keys: backbone.net.*, backbone.simfp_*
+    keyed_layout = True
 
     def __init__(self, state_dict, size="b", dtype="bf16", device="cuda:0", pixel_mean=(123.675, 116.28, 103.53),
                  pixel_std=(58.395, 57.12, 57.375), img_size=1024, **overrides):

@@ -437,6 +437,9 @@ int aldi_linear_resize_rows(float* src, int rows_in, float* dst, int rows_out, i
 int aldi_maxpool2x2(const void* x, void* out, int dtype, int n, int h, int w, int stride, void* stream);
 int aldi_maxpool2x2_backward(const void* x, const void* dy, void* dx, int dtype, int n, int h, int w, int stride,
                              void* stream);
+/* ReLU after a LayerNorm (FastRCNNConvFCHead with NORM "LN": conv -> LN -> ReLU, configs/Base-RCNN-VitDetB.yaml:7-12):
+ * da == NULL -> out = max(x, 0); else out = da * (x > 0) */
+int aldi_relu(const void* x, const void* da, void* out, size_t n, int dtype, void* stream);
 
 /* Multi-head attention with MViTv2's decomposed relative position term (detectron2 vit.Attention + add_decomposed_rel_pos),
  * head dim 64, flash-style (the (tokens x tokens) matrix is never materialised):

@@ -81,8 +81,12 @@ def test_unsupported_combinations_fail_with_reference_errors(tmp_path):
                                               "[192, 384, 768, 1536]"]))
     assert cn.backbone == "convnext" and cn.convnext_dims == (192, 384, 768, 1536)
     cfg = _cfg(tmp_path, ["MODEL.BACKBONE.NAME", "build_vitdet_b_backbone"])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError, match="ViTDet heads"):      # the backbone alone, without Base-RCNN-VitDetB's heads
         step_config_from_cfg(cfg)
+    vb = step_config_from_cfg(_cfg(tmp_path, ["MODEL.BACKBONE.NAME", "build_vitdet_b_backbone", "MODEL.RPN.CONV_DIMS", "[-1, -1]",
+                                              "MODEL.ROI_BOX_HEAD.NUM_CONV", "4", "MODEL.ROI_BOX_HEAD.NORM", "LN",
+                                              "MODEL.ROI_BOX_HEAD.NUM_FC", "1", "SOLVER.OPTIMIZER", "ADAMW"]))
+    assert (vb.backbone, vb.optimizer, vb.base_lr, vb.weight_decay) == ("vitdet_b", "ADAMW", 1e-4, 0.1)
     cfg = _cfg(tmp_path, ["MODEL.RPN.PRE_NMS_TOPK_TRAIN", "12000"])       # detectron2's own default, not the ALDI configs'
     with pytest.raises(NotImplementedError, match="PRE_NMS_TOPK"):
         step_config_from_cfg(cfg)
@@ -143,7 +147,7 @@ REF_CONFIGS = "/root/reference/configs"
 def test_every_shipped_yaml_loads_or_fails_as_documented():
     """The reference's own test strategy is 'every config starts' (tests/test_all_configs_cityscapes.sh).  Here:
     every shipped YAML goes through the cfg mirror (`_BASE_` chains, `add_aldi_config` keys); R50-FPN and ConvNeXt-FPN
-    configs map onto a StepConfig; ViTDet configs load and are refused with NotImplementedError (a18, not built);
+    configs map onto a StepConfig, and so do the ViTDet-B / ViTDet-L configs (AdamW, RGB pixel statistics);
     Deformable-DETR / YOLO YAMLs need config keys that the reference's tools/train_net.py itself only registers when the
     optional sub-library imports (yolo, :37-41) or not at all (detr: commented out, :47-50) -> 'Non-existent config key'."""
     import glob
@@ -162,12 +166,12 @@ def test_every_shipped_yaml_loads_or_fails_as_documented():
             assert name == os.path.join("sim10k", "ALDI-Best-Sim10k.yaml"), name     # its _BASE_ is not in the reference tree
             seen["missing_base"] += 1
             continue
+        sc = step_config_from_cfg(cfg)
         if "VitDet" in name or "ViT" in name:
-            with pytest.raises(NotImplementedError):
-                step_config_from_cfg(cfg)
+            assert sc.backbone == ("vitdet_l" if ("VitDetL" in name or "ViTL" in name) else "vitdet_b"), (name, sc.backbone)
+            assert sc.optimizer == "ADAMW" and sc.base_lr == 1e-4 and sc.pixel_std == (58.395, 57.12, 57.375), name
             seen["vit"] += 1
             continue
-        sc = step_config_from_cfg(cfg)
         assert sc.backbone in ("resnet50", "convnext") and sc.ims_per_gpu >= 1, name
         if "ConvNeXt" in name:
             assert sc.backbone == "convnext" and sc.optimizer == "ADAMW" and sc.convnext_dims == (192, 384, 768, 1536)
