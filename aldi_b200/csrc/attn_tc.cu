@@ -51,6 +51,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2(float x) {      // 2^x, one MUFU (x <= 0 here; -inf -> 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
@@ -81,7 +86,7 @@ __device__ __forceinline__ void load_bias(const float* trow, const TcArgs& a, in
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kFwdSmem = 6 * kTileBytes + 1024;   // Q, K x2 (P chunk 0 reuses the K buffer S has consumed), V x2, P chunk 1
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)      // two CTAs per SM: one's softmax overlaps the other's MMAs / TMEM latency
 attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -178,22 +183,32 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
       mbar_wait(&s_bar, kt & 1);
       __syncwarp();
       tc_fence_after();
+      // interior tiles (every key of the patch inside the grid) take the path without per-key masks
+      const bool interior = (kh0 + kPH <= a.gh) && (kw0 + kPW <= a.gw);
       float mt = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
         tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
         tmem_ld_wait();
+        if (interior) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * c + (i >> 4), pw = i & 15;
-          const bool ok = (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
-          const float s2 = __uint_as_float(raw[i]) * a.scale_log2 + th[ph] + tw[pw];
-          mt = fmaxf(mt, ok ? s2 : -INFINITY);
+          for (int i = 0; i < 32; ++i)
+            mt = fmaxf(mt, fmaf(__uint_as_float(raw[i]), a.scale_log2, th[2 * c + (i >> 4)]) + tw[i & 15]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ph = 2 * c + (i >> 4), pw = i & 15;
+            const bool ok = (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
+            const float s2 = fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw];
+            mt = fmaxf(mt, ok ? s2 : -INFINITY);
+          }
         }
       }
       const float mn = fmaxf(m, mt);
-      const float alpha = exp2f(m - mn);
+      const float alpha = ex2(m - mn);
+#pragma unroll
+      for (int i = 0; i < kPH; ++i) th[i] -= mn;        // the exponent's offset rides in the row term
       float lp = 0.f;
       uint8_t* sP0 = sK + buf * kTileBytes;
 #pragma unroll
@@ -202,13 +217,20 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
         tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
         tmem_ld_wait();
         float p[32];
+        if (interior) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * c + (i >> 4), pw = i & 15;
-          const bool ok = (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
-          const float s2 = __uint_as_float(raw[i]) * a.scale_log2 + th[ph] + tw[pw];
-          p[i] = ok ? exp2f(s2 - mn) : 0.f;
-          lp += p[i];
+          for (int i = 0; i < 32; ++i) {
+            p[i] = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[2 * c + (i >> 4)]) + tw[i & 15]);
+            lp += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ph = 2 * c + (i >> 4), pw = i & 15;
+            const bool ok = (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
+            p[i] = ok ? ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw]) : 0.f;
+            lp += p[i];
+          }
         }
         uint8_t* dst = (c < 2) ? sP0 : sP1;
 #pragma unroll
@@ -264,10 +286,13 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // backward, query side: dq, drelpos, delta
+// Warps 0-7: TWO threads per query row -- warpgroup 0 takes key columns 0-63 of a tile (patch rows 0-3), warpgroup 1 columns
+// 64-127 (patch rows 4-7); warp 8 lane 0 issues TMA + MMA.  One CTA per SM (TMEM: S 128 + dP 128 + dQ 64 columns).
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 288;
 __host__ __device__ constexpr int dq_smem_bytes(int tiles_w) { return 8 * kTileBytes + tiles_w * kPW * kTile * 4 + 1024; }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -276,7 +301,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   uint8_t* sK = sDO + kTileBytes;       // [2]
   uint8_t* sV = sK + 2 * kTileBytes;    // [2]
   uint8_t* sDS = sV + 2 * kTileBytes;   // [2 chunks of 64 keys]
-  float* sDtw = reinterpret_cast<float*>(sDS + 2 * kTileBytes);   // [key column][row]
+  float* sDtw = reinterpret_cast<float*>(sDS + 2 * kTileBytes);   // [key column][row]: column sums of dS over the key rows
   __shared__ __align__(8) uint64_t q_bar, kv_bar[2], s_bar, o_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -295,14 +320,16 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     mbar_init(&o_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<512>(&tmem_base_smem);
+  if (warp == 8) tmem_alloc<512>(&tmem_base_smem);
+  if (a.relpos)
+    for (int i = tid; i < a.tiles_w * kPW * kTile; i += kBwdThreads) sDtw[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(&q_bar, 2 * kTileBytes);
       tma_load_4d(sQ, &tmQKV, &q_bar, h * 64, qw0, qh0, b);
@@ -350,7 +377,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       __syncwarp();
     }
   } else {
-    const int r = tid;
+    const int r = tid & 127, half = tid >> 7;      // row of the query tile; which 64 key columns of every tile
     const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
     const bool valid_q = qh < a.gh && qw < a.gw;
     const int tn = a.gh * a.gw;
@@ -359,9 +386,9 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     const long long roff = (tok * a.heads + h) * a.rp_stride;
     const float* trow = (a.relpos && valid_q) ? a.relpos + roff : nullptr;
     float* drow = (a.relpos && valid_q) ? a.drelpos + roff : nullptr;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const long long stat = ((long long)b * a.heads + h) * tn + qtok;
-    // delta = rowsum(dO * O); lse in the exp2 domain
+    // delta = rowsum(dO * O); lse in the exp2 domain (both threads of a row compute them)
     float delta = 0.f;
     {
       const long long orow = (long long)b * a.out_batch_stride + (long long)qtok * a.out_stride + h * 64;
@@ -380,26 +407,33 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       }
     }
     const float lse2 = a.lse[stat] * kLog2e;
-    if (valid_q) a.delta[stat] = delta;
-    if (drow) {
-      for (int c = 0; c < a.rp_stride; ++c) drow[c] = 0.f;
-      for (int kw = 0; kw < a.tiles_w * kPW; ++kw) sDtw[kw * kTile + r] = 0.f;
+    if (valid_q && half == 0) a.delta[stat] = delta;
+    if (drow) {      // every column of the row is written: zeros first, the touched columns below
+      const int c0 = half ? a.rp_stride / 2 : 0, c1 = half ? a.rp_stride : a.rp_stride / 2;
+      for (int c = c0; c < c1; ++c) drow[c] = 0.f;
     }
-    float dth[kPH];
+    named_bar_sync(1, 256);      // the row's two threads zero one half each and later write columns in either half
+    float dth[4];
 #pragma unroll
-    for (int i = 0; i < kPH; ++i) dth[i] = 0.f;
+    for (int i = 0; i < 4; ++i) dth[i] = 0.f;
     for (int kt = 0; kt < nkt; ++kt) {
       const int ktw = kt % a.tiles_w;
-      const int kh0 = (kt / a.tiles_w) * kPH, kw0 = ktw * kPW;
-      float th[kPH], tw[kPW], dtw[kPW];
-      load_bias(trow, a, qh, qw, kh0, kw0, th, tw);
+      const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = ktw * kPW;     // this thread's 4 x 16 keys
+      float th[4], tw[kPW], dtw[kPW];
 #pragma unroll
-      for (int i = 0; i < kPW; ++i) dtw[i] = 0.f;
+      for (int i = 0; i < 4; ++i) th[i] = (trow && kh0 + i < a.gh) ? __ldg(trow + a.gh - 1 + qh - kh0 - i) * kLog2e - lse2 : -lse2;
+#pragma unroll
+      for (int i = 0; i < kPW; ++i) {
+        tw[i] = (trow && kw0 + i < a.gw) ? __ldg(trow + 2 * a.gh - 1 + a.gw - 1 + qw - kw0 - i) * kLog2e : 0.f;
+        dtw[i] = 0.f;
+      }
+      const bool interior = valid_q && (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
       mbar_wait(&s_bar, kt & 1);
       __syncwarp();
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cl = 0; cl < 2; ++cl) {
+        const int c = 2 * half + cl;           // 32-column chunk of the tile
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
         tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
@@ -407,10 +441,9 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         float ds[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * c + (i >> 4), pw = i & 15;
-          const bool ok = valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
-          const float s2 = __uint_as_float(rs[i]) * a.scale_log2 + th[ph] + tw[pw];
-          const float p = ok ? exp2f(s2 - lse2) : 0.f;
+          const int ph = 2 * cl + (i >> 4), pw = i & 15;
+          float p = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
+          if (!interior) p = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p : 0.f;
           ds[i] = p * (__uint_as_float(rp[i]) - delta);
           dth[ph] += ds[i];
           dtw[pw] += ds[i];
@@ -422,17 +455,16 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           v.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
           v.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
           v.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-          *reinterpret_cast<uint4*>(sDS + (c >> 1) * kTileBytes + swz128(r, (c & 1) * 4 + g)) = v;
+          *reinterpret_cast<uint4*>(sDS + half * kTileBytes + swz128(r, cl * 4 + g)) = v;
         }
       }
       if (drow) {
 #pragma unroll
-        for (int i = 0; i < kPW; ++i) sDtw[(kw0 + i) * kTile + r] += dtw[i];
+        for (int i = 0; i < kPW; ++i) atomicAdd(&sDtw[(kw0 + i) * kTile + r], dtw[i]);    // shared with the row's other thread
         if (ktw == a.tiles_w - 1) {      // this key-row band is complete: every column index is written exactly once
 #pragma unroll
-          for (int i = 0; i < kPH; ++i) {
-            const int kh = kh0 + i;
-            if (kh < a.gh) drow[a.gh - 1 + qh - kh] = dth[i];
+          for (int i = 0; i < 4; ++i) {
+            if (kh0 + i < a.gh) drow[a.gh - 1 + qh - kh0 - i] = dth[i];
             dth[i] = 0.f;
           }
         }
@@ -445,42 +477,45 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     }
     tc_fence_after();
     // tcgen05.ld is warp-collective: rows outside the grid load too, only the stores are predicated
-    uint32_t raw[2][32];
-    tmem_ld_32x32(tmem_dq + lane_off, raw[0]);
-    tmem_ld_32x32(tmem_dq + lane_off + 32, raw[1]);
+    uint32_t raw[32];
+    tmem_ld_32x32(tmem_dq + lane_off + half * 32, raw);
     tmem_ld_wait();
     if (valid_q) {
-      __nv_bfloat16* dqrow = a.dqkv + (long long)b * a.batch_stride + (long long)qtok * a.row_stride + h * 64;
+      __nv_bfloat16* dqrow = a.dqkv + (long long)b * a.batch_stride + (long long)qtok * a.row_stride + h * 64 + half * 32;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack2(__uint_as_float(raw[c][8 * g]) * a.scale, __uint_as_float(raw[c][8 * g + 1]) * a.scale);
-          v.y = pack2(__uint_as_float(raw[c][8 * g + 2]) * a.scale, __uint_as_float(raw[c][8 * g + 3]) * a.scale);
-          v.z = pack2(__uint_as_float(raw[c][8 * g + 4]) * a.scale, __uint_as_float(raw[c][8 * g + 5]) * a.scale);
-          v.w = pack2(__uint_as_float(raw[c][8 * g + 6]) * a.scale, __uint_as_float(raw[c][8 * g + 7]) * a.scale);
-          *reinterpret_cast<uint4*>(dqrow + c * 32 + 8 * g) = v;
-        }
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack2(__uint_as_float(raw[8 * g]) * a.scale, __uint_as_float(raw[8 * g + 1]) * a.scale);
+        v.y = pack2(__uint_as_float(raw[8 * g + 2]) * a.scale, __uint_as_float(raw[8 * g + 3]) * a.scale);
+        v.z = pack2(__uint_as_float(raw[8 * g + 4]) * a.scale, __uint_as_float(raw[8 * g + 5]) * a.scale);
+        v.w = pack2(__uint_as_float(raw[8 * g + 6]) * a.scale, __uint_as_float(raw[8 * g + 7]) * a.scale);
+        *reinterpret_cast<uint4*>(dqrow + 8 * g) = v;
       }
-      if (drow)
-        for (int kw = 0; kw < a.gw; ++kw) drow[2 * a.gh - 1 + a.gw - 1 + qw - kw] = sDtw[kw * kTile + r];
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
+  __syncthreads();      // all shared-memory column sums are final
+  if (warp < 8 && a.relpos) {
+    const int r = tid & 127, half = tid >> 7;
+    const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
+    if (qh < a.gh && qw < a.gw) {
+      float* drow = a.drelpos + (((long long)b * a.gh * a.gw + qh * a.gw + qw) * a.heads + h) * a.rp_stride;
+      const int k0 = half ? a.gw / 2 : 0, k1 = half ? a.gw : a.gw / 2;
+      for (int kw = k0; kw < k1; ++kw) drow[2 * a.gh - 1 + a.gw - 1 + qw - kw] = sDtw[kw * kTile + r];
+    }
+  }
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, key side: dk, dv
+// backward, key side: dk, dv   (same thread layout: two threads per query row of the current query tile)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDkvSmem = 10 * kTileBytes + 1024;   // K, V, Q x2, dO x2, P (2 chunks), dS (2 chunks)
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -508,14 +543,14 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(&o_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<512>(&tmem_base_smem);
+  if (warp == 8) tmem_alloc<512>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(&k_bar, 2 * kTileBytes);
       tma_load_4d(sK, &tmQKV, &k_bar, a.dim + h * 64, kw0, kh0, b);
@@ -563,9 +598,10 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       __syncwarp();
     }
   } else {
-    const int r = tid;
+    const int r = tid & 127, half = tid >> 7;
     const int tn = a.gh * a.gw;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int khh = kh0 + 4 * half;            // this thread's 4 x 16 keys of the CTA's key tile
     for (int qt = 0; qt < nqt; ++qt) {
       const int qh = (qt / a.tiles_w) * kPH + r / kPW, qw = (qt % a.tiles_w) * kPW + r % kPW;
       const bool valid_q = qh < a.gh && qw < a.gw;
@@ -575,13 +611,18 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const long long stat = ((long long)b * a.heads + h) * tn + qtok;
       const float lse2 = __ldg(a.lse + stat) * kLog2e;
       const float delta = __ldg(a.delta + stat);
-      float th[kPH], tw[kPW];
-      load_bias(trow, a, qh, qw, kh0, kw0, th, tw);
+      float th[4], tw[kPW];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) th[i] = (trow && khh + i < a.gh) ? __ldg(trow + a.gh - 1 + qh - khh - i) * kLog2e - lse2 : -lse2;
+#pragma unroll
+      for (int i = 0; i < kPW; ++i) tw[i] = (trow && kw0 + i < a.gw) ? __ldg(trow + 2 * a.gh - 1 + a.gw - 1 + qw - kw0 - i) * kLog2e : 0.f;
+      const bool interior = valid_q && (khh + 4 <= a.gh) && (kw0 + kPW <= a.gw);
       mbar_wait(&s_bar, qt & 1);
       __syncwarp();
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cl = 0; cl < 2; ++cl) {
+        const int c = 2 * half + cl;
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
         tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
@@ -589,11 +630,11 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float p[32], ds[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * c + (i >> 4), pw = i & 15;
-          const bool ok = valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
-          const float s2 = __uint_as_float(rs[i]) * a.scale_log2 + th[ph] + tw[pw];
-          p[i] = ok ? exp2f(s2 - lse2) : 0.f;
-          ds[i] = p[i] * (__uint_as_float(rp[i]) - delta);
+          const int ph = 2 * cl + (i >> 4), pw = i & 15;
+          float pv = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
+          if (!interior) pv = (valid_q && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
+          p[i] = pv;
+          ds[i] = pv * (__uint_as_float(rp[i]) - delta);
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -606,7 +647,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           w.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
           w.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
           w.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-          const uint32_t off = (c >> 1) * kTileBytes + swz128(r, (c & 1) * 4 + g);
+          const uint32_t off = half * kTileBytes + swz128(r, cl * 4 + g);
           *reinterpret_cast<uint4*>(sP + off) = v;
           *reinterpret_cast<uint4*>(sDS + off) = w;
         }
@@ -618,36 +659,33 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       __syncwarp();
     }
     tc_fence_after();
-    // this thread's TMEM lane = key row r of the CTA's key tile
+    // TMEM lane = key row r of the CTA's key tile; warpgroup 0 writes dV, warpgroup 1 dK
     const int kh = kh0 + r / kPW, kw = kw0 + r % kPW;
     const bool valid_k = kh < a.gh && kw < a.gw;
-    __nv_bfloat16* drow = a.dqkv + (long long)b * a.batch_stride + (long long)(valid_k ? kh * a.gw + kw : 0) * a.row_stride + h * 64;
+    const float sc = half ? a.scale : 1.f;
+    __nv_bfloat16* dst = a.dqkv + (long long)b * a.batch_stride + (long long)(valid_k ? kh * a.gw + kw : 0) * a.row_stride + h * 64 +
+                         (half ? a.dim : 2 * a.dim);
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {       // 0: dV -> v third, 1: dK -> k third
-      const float sc = which ? a.scale : 1.f;
-      __nv_bfloat16* dst = drow + (which ? a.dim : 2 * a.dim);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32((half ? tmem_dk : tmem_dv) + lane_off + c * 32, raw);
+      tmem_ld_wait();
+      if (valid_k) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32((which ? tmem_dk : tmem_dv) + lane_off + c * 32, raw);
-        tmem_ld_wait();
-        if (valid_k) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 v;
-            v.x = pack2(__uint_as_float(raw[8 * g]) * sc, __uint_as_float(raw[8 * g + 1]) * sc);
-            v.y = pack2(__uint_as_float(raw[8 * g + 2]) * sc, __uint_as_float(raw[8 * g + 3]) * sc);
-            v.z = pack2(__uint_as_float(raw[8 * g + 4]) * sc, __uint_as_float(raw[8 * g + 5]) * sc);
-            v.w = pack2(__uint_as_float(raw[8 * g + 6]) * sc, __uint_as_float(raw[8 * g + 7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * g) = v;
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack2(__uint_as_float(raw[8 * g]) * sc, __uint_as_float(raw[8 * g + 1]) * sc);
+          v.y = pack2(__uint_as_float(raw[8 * g + 2]) * sc, __uint_as_float(raw[8 * g + 3]) * sc);
+          v.z = pack2(__uint_as_float(raw[8 * g + 4]) * sc, __uint_as_float(raw[8 * g + 5]) * sc);
+          v.w = pack2(__uint_as_float(raw[8 * g + 6]) * sc, __uint_as_float(raw[8 * g + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + c * 32 + 8 * g) = v;
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -744,10 +782,10 @@ int aldi_attention_backward_tc(const aldi_attn_params* p, cudaStream_t stream) {
     dkv_attr = true;
   }
   const dim3 grid(a.tiles_h * a.tiles_w, p->heads, p->batch);
-  attn_bwd_dq_tc<<<grid, kThreads, dq_smem, stream>>>(tmQKV, tmDO, a);
+  attn_bwd_dq_tc<<<grid, kBwdThreads, dq_smem, stream>>>(tmQKV, tmDO, a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_attention_backward(dq)");
-  attn_bwd_dkv_tc<<<grid, kThreads, kDkvSmem, stream>>>(tmQKV, tmDO, a);
+  attn_bwd_dkv_tc<<<grid, kBwdThreads, kDkvSmem, stream>>>(tmQKV, tmDO, a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_attention_backward(dkv)");
   return ALDI_OK;

@@ -23,6 +23,7 @@ Parity: tests/test_gpu_vit.py holds every stage against oracle/vit_ref.py (parit
 /root/reference).
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -222,8 +223,12 @@ class _Gemm:
     def backward(self, x, dy, want_dx=True, dx=None, accumulate=False):
         net = self.net
         pad = self.k // 2
-        ops.wgrad(x, dy, self.gview(), taps_h=self.k, taps_w=self.k, pad_h=pad, pad_w=pad, cout_store=self.cout, cin_store=self.cin)
-        if self.bias_key:
+        # bf16: a plain bias gradient rides on the weight-gradient pass (column sums of the dy tiles it already stages in
+        # shared memory, as in the ConvNeXt blocks); ALDI_VIT_COLSUM=1 keeps the separate aldi_colsum pass (A/B knob)
+        fused = bool(self.bias_key) and self.bias_rep == 1 and dy.dtype == torch.bfloat16 and os.environ.get("ALDI_VIT_COLSUM") != "1"
+        ops.wgrad(x, dy, self.gview(), taps_h=self.k, taps_w=self.k, pad_h=pad, pad_w=pad, cout_store=self.cout, cin_store=self.cin,
+                  dbias=net.view(self.bias_key, net.grad) if fused else None)
+        if self.bias_key and not fused:
             db = net.view(self.bias_key, net.grad)
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             assert dy.is_contiguous()

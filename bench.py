@@ -36,7 +36,8 @@ CONVNEXT_L = ((3, 3, 27, 3), (192, 384, 768, 1536))
 def select_config(name):
     """--config: rcnn_r50 = BASELINE configs[1] (the headline, default); convnext_l = BASELINE configs[4]: ALDI++ Faster R-CNN
     on ConvNeXt-L FPN (configs/Base-RCNN-ConvNeXt-FPN.yaml), CFC frames 1920x1080 resized to 1024x1820 -> 1024x1824 canvas,
-    2 source + 2 target images per GPU, AdamW, DropPath 0.2."""
+    2 source + 2 target images per GPU, AdamW, DropPath 0.2; vitdet_b = BASELINE configs[2]: ALDI++ ViTDet-B
+    (configs/Base-RCNN-VitDetB.yaml: IMS_PER_BATCH 48 on 8 GPUs = 3 source + 3 target images per GPU, IMS_PER_GPU 1), 1024^2."""
     global METRIC, H, W, N_SRC, N_TGT, IMS_PER_GPU, WORKLOAD, CONFIG
     CONFIG = name
     if name == "convnext_l":
@@ -45,13 +46,25 @@ def select_config(name):
         WORKLOAD = ("ALDI++ Faster R-CNN ConvNeXt-L FPN (BASELINE configs[4]): synthetic %dx%d (CFC 1920x1080 frame resized), "
                     "%d source + %d target images per GPU, IMS_PER_GPU %d, ALDI-Best distillation flags, K=8, AdamW, DropPath 0.2"
                     % (H, W, N_SRC, N_TGT, IMS_PER_GPU))
+    if name == "vitdet_b":
+        METRIC = "ALDI++ ViTDet-B train-step images/sec"
+        H, W, N_SRC, N_TGT, IMS_PER_GPU = 1024, 1024, 3, 3, 1
+        WORKLOAD = ("ALDI++ ViTDet-B (BASELINE configs[2], configs/Base-RCNN-VitDetB.yaml): synthetic %dx%d, %d source + %d "
+                    "target images per GPU, IMS_PER_GPU %d, ALDI-Best distillation flags, K=8, AdamW with layer-wise lr decay "
+                    "0.7, DropPath 0.1, tcgen05 windowed (14x14) + global attention" % (H, W, N_SRC, N_TGT, IMS_PER_GPU))
 
 
 def build_step(args, device, pg):
     """-> (B200TrainStep, StepConfig) of the selected workload on synthetic random-init weights."""
     from aldi_b200 import arch
     from aldi_b200.train_step import B200TrainStep, StepConfig
-    if CONFIG == "convnext_l":
+    if CONFIG == "vitdet_b":
+        from aldi_b200.train_step import synthetic_state_dict_for
+        cfg = StepConfig(dtype="bf16", ims_per_gpu=args.ims_per_gpu or IMS_PER_GPU, backbone="vitdet_b", optimizer="ADAMW",
+                         base_lr=1e-4 if args.base_lr is None else args.base_lr, weight_decay=0.1,
+                         pixel_mean=(123.675, 116.28, 103.53), pixel_std=(58.395, 57.12, 57.375), cuda_graph=not args.no_graph)
+        sd = synthetic_state_dict_for(cfg, 0)
+    elif CONFIG == "convnext_l":
         from aldi_b200.convnext import synthetic_state_dict as convnext_init
         depths, dims = CONVNEXT_L
         sd = arch.synthetic_state_dict(0, bottom_up_channels=dims)
@@ -121,8 +134,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_data(seed, pinned, h=H, w=W):
+def make_data(seed, pinned, h=None, w=None):
     from aldi_b200 import synth_data
+    h, w = h or H, w or W            # the SELECTED config's canvas (select_config rebinds the globals after import)
     ls, uw, us = synth_data.synthetic_batch(seed, N_SRC, N_TGT, h, w, num_boxes=12)
     if pinned:
         for b in (ls, uw, us):
@@ -521,6 +535,17 @@ def run_ours(args):
                                           # tensor-argument bytes / time: the HBM rate of the elementwise / gather kernels
                                           "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] else None}
                                       for k, v in summ.items() if k != "aldi_conv_tc"}}
+        if CONFIG == "vitdet_b" and "aldi_attention_forward" in summ:
+            # BASELINE configs[2] names the tensor-core ViT attention path: its kernels against the bf16 tensor peak
+            # (algorithmic flops: 4 T^2 64 per head forward, 10 T^2 64 backward; the backward recomputes S and dP on top)
+            att = {}
+            for nm in ("aldi_attention_forward", "aldi_attention_backward"):
+                d = summ.get(nm)
+                if d:
+                    t = d["flops"] / (d["ms"] * 1e-3) / 1e12
+                    att[nm] = {"achieved": t, "peak": peak, "unit": "TFLOP/s", "frac": t / peak, "ms_per_step": d["ms"],
+                               "launches_per_step": d["launches"]}
+            roofline["attention_kernels"] = att
         if CONFIG == "convnext_l" and "aldi_dwconv7" in summ:
             # BASELINE configs[4] is the HBM-bound high-resolution path: the depthwise 7x7 stencil against the copy peak
             d = summ["aldi_dwconv7"]
@@ -686,8 +711,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="rcnn_r50", choices=["rcnn_r50", "convnext_l"],
-                    help="rcnn_r50: BASELINE configs[1], the headline (default); convnext_l: BASELINE configs[4]")
+    ap.add_argument("--config", default="rcnn_r50", choices=["rcnn_r50", "convnext_l", "vitdet_b"],
+                    help="rcnn_r50: BASELINE configs[1], the headline (default); convnext_l: BASELINE configs[4]; vitdet_b: "
+                         "BASELINE configs[2]")
+    ap.add_argument("--ims-per-gpu", type=int, default=0, help="override SOLVER.IMS_PER_GPU (micro-batch size) of the config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-deviation", action="store_true", help="skip the bf16-vs-fp32-level comparison of one full-size step")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying CUDA graphs")
