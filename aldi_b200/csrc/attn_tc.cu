@@ -14,7 +14,6 @@
 //            row / column sums of dS are the gradient of the relative-position products (drelpos).
 //   backward dkv (CTA = key tile, loop over query tiles): S, dP as above (thread = query row), P and dS staged ONCE and
 //            read through MN-major descriptors as P^T / dS^T: dV += P^T dO, dK += dS^T Q in TMEM.
-// Warps 0-3: one thread per tile row (softmax / gradient math, TMEM loads); warp 4 lane 0: TMA + MMA issue.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tmap.h"
@@ -27,15 +26,16 @@ namespace {
 constexpr int kPW = 16, kPH = 8;          // token patch of a tile
 constexpr int kTile = kPW * kPH;          // 128 tokens = UMMA M
 constexpr int kTileBytes = kTile * 128;   // 128 rows x 64 bf16
-constexpr int kThreads = 160;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct TcArgs {
-  int gh, gw, heads, dim, tiles_h, tiles_w, rp_stride;
+  int gh, gw, heads, dim, tiles_h, tiles_w;
   float scale, scale_log2;
-  const float* relpos;
-  float* drelpos;
+  const float* rel_h;      // key-major relative-position products: [(b, h, kh), q] / [(b, h, kw), q], query index fastest
+  const float* rel_w;
+  float* drel_h;
+  float* drel_w;
   float* lse;
   float* delta;
   __nv_bfloat16* out;
@@ -67,26 +67,28 @@ __device__ __forceinline__ uint64_t desc_mnmajor(const uint8_t* tile, uint32_t l
   return make_smem_desc_sw128(smem_u32(tile), lbo, 1024);
 }
 
-// relative-position terms of one (query row, key tile), pre-multiplied by log2(e): 8 key rows + 16 key columns
-__device__ __forceinline__ void load_bias(const float* trow, const TcArgs& a, int qh, int qw, int kh0, int kw0, float* th, float* tw) {
-#pragma unroll
-  for (int i = 0; i < kPH; ++i) {
-    const int kh = kh0 + i;
-    th[i] = (trow && kh < a.gh) ? __ldg(trow + a.gh - 1 + qh - kh) * kLog2e : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < kPW; ++i) {
-    const int kw = kw0 + i;
-    tw[i] = (trow && kw < a.gw) ? __ldg(trow + 2 * a.gh - 1 + a.gw - 1 + qw - kw) * kLog2e : 0.f;
-  }
-}
+// ---------------------------------------------------------------------------------------------------------------------
+// Thread layout of all three kernels: 256 threads, TWO threads per tile row (TMEM lane): warps 0-3 take key columns 0-63 of
+// every tile (patch rows 0-3), warps 4-7 columns 64-127 (patch rows 4-7).  Thread 0 also issues TMA and MMA between the
+// phases -- the products of the NEXT tile are issued right behind the current tile's second product, so the tensor pipe works
+// while the rows are read back.  (A ninth issuer warp would put three warps on one scheduler and cap every thread at 168
+// registers.)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kCompute = 256;
+
+struct RowCtx {
+  int r, half, qh, qw;
+  bool valid;
+  uint32_t lane_off;
+};
 
 // ---------------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kFwdSmem = 6 * kTileBytes + 1024;   // Q, K x2 (P chunk 0 reuses the K buffer S has consumed), V x2, P chunk 1
+constexpr int kFwdSmem = 6 * kTileBytes + 2048 + 1024;   // Q, K x2 (P chunk 0 reuses the K buffer S has consumed), V x2, P chunk 1,
+                                                          // row-max / row-sum exchange between the two threads of a row
 
-__global__ void __launch_bounds__(kThreads, 2)      // two CTAs per SM: one's softmax overlaps the other's MMAs / TMEM latency
+__global__ void __launch_bounds__(kCompute, 2)      // two CTAs per SM: one's softmax overlaps the other's MMAs / TMEM latency
 attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -94,13 +96,16 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
   uint8_t* sK = sQ + kTileBytes;        // [2]
   uint8_t* sV = sK + 2 * kTileBytes;    // [2]
   uint8_t* sP1 = sV + 2 * kTileBytes;   // keys 64-127 of P; keys 0-63 go to sK[buf]
+  float* sX = reinterpret_cast<float*>(sP1 + kTileBytes);   // [2][128]
   __shared__ __align__(8) uint64_t q_bar, kv_bar[2], s_bar, o_bar;
   __shared__ uint32_t tmem_base_smem;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int qh0 = (qt / a.tiles_w) * kPH, qw0 = (qt % a.tiles_w) * kPW;
   const int nkt = a.tiles_h * a.tiles_w;
+  constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
+  constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, 64, 0, 1);
 
   if (tid == 0) {
     prefetch_tmap(&tmQKV);
@@ -111,188 +116,171 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
     mbar_init(&o_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<256>(&tmem_base_smem);
+  if (warp == 0) tmem_alloc<256>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
-  if (warp == 4) {
-    // ------------------------------------------------ issuer ------------------------------------------------
-    if (lane == 0) {
-      mbar_expect_tx(&q_bar, kTileBytes);
-      tma_load_4d(sQ, &tmQKV, &q_bar, h * 64, qw0, qh0, b);
-      mbar_expect_tx(&kv_bar[0], 2 * kTileBytes);
-      tma_load_4d(sK, &tmQKV, &kv_bar[0], a.dim + h * 64, 0, 0, b);
-      tma_load_4d(sV, &tmQKV, &kv_bar[0], 2 * a.dim + h * 64, 0, 0, b);
+  auto load_kv = [&](int kt) {       // thread 0: K and V patches of key tile kt into buffer kt & 1
+    const int buf = kt & 1, kh0 = (kt / a.tiles_w) * kPH, kw0 = (kt % a.tiles_w) * kPW;
+    mbar_expect_tx(&kv_bar[buf], 2 * kTileBytes);
+    tma_load_4d(sK + buf * kTileBytes, &tmQKV, &kv_bar[buf], a.dim + h * 64, kw0, kh0, b);
+    tma_load_4d(sV + buf * kTileBytes, &tmQKV, &kv_bar[buf], 2 * a.dim + h * 64, kw0, kh0, b);
+  };
+  auto issue_s = [&](int kt) {       // thread 0: S = Q K^T of key tile kt
+    const int buf = kt & 1;
+    mbar_wait(&kv_bar[buf], (kt >> 1) & 1);
+    tc_fence_after();
+    const uint64_t ad = desc_kmajor(sQ), bd = desc_kmajor(sK + buf * kTileBytes);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
+    umma_commit(&s_bar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&q_bar, kTileBytes);
+    tma_load_4d(sQ, &tmQKV, &q_bar, h * 64, qw0, qh0, b);
+    load_kv(0);
+    if (nkt > 1) load_kv(1);
+    mbar_wait(&q_bar, 0);
+    issue_s(0);
+  }
+  __syncwarp();
+
+  const int r = tid & 127, half = tid >> 7;
+  const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
+  const bool valid_q = qh < a.gh && qw < a.gw;
+  const int tn = a.gh * a.gw;
+  const long long bh = (long long)b * a.heads + h;
+  const float* rh = (a.rel_h && valid_q) ? a.rel_h + bh * a.gh * tn + qh * a.gw + qw : nullptr;
+  const float* rw = (a.rel_h && valid_q) ? a.rel_w + bh * a.gw * tn + qh * a.gw + qw : nullptr;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  float o[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = (kt % a.tiles_w) * kPW;     // this thread's 4 x 16 keys
+    float th[4], tw[kPW];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) th[i] = (rh && kh0 + i < a.gh) ? __ldg(rh + (long long)(kh0 + i) * tn) * kLog2e : 0.f;
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) * kLog2e : 0.f;
+    const bool interior = (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
+    mbar_wait(&s_bar, kt & 1);
+    __syncwarp();
+    tc_fence_after();
+    float mt = -INFINITY;
+#pragma unroll
+    for (int cl = 0; cl < 2; ++cl) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_s + lane_off + (2 * half + cl) * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ph = 2 * cl + (i >> 4), pw = i & 15;
+        const float s2 = fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw];
+        mt = fmaxf(mt, (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? s2 : -INFINITY);
+      }
     }
-    constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, 64, 0, 1);
-    for (int kt = 0; kt < nkt; ++kt) {
-      const int buf = kt & 1;
-      if (lane == 0) {
-        if (kt == 0) mbar_wait(&q_bar, 0);
-        mbar_wait(&kv_bar[buf], (kt >> 1) & 1);
-        tc_fence_after();
-        const uint64_t ad = desc_kmajor(sQ), bd = desc_kmajor(sK + buf * kTileBytes);
+    sX[half * kTile + r] = mt;
+    __syncthreads();
+    const float mn = fmaxf(m, fmaxf(mt, sX[(half ^ 1) * kTile + r]));     // >= one valid key per tile: finite
+    const float alpha = ex2(m - mn);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_bar);
-        if (kt + 1 < nkt) {
-          if (kt > 0) mbar_wait(&o_bar, (kt - 1) & 1);   // P V of tile kt-1 has finished reading the other buffers
-          const int nk = kt + 1, kh0 = (nk / a.tiles_w) * kPH, kw0 = (nk % a.tiles_w) * kPW;
-          mbar_expect_tx(&kv_bar[buf ^ 1], 2 * kTileBytes);
-          tma_load_4d(sK + (buf ^ 1) * kTileBytes, &tmQKV, &kv_bar[buf ^ 1], a.dim + h * 64, kw0, kh0, b);
-          tma_load_4d(sV + (buf ^ 1) * kTileBytes, &tmQKV, &kv_bar[buf ^ 1], 2 * a.dim + h * 64, kw0, kh0, b);
-        }
+    for (int i = 0; i < 4; ++i) th[i] -= mn;        // the exponent's offset rides in the row term
+    float lp = 0.f;
+    uint8_t* dst = half ? sP1 : sK + buf * kTileBytes;
+#pragma unroll
+    for (int cl = 0; cl < 2; ++cl) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_s + lane_off + (2 * half + cl) * 32, raw);
+      tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ph = 2 * cl + (i >> 4), pw = i & 15;
+        const float e = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw]);
+        p[i] = (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? e : 0.f;
+        lp += p[i];
       }
-      __syncwarp();
-      __syncthreads();     // P of this tile is in shared memory
-      if (lane == 0) {
-        tc_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const uint64_t ad = desc_kmajor(cc == 0 ? sK + buf * kTileBytes : sP1);
-          const uint64_t bd = desc_mnmajor(sV + buf * kTileBytes + cc * 8192, 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, ad + 2 * k, bd + 128 * k, idesc_pv, (cc | k) != 0);
-        }
-        umma_commit(&o_bar);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------ one thread per query row ------------------------------------------------
-    const int r = tid;
-    const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
-    const bool valid_q = qh < a.gh && qw < a.gw;
-    const int tn = a.gh * a.gw;
-    const long long tok = (long long)b * tn + (valid_q ? qh * a.gw + qw : 0);
-    const float* trow = (a.relpos && valid_q) ? a.relpos + (tok * a.heads + h) * a.rp_stride : nullptr;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    float o[64];
-#pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    for (int kt = 0; kt < nkt; ++kt) {
-      const int buf = kt & 1;
-      const int kh0 = (kt / a.tiles_w) * kPH, kw0 = (kt % a.tiles_w) * kPW;
-      float th[kPH], tw[kPW];
-      load_bias(trow, a, qh, qw, kh0, kw0, th, tw);
-      mbar_wait(&s_bar, kt & 1);
-      __syncwarp();
-      tc_fence_after();
-      // interior tiles (every key of the patch inside the grid) take the path without per-key masks
-      const bool interior = (kh0 + kPH <= a.gh) && (kw0 + kPW <= a.gw);
-      float mt = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
-        tmem_ld_wait();
-        if (interior) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            mt = fmaxf(mt, fmaf(__uint_as_float(raw[i]), a.scale_log2, th[2 * c + (i >> 4)]) + tw[i & 15]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int ph = 2 * c + (i >> 4), pw = i & 15;
-            const bool ok = (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
-            const float s2 = fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw];
-            mt = fmaxf(mt, ok ? s2 : -INFINITY);
-          }
-        }
-      }
-      const float mn = fmaxf(m, mt);
-      const float alpha = ex2(m - mn);
-#pragma unroll
-      for (int i = 0; i < kPH; ++i) th[i] -= mn;        // the exponent's offset rides in the row term
-      float lp = 0.f;
-      uint8_t* sP0 = sK + buf * kTileBytes;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
-        tmem_ld_wait();
-        float p[32];
-        if (interior) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[2 * c + (i >> 4)]) + tw[i & 15]);
-            lp += p[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int ph = 2 * c + (i >> 4), pw = i & 15;
-            const bool ok = (kh0 + ph < a.gh) && (kw0 + pw < a.gw);
-            p[i] = ok ? ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw]) : 0.f;
-            lp += p[i];
-          }
-        }
-        uint8_t* dst = (c < 2) ? sP0 : sP1;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack2(p[8 * g], p[8 * g + 1]);
-          v.y = pack2(p[8 * g + 2], p[8 * g + 3]);
-          v.z = pack2(p[8 * g + 4], p[8 * g + 5]);
-          v.w = pack2(p[8 * g + 6], p[8 * g + 7]);
-          *reinterpret_cast<uint4*>(dst + swz128(r, (c & 1) * 4 + g)) = v;
-        }
-      }
-      m = mn;
-      l = l * alpha + lp;
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();     // -> issuer: P V
-      mbar_wait(&o_bar, kt & 1);
-      __syncwarp();
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_o + lane_off + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(raw[i]);
-      }
-      tc_fence_before();
-    }
-    if (valid_q) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* orow = a.out + (long long)b * a.out_batch_stride + (long long)(qh * a.gw + qw) * a.out_stride + h * 64;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 v;
-        v.x = pack2(o[8 * g] * inv, o[8 * g + 1] * inv);
-        v.y = pack2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-        v.z = pack2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-        v.w = pack2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + 8 * g) = v;
+        v.x = pack2(p[8 * g], p[8 * g + 1]);
+        v.y = pack2(p[8 * g + 2], p[8 * g + 3]);
+        v.z = pack2(p[8 * g + 4], p[8 * g + 5]);
+        v.w = pack2(p[8 * g + 6], p[8 * g + 7]);
+        *reinterpret_cast<uint4*>(dst + swz128(r, cl * 4 + g)) = v;
       }
-      a.lse[((long long)b * a.heads + h) * tn + qh * a.gw + qw] = (m + log2f(l)) * kLn2;
     }
+    m = mn;
+    l = l * alpha + lp;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();     // P of this tile is in shared memory; every thread has finished with S
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint64_t ad = desc_kmajor(cc == 0 ? sK + buf * kTileBytes : sP1);
+        const uint64_t bd = desc_mnmajor(sV + buf * kTileBytes + cc * 8192, 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, ad + 2 * k, bd + 128 * k, idesc_pv, (cc | k) != 0);
+      }
+      umma_commit(&o_bar);
+      if (kt + 1 < nkt) issue_s(kt + 1);      // runs behind P V while the rows below read O back
+    }
+    __syncwarp();
+    mbar_wait(&o_bar, kt & 1);
+    __syncwarp();
+    tc_fence_after();
+    if (tid == 0 && kt + 2 < nkt) load_kv(kt + 2);     // P V has finished with this buffer (V and the P chunk in the K slot)
+    __syncwarp();
+    {
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(raw[i]));
+    }
+    tc_fence_before();
+  }
+  // row sum = both halves
+  __syncthreads();
+  sX[half * kTile + r] = l;
+  __syncthreads();
+  l += sX[(half ^ 1) * kTile + r];
+  if (valid_q) {
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = a.out + (long long)b * a.out_batch_stride + (long long)(qh * a.gw + qw) * a.out_stride + h * 64 + half * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 v;
+      v.x = pack2(o[8 * g] * inv, o[8 * g + 1] * inv);
+      v.y = pack2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+      v.z = pack2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
+      v.w = pack2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+      *reinterpret_cast<uint4*>(orow + 8 * g) = v;
+    }
+    if (half == 0) a.lse[((long long)b * a.heads + h) * tn + qh * a.gw + qw] = (m + log2f(l)) * kLn2;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, query side: dq, drelpos, delta
-// Warps 0-7: TWO threads per query row -- warpgroup 0 takes key columns 0-63 of a tile (patch rows 0-3), warpgroup 1 columns
-// 64-127 (patch rows 4-7); warp 8 lane 0 issues TMA + MMA.  One CTA per SM (TMEM: S 128 + dP 128 + dQ 64 columns).
+// backward, query side: dq, drelpos, delta.  One CTA per SM (TMEM: S 128 + dP 128 + dQ 64 columns).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBwdThreads = 288;
 __host__ __device__ constexpr int dq_smem_bytes(int tiles_w) { return 8 * kTileBytes + tiles_w * kPW * kTile * 4 + 1024; }
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kCompute, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -305,10 +293,12 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   __shared__ __align__(8) uint64_t q_bar, kv_bar[2], s_bar, o_bar;
   __shared__ uint32_t tmem_base_smem;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int qh0 = (qt / a.tiles_w) * kPH, qw0 = (qt % a.tiles_w) * kPW;
   const int nkt = a.tiles_h * a.tiles_w;
+  constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
+  constexpr uint32_t idesc_dq = make_idesc_bf16(kTile, 64, 0, 1);
 
   if (tid == 0) {
     prefetch_tmap(&tmQKV);
@@ -320,163 +310,158 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     mbar_init(&o_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<512>(&tmem_base_smem);
-  if (a.relpos)
-    for (int i = tid; i < a.tiles_w * kPW * kTile; i += kBwdThreads) sDtw[i] = 0.f;
+  if (warp == 0) tmem_alloc<512>(&tmem_base_smem);
+  if (a.rel_h)
+    for (int i = tid; i < a.tiles_w * kPW * kTile; i += kCompute) sDtw[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
 
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_expect_tx(&q_bar, 2 * kTileBytes);
-      tma_load_4d(sQ, &tmQKV, &q_bar, h * 64, qw0, qh0, b);
-      tma_load_4d(sDO, &tmDO, &q_bar, h * 64, qw0, qh0, b);
-      mbar_expect_tx(&kv_bar[0], 2 * kTileBytes);
-      tma_load_4d(sK, &tmQKV, &kv_bar[0], a.dim + h * 64, 0, 0, b);
-      tma_load_4d(sV, &tmQKV, &kv_bar[0], 2 * a.dim + h * 64, 0, 0, b);
+  auto load_kv = [&](int kt) {
+    const int buf = kt & 1, kh0 = (kt / a.tiles_w) * kPH, kw0 = (kt % a.tiles_w) * kPW;
+    mbar_expect_tx(&kv_bar[buf], 2 * kTileBytes);
+    tma_load_4d(sK + buf * kTileBytes, &tmQKV, &kv_bar[buf], a.dim + h * 64, kw0, kh0, b);
+    tma_load_4d(sV + buf * kTileBytes, &tmQKV, &kv_bar[buf], 2 * a.dim + h * 64, kw0, kh0, b);
+  };
+  auto issue_s = [&](int kt) {       // S = Q K^T and dP = dO V^T of key tile kt
+    const int buf = kt & 1;
+    mbar_wait(&kv_bar[buf], (kt >> 1) & 1);
+    tc_fence_after();
+    const uint64_t qd = desc_kmajor(sQ), dod = desc_kmajor(sDO);
+    const uint64_t kd = desc_kmajor(sK + buf * kTileBytes), vd = desc_kmajor(sV + buf * kTileBytes);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_dp, dod + 2 * k, vd + 2 * k, idesc_s, k != 0);
+    umma_commit(&s_bar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&q_bar, 2 * kTileBytes);
+    tma_load_4d(sQ, &tmQKV, &q_bar, h * 64, qw0, qh0, b);
+    tma_load_4d(sDO, &tmDO, &q_bar, h * 64, qw0, qh0, b);
+    load_kv(0);
+    if (nkt > 1) load_kv(1);
+    mbar_wait(&q_bar, 0);
+    issue_s(0);
+  }
+  __syncwarp();
+
+  const int r = tid & 127, half = tid >> 7;      // row of the query tile; which 64 key columns of every tile
+  const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
+  const bool valid_q = qh < a.gh && qw < a.gw;
+  const int tn = a.gh * a.gw;
+  const int qtok = valid_q ? qh * a.gw + qw : 0;
+  const long long bh = (long long)b * a.heads + h;
+  const bool has_rel = a.rel_h && valid_q;
+  const float* rh = has_rel ? a.rel_h + bh * a.gh * tn + qtok : nullptr;
+  const float* rw = has_rel ? a.rel_w + bh * a.gw * tn + qtok : nullptr;
+  float* dh = has_rel ? a.drel_h + bh * a.gh * tn + qtok : nullptr;      // every (key row / column, query) element is written
+  float* dw = has_rel ? a.drel_w + bh * a.gw * tn + qtok : nullptr;      // exactly once: no zero fill
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const long long stat = bh * tn + qtok;
+  // delta = rowsum(dO * O); lse in the exp2 domain (both threads of a row compute them)
+  float delta = 0.f;
+  {
+    const long long orow = (long long)b * a.out_batch_stride + (long long)qtok * a.out_stride + h * 64;
+    const uint4* po = reinterpret_cast<const uint4*>(a.out + orow);
+    const uint4* pd = reinterpret_cast<const uint4*>(a.dout + orow);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 vo = __ldg(po + g), vd = __ldg(pd + g);
+      const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&vo);
+      const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&vd);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fo = __bfloat1622float2(ho[k]), fd = __bfloat1622float2(hd[k]);
+        delta += fo.x * fd.x + fo.y * fd.y;
+      }
     }
-    constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
-    constexpr uint32_t idesc_dq = make_idesc_bf16(kTile, 64, 0, 1);
-    for (int kt = 0; kt < nkt; ++kt) {
-      const int buf = kt & 1;
-      if (lane == 0) {
-        if (kt == 0) mbar_wait(&q_bar, 0);
-        mbar_wait(&kv_bar[buf], (kt >> 1) & 1);
-        tc_fence_after();
-        const uint64_t qd = desc_kmajor(sQ), dod = desc_kmajor(sDO);
-        const uint64_t kd = desc_kmajor(sK + buf * kTileBytes), vd = desc_kmajor(sV + buf * kTileBytes);
+  }
+  const float lse2 = a.lse[stat] * kLog2e;
+  if (valid_q && half == 0) a.delta[stat] = delta;
+  float dth[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);       // S = Q K^T
+  for (int i = 0; i < 4; ++i) dth[i] = 0.f;
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    const int ktw = kt % a.tiles_w;
+    const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = ktw * kPW;     // this thread's 4 x 16 keys
+    float th[4], tw[kPW], dtw[kPW];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_dp, dod + 2 * k, vd + 2 * k, idesc_s, k != 0);     // dP = dO V^T
-        umma_commit(&s_bar);
-        if (kt + 1 < nkt) {
-          if (kt > 0) mbar_wait(&o_bar, (kt - 1) & 1);   // dQ += dS K of tile kt-1 has finished reading the other K buffer
-          const int nk = kt + 1, kh0 = (nk / a.tiles_w) * kPH, kw0 = (nk % a.tiles_w) * kPW;
-          mbar_expect_tx(&kv_bar[buf ^ 1], 2 * kTileBytes);
-          tma_load_4d(sK + (buf ^ 1) * kTileBytes, &tmQKV, &kv_bar[buf ^ 1], a.dim + h * 64, kw0, kh0, b);
-          tma_load_4d(sV + (buf ^ 1) * kTileBytes, &tmQKV, &kv_bar[buf ^ 1], 2 * a.dim + h * 64, kw0, kh0, b);
+    for (int i = 0; i < 4; ++i) th[i] = (rh && kh0 + i < a.gh) ? __ldg(rh + (long long)(kh0 + i) * tn) * kLog2e - lse2 : -lse2;
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) {
+      tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) * kLog2e : 0.f;
+      dtw[i] = 0.f;
+    }
+    const bool interior = valid_q && (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
+    mbar_wait(&s_bar, kt & 1);
+    __syncwarp();
+    tc_fence_after();
+#pragma unroll
+    for (int cl = 0; cl < 2; ++cl) {
+      const int c = 2 * half + cl;           // 32-column chunk of the tile
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
+      tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
+      tmem_ld_wait();
+      float ds[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ph = 2 * cl + (i >> 4), pw = i & 15;
+        float p = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
+        if (!interior) p = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p : 0.f;
+        ds[i] = p * (__uint_as_float(rp[i]) - delta);
+        dth[ph] += ds[i];
+        dtw[pw] += ds[i];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack2(ds[8 * g], ds[8 * g + 1]);
+        v.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
+        v.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
+        v.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
+        *reinterpret_cast<uint4*>(sDS + half * kTileBytes + swz128(r, cl * 4 + g)) = v;
+      }
+    }
+    if (dh) {
+#pragma unroll
+      for (int i = 0; i < kPW; ++i) atomicAdd(&sDtw[(kw0 + i) * kTile + r], dtw[i]);    // shared with the row's other thread
+      if (ktw == a.tiles_w - 1) {      // this band of key rows is complete
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (kh0 + i < a.gh) dh[(long long)(kh0 + i) * tn] = dth[i];
+          dth[i] = 0.f;
         }
       }
-      __syncwarp();
-      __syncthreads();     // dS of this tile is in shared memory
-      if (lane == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const uint64_t ad = desc_kmajor(sDS + cc * kTileBytes);
-          const uint64_t bd = desc_mnmajor(sK + buf * kTileBytes + cc * 8192, 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_dq, ad + 2 * k, bd + 128 * k, idesc_dq, (kt | cc | k) != 0);
-        }
-        umma_commit(&o_bar);
-      }
-      __syncwarp();
     }
-  } else {
-    const int r = tid & 127, half = tid >> 7;      // row of the query tile; which 64 key columns of every tile
-    const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
-    const bool valid_q = qh < a.gh && qw < a.gw;
-    const int tn = a.gh * a.gw;
-    const int qtok = valid_q ? qh * a.gw + qw : 0;
-    const long long tok = (long long)b * tn + qtok;
-    const long long roff = (tok * a.heads + h) * a.rp_stride;
-    const float* trow = (a.relpos && valid_q) ? a.relpos + roff : nullptr;
-    float* drow = (a.relpos && valid_q) ? a.drelpos + roff : nullptr;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const long long stat = ((long long)b * a.heads + h) * tn + qtok;
-    // delta = rowsum(dO * O); lse in the exp2 domain (both threads of a row compute them)
-    float delta = 0.f;
-    {
-      const long long orow = (long long)b * a.out_batch_stride + (long long)qtok * a.out_stride + h * 64;
-      const uint4* po = reinterpret_cast<const uint4*>(a.out + orow);
-      const uint4* pd = reinterpret_cast<const uint4*>(a.dout + orow);
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 vo = __ldg(po + g), vd = __ldg(pd + g);
-        const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&vo);
-        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&vd);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 fo = __bfloat1622float2(ho[k]), fd = __bfloat1622float2(hd[k]);
-          delta += fo.x * fd.x + fo.y * fd.y;
-        }
-      }
-    }
-    const float lse2 = a.lse[stat] * kLog2e;
-    if (valid_q && half == 0) a.delta[stat] = delta;
-    if (drow) {      // every column of the row is written: zeros first, the touched columns below
-      const int c0 = half ? a.rp_stride / 2 : 0, c1 = half ? a.rp_stride : a.rp_stride / 2;
-      for (int c = c0; c < c1; ++c) drow[c] = 0.f;
-    }
-    named_bar_sync(1, 256);      // the row's two threads zero one half each and later write columns in either half
-    float dth[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dth[i] = 0.f;
-    for (int kt = 0; kt < nkt; ++kt) {
-      const int ktw = kt % a.tiles_w;
-      const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = ktw * kPW;     // this thread's 4 x 16 keys
-      float th[4], tw[kPW], dtw[kPW];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) th[i] = (trow && kh0 + i < a.gh) ? __ldg(trow + a.gh - 1 + qh - kh0 - i) * kLog2e - lse2 : -lse2;
-#pragma unroll
-      for (int i = 0; i < kPW; ++i) {
-        tw[i] = (trow && kw0 + i < a.gw) ? __ldg(trow + 2 * a.gh - 1 + a.gw - 1 + qw - kw0 - i) * kLog2e : 0.f;
-        dtw[i] = 0.f;
-      }
-      const bool interior = valid_q && (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
-      mbar_wait(&s_bar, kt & 1);
-      __syncwarp();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();     // dS of this tile is in shared memory; every thread has finished with S and dP
+    if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int cl = 0; cl < 2; ++cl) {
-        const int c = 2 * half + cl;           // 32-column chunk of the tile
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
-        tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
-        tmem_ld_wait();
-        float ds[32];
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint64_t ad = desc_kmajor(sDS + cc * kTileBytes);
+        const uint64_t bd = desc_mnmajor(sK + buf * kTileBytes + cc * 8192, 8192);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * cl + (i >> 4), pw = i & 15;
-          float p = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
-          if (!interior) p = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p : 0.f;
-          ds[i] = p * (__uint_as_float(rp[i]) - delta);
-          dth[ph] += ds[i];
-          dtw[pw] += ds[i];
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack2(ds[8 * g], ds[8 * g + 1]);
-          v.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
-          v.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
-          v.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-          *reinterpret_cast<uint4*>(sDS + half * kTileBytes + swz128(r, cl * 4 + g)) = v;
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_dq, ad + 2 * k, bd + 128 * k, idesc_dq, (kt | cc | k) != 0);      // dQ += dS K
       }
-      if (drow) {
-#pragma unroll
-        for (int i = 0; i < kPW; ++i) atomicAdd(&sDtw[(kw0 + i) * kTile + r], dtw[i]);    // shared with the row's other thread
-        if (ktw == a.tiles_w - 1) {      // this key-row band is complete: every column index is written exactly once
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (kh0 + i < a.gh) drow[a.gh - 1 + qh - kh0 - i] = dth[i];
-            dth[i] = 0.f;
-          }
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();     // -> issuer: dQ += dS K
-      mbar_wait(&o_bar, kt & 1);    // dS buffer and this K tile are free again
-      __syncwarp();
+      umma_commit(&o_bar);
+      if (kt + 1 < nkt) issue_s(kt + 1);
     }
-    tc_fence_after();
-    // tcgen05.ld is warp-collective: rows outside the grid load too, only the stores are predicated
+    __syncwarp();
+    mbar_wait(&o_bar, kt & 1);    // dS buffer and this tile's K / V buffers are free again
+    __syncwarp();
+    if (tid == 0 && kt + 2 < nkt) load_kv(kt + 2);
+    __syncwarp();
+  }
+  tc_fence_after();
+  // tcgen05.ld is warp-collective: rows outside the grid load too, only the stores are predicated
+  {
     uint32_t raw[32];
     tmem_ld_32x32(tmem_dq + lane_off + half * 32, raw);
     tmem_ld_wait();
@@ -495,27 +480,22 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();      // all shared-memory column sums are final
-  if (warp < 8 && a.relpos) {
-    const int r = tid & 127, half = tid >> 7;
-    const int qh = qh0 + r / kPW, qw = qw0 + r % kPW;
-    if (qh < a.gh && qw < a.gw) {
-      float* drow = a.drelpos + (((long long)b * a.gh * a.gw + qh * a.gw + qw) * a.heads + h) * a.rp_stride;
-      const int k0 = half ? a.gw / 2 : 0, k1 = half ? a.gw : a.gw / 2;
-      for (int kw = k0; kw < k1; ++kw) drow[2 * a.gh - 1 + a.gw - 1 + qw - kw] = sDtw[kw * kTile + r];
-    }
+  if (dw) {
+    const int k0 = half ? a.gw / 2 : 0, k1 = half ? a.gw : a.gw / 2;
+    for (int kw = k0; kw < k1; ++kw) dw[(long long)kw * tn] = sDtw[kw * kTile + r];
   }
-  if (warp == 8) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, key side: dk, dv   (same thread layout: two threads per query row of the current query tile)
+// backward, key side: dk, dv   (CTA = key tile, loop over query tiles; the two threads of a row split the CTA's keys)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDkvSmem = 10 * kTileBytes + 1024;   // K, V, Q x2, dO x2, P (2 chunks), dS (2 chunks)
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kCompute, 1)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -528,10 +508,12 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __shared__ __align__(8) uint64_t k_bar, qd_bar[2], s_bar, o_bar;
   __shared__ uint32_t tmem_base_smem;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kh0 = (kt / a.tiles_w) * kPH, kw0 = (kt % a.tiles_w) * kPW;
   const int nqt = a.tiles_h * a.tiles_w;
+  constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
+  constexpr uint32_t idesc_t = make_idesc_bf16(kTile, 64, 1, 1);
 
   if (tid == 0) {
     prefetch_tmap(&tmQKV);
@@ -543,123 +525,122 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(&o_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<512>(&tmem_base_smem);
+  if (warp == 0) tmem_alloc<512>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
 
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_expect_tx(&k_bar, 2 * kTileBytes);
-      tma_load_4d(sK, &tmQKV, &k_bar, a.dim + h * 64, kw0, kh0, b);
-      tma_load_4d(sV, &tmQKV, &k_bar, 2 * a.dim + h * 64, kw0, kh0, b);
-      mbar_expect_tx(&qd_bar[0], 2 * kTileBytes);
-      tma_load_4d(sQ, &tmQKV, &qd_bar[0], h * 64, 0, 0, b);
-      tma_load_4d(sDO, &tmDO, &qd_bar[0], h * 64, 0, 0, b);
-    }
-    constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
-    constexpr uint32_t idesc_t = make_idesc_bf16(kTile, 64, 1, 1);
-    for (int qt = 0; qt < nqt; ++qt) {
-      const int buf = qt & 1;
-      if (lane == 0) {
-        if (qt == 0) mbar_wait(&k_bar, 0);
-        mbar_wait(&qd_bar[buf], (qt >> 1) & 1);
-        tc_fence_after();
-        const uint64_t qd = desc_kmajor(sQ + buf * kTileBytes), dod = desc_kmajor(sDO + buf * kTileBytes);
-        const uint64_t kd = desc_kmajor(sK), vd = desc_kmajor(sV);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);       // S = Q K^T
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_dp, dod + 2 * k, vd + 2 * k, idesc_s, k != 0);     // dP = dO V^T
-        umma_commit(&s_bar);
-        if (qt + 1 < nqt) {
-          if (qt > 0) mbar_wait(&o_bar, (qt - 1) & 1);   // the transposed products of tile qt-1 have finished with the other buffers
-          const int nq = qt + 1, qh0 = (nq / a.tiles_w) * kPH, qw0 = (nq % a.tiles_w) * kPW;
-          mbar_expect_tx(&qd_bar[buf ^ 1], 2 * kTileBytes);
-          tma_load_4d(sQ + (buf ^ 1) * kTileBytes, &tmQKV, &qd_bar[buf ^ 1], h * 64, qw0, qh0, b);
-          tma_load_4d(sDO + (buf ^ 1) * kTileBytes, &tmDO, &qd_bar[buf ^ 1], h * 64, qw0, qh0, b);
-        }
-      }
-      __syncwarp();
-      __syncthreads();     // P and dS of this tile are in shared memory
-      if (lane == 0) {
-        tc_fence_after();
-        // A = P^T / dS^T: the [query row][key] tiles read MN-major (K = query rows, M = keys: two 64-key groups one chunk apart)
-        const uint64_t pd = desc_mnmajor(sP, kTileBytes), dsd = desc_mnmajor(sDS, kTileBytes);
-        const uint64_t dod = desc_mnmajor(sDO + buf * kTileBytes, 8192), qd = desc_mnmajor(sQ + buf * kTileBytes, 8192);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dv, pd + 128 * k, dod + 128 * k, idesc_t, (qt | k) != 0);   // dV += P^T dO
-#pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dk, dsd + 128 * k, qd + 128 * k, idesc_t, (qt | k) != 0);   // dK += dS^T Q
-        umma_commit(&o_bar);
-      }
-      __syncwarp();
-    }
-  } else {
-    const int r = tid & 127, half = tid >> 7;
-    const int tn = a.gh * a.gw;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const int khh = kh0 + 4 * half;            // this thread's 4 x 16 keys of the CTA's key tile
-    for (int qt = 0; qt < nqt; ++qt) {
-      const int qh = (qt / a.tiles_w) * kPH + r / kPW, qw = (qt % a.tiles_w) * kPW + r % kPW;
-      const bool valid_q = qh < a.gh && qw < a.gw;
-      const int qtok = valid_q ? qh * a.gw + qw : 0;
-      const long long tok = (long long)b * tn + qtok;
-      const float* trow = (a.relpos && valid_q) ? a.relpos + (tok * a.heads + h) * a.rp_stride : nullptr;
-      const long long stat = ((long long)b * a.heads + h) * tn + qtok;
-      const float lse2 = __ldg(a.lse + stat) * kLog2e;
-      const float delta = __ldg(a.delta + stat);
-      float th[4], tw[kPW];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) th[i] = (trow && khh + i < a.gh) ? __ldg(trow + a.gh - 1 + qh - khh - i) * kLog2e - lse2 : -lse2;
-#pragma unroll
-      for (int i = 0; i < kPW; ++i) tw[i] = (trow && kw0 + i < a.gw) ? __ldg(trow + 2 * a.gh - 1 + a.gw - 1 + qw - kw0 - i) * kLog2e : 0.f;
-      const bool interior = valid_q && (khh + 4 <= a.gh) && (kw0 + kPW <= a.gw);
-      mbar_wait(&s_bar, qt & 1);
-      __syncwarp();
-      tc_fence_after();
-#pragma unroll
-      for (int cl = 0; cl < 2; ++cl) {
-        const int c = 2 * half + cl;
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
-        tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
-        tmem_ld_wait();
-        float p[32], ds[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * cl + (i >> 4), pw = i & 15;
-          float pv = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
-          if (!interior) pv = (valid_q && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
-          p[i] = pv;
-          ds[i] = pv * (__uint_as_float(rp[i]) - delta);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v, w;
-          v.x = pack2(p[8 * g], p[8 * g + 1]);
-          v.y = pack2(p[8 * g + 2], p[8 * g + 3]);
-          v.z = pack2(p[8 * g + 4], p[8 * g + 5]);
-          v.w = pack2(p[8 * g + 6], p[8 * g + 7]);
-          w.x = pack2(ds[8 * g], ds[8 * g + 1]);
-          w.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
-          w.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
-          w.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-          const uint32_t off = half * kTileBytes + swz128(r, cl * 4 + g);
-          *reinterpret_cast<uint4*>(sP + off) = v;
-          *reinterpret_cast<uint4*>(sDS + off) = w;
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();     // -> issuer: dV += P^T dO, dK += dS^T Q
-      mbar_wait(&o_bar, qt & 1);
-      __syncwarp();
-    }
+  auto load_q = [&](int qt) {
+    const int buf = qt & 1, qh0 = (qt / a.tiles_w) * kPH, qw0 = (qt % a.tiles_w) * kPW;
+    mbar_expect_tx(&qd_bar[buf], 2 * kTileBytes);
+    tma_load_4d(sQ + buf * kTileBytes, &tmQKV, &qd_bar[buf], h * 64, qw0, qh0, b);
+    tma_load_4d(sDO + buf * kTileBytes, &tmDO, &qd_bar[buf], h * 64, qw0, qh0, b);
+  };
+  auto issue_s = [&](int qt) {       // S = Q K^T and dP = dO V^T of query tile qt
+    const int buf = qt & 1;
+    mbar_wait(&qd_bar[buf], (qt >> 1) & 1);
     tc_fence_after();
-    // TMEM lane = key row r of the CTA's key tile; warpgroup 0 writes dV, warpgroup 1 dK
+    const uint64_t qd = desc_kmajor(sQ + buf * kTileBytes), dod = desc_kmajor(sDO + buf * kTileBytes);
+    const uint64_t kd = desc_kmajor(sK), vd = desc_kmajor(sV);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_dp, dod + 2 * k, vd + 2 * k, idesc_s, k != 0);
+    umma_commit(&s_bar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&k_bar, 2 * kTileBytes);
+    tma_load_4d(sK, &tmQKV, &k_bar, a.dim + h * 64, kw0, kh0, b);
+    tma_load_4d(sV, &tmQKV, &k_bar, 2 * a.dim + h * 64, kw0, kh0, b);
+    load_q(0);
+    if (nqt > 1) load_q(1);
+    mbar_wait(&k_bar, 0);
+    issue_s(0);
+  }
+  __syncwarp();
+
+  const int r = tid & 127, half = tid >> 7;
+  const int tn = a.gh * a.gw;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const int khh = kh0 + 4 * half;            // this thread's 4 x 16 keys of the CTA's key tile
+  for (int qt = 0; qt < nqt; ++qt) {
+    const int buf = qt & 1;
+    const int qh = (qt / a.tiles_w) * kPH + r / kPW, qw = (qt % a.tiles_w) * kPW + r % kPW;
+    const bool valid_q = qh < a.gh && qw < a.gw;
+    const int qtok = valid_q ? qh * a.gw + qw : 0;
+    const long long bh = (long long)b * a.heads + h;
+    const float* rh = (a.rel_h && valid_q) ? a.rel_h + bh * a.gh * tn + qtok : nullptr;
+    const float* rw = (a.rel_h && valid_q) ? a.rel_w + bh * a.gw * tn + qtok : nullptr;
+    const long long stat = bh * tn + qtok;
+    const float lse2 = __ldg(a.lse + stat) * kLog2e;
+    const float delta = __ldg(a.delta + stat);
+    float th[4], tw[kPW];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) th[i] = (rh && khh + i < a.gh) ? __ldg(rh + (long long)(khh + i) * tn) * kLog2e - lse2 : -lse2;
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) * kLog2e : 0.f;
+    const bool interior = valid_q && (khh + 4 <= a.gh) && (kw0 + kPW <= a.gw);
+    mbar_wait(&s_bar, qt & 1);
+    __syncwarp();
+    tc_fence_after();
+#pragma unroll
+    for (int cl = 0; cl < 2; ++cl) {
+      const int c = 2 * half + cl;
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
+      tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
+      tmem_ld_wait();
+      float p[32], ds[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ph = 2 * cl + (i >> 4), pw = i & 15;
+        float pv = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
+        if (!interior) pv = (valid_q && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
+        p[i] = pv;
+        ds[i] = pv * (__uint_as_float(rp[i]) - delta);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v, w;
+        v.x = pack2(p[8 * g], p[8 * g + 1]);
+        v.y = pack2(p[8 * g + 2], p[8 * g + 3]);
+        v.z = pack2(p[8 * g + 4], p[8 * g + 5]);
+        v.w = pack2(p[8 * g + 6], p[8 * g + 7]);
+        w.x = pack2(ds[8 * g], ds[8 * g + 1]);
+        w.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
+        w.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
+        w.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
+        const uint32_t off = half * kTileBytes + swz128(r, cl * 4 + g);
+        *reinterpret_cast<uint4*>(sP + off) = v;
+        *reinterpret_cast<uint4*>(sDS + off) = w;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();     // P and dS of this tile are in shared memory; every thread has finished with S and dP
+    if (tid == 0) {
+      tc_fence_after();
+      // A = P^T / dS^T: the [query row][key] tiles read MN-major (K = query rows, M = keys: two 64-key groups one chunk apart)
+      const uint64_t pd = desc_mnmajor(sP, kTileBytes), dsd = desc_mnmajor(sDS, kTileBytes);
+      const uint64_t dod = desc_mnmajor(sDO + buf * kTileBytes, 8192), qd = desc_mnmajor(sQ + buf * kTileBytes, 8192);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) umma_bf16(tmem_dv, pd + 128 * k, dod + 128 * k, idesc_t, (qt | k) != 0);   // dV += P^T dO
+#pragma unroll
+      for (int k = 0; k < 8; ++k) umma_bf16(tmem_dk, dsd + 128 * k, qd + 128 * k, idesc_t, (qt | k) != 0);   // dK += dS^T Q
+      umma_commit(&o_bar);
+      if (qt + 1 < nqt) issue_s(qt + 1);
+    }
+    __syncwarp();
+    mbar_wait(&o_bar, qt & 1);
+    __syncwarp();
+    if (tid == 0 && qt + 2 < nqt) load_q(qt + 2);
+    __syncwarp();
+  }
+  tc_fence_after();
+  // TMEM lane = key row r of the CTA's key tile; threads 0-127 write dV, threads 128-255 dK
+  {
     const int kh = kh0 + r / kPW, kw = kw0 + r % kPW;
     const bool valid_k = kh < a.gh && kw < a.gw;
     const float sc = half ? a.scale : 1.f;
@@ -685,7 +666,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -705,9 +686,8 @@ TcArgs make_tc_args(const aldi_attn_params* p) {
   TcArgs a;
   a.gh = p->gh; a.gw = p->gw; a.heads = p->heads; a.dim = p->heads * 64;
   a.tiles_h = aldi_div_up(p->gh, kPH); a.tiles_w = aldi_div_up(p->gw, kPW);
-  a.rp_stride = p->rp_stride;
   a.scale = p->scale; a.scale_log2 = p->scale * kLog2e;
-  a.relpos = p->relpos; a.drelpos = p->drelpos; a.lse = p->lse; a.delta = p->delta;
+  a.rel_h = p->rel_h; a.rel_w = p->rel_w; a.drel_h = p->drel_h; a.drel_w = p->drel_w; a.lse = p->lse; a.delta = p->delta;
   a.out = reinterpret_cast<__nv_bfloat16*>(p->out);
   a.dout = reinterpret_cast<const __nv_bfloat16*>(p->dout);
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(p->dqkv);
@@ -750,7 +730,7 @@ int aldi_attention_forward_tc(const aldi_attn_params* p, cudaStream_t stream) {
     attr = true;
   }
   const dim3 grid(a.tiles_h * a.tiles_w, p->heads, p->batch);
-  attn_fwd_tc<<<grid, kThreads, kFwdSmem, stream>>>(tmQKV, a);
+  attn_fwd_tc<<<grid, kCompute, kFwdSmem, stream>>>(tmQKV, a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_attention_forward");
   return ALDI_OK;
@@ -782,10 +762,10 @@ int aldi_attention_backward_tc(const aldi_attn_params* p, cudaStream_t stream) {
     dkv_attr = true;
   }
   const dim3 grid(a.tiles_h * a.tiles_w, p->heads, p->batch);
-  attn_bwd_dq_tc<<<grid, kBwdThreads, dq_smem, stream>>>(tmQKV, tmDO, a);
+  attn_bwd_dq_tc<<<grid, kCompute, dq_smem, stream>>>(tmQKV, tmDO, a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_attention_backward(dq)");
-  attn_bwd_dkv_tc<<<grid, kBwdThreads, kDkvSmem, stream>>>(tmQKV, tmDO, a);
+  attn_bwd_dkv_tc<<<grid, kCompute, kDkvSmem, stream>>>(tmQKV, tmDO, a);
   ALDI_COUNT_LAUNCH();
   ALDI_CUDA_LAUNCH_CHECK("aldi_attention_backward(dkv)");
   return ALDI_OK;

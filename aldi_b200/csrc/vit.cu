@@ -183,6 +183,48 @@ maxpool2x2_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restri
   }
 }
 
+// GEMM layout rel[(b, q, h), c] <-> key-major rel_h[(b, h, kh), q], rel_w[(b, h, kw), q]; one block = 16 queries of one
+// (b, h): rows cross shared memory so that both sides move contiguous runs (columns on the GEMM side, queries on the other)
+constexpr int kRtQ = 16;
+__global__ void __launch_bounds__(256)
+relpos_transpose_kernel(float* __restrict__ rel, int rp, float* __restrict__ rel_h, float* __restrict__ rel_w, int gh, int gw,
+                        int heads, int backward) {
+  extern __shared__ float tile[];                 // [kRtQ][rp + 1]
+  const int tn = gh * gw, q0 = blockIdx.x * kRtQ, h = blockIdx.y, b = blockIdx.z;
+  const int nq = min(kRtQ, tn - q0), ld = rp + 1;
+  const long long bh = (long long)b * heads + h;
+  const int nh = 2 * gh - 1;
+  if (!backward) {
+    for (int i = threadIdx.x; i < nq * rp; i += blockDim.x) {
+      const int qi = i / rp, c = i - qi * rp;
+      tile[qi * ld + c] = rel[(((long long)b * tn + q0 + qi) * heads + h) * rp + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (gh + gw) * kRtQ; i += blockDim.x) {
+      const int k = i / kRtQ, qi = i % kRtQ;
+      if (qi >= nq) continue;
+      const int q = q0 + qi, qh = q / gw, qw = q - qh * gw;
+      if (k < gh) rel_h[(bh * gh + k) * tn + q] = tile[qi * ld + gh - 1 + qh - k];
+      else rel_w[(bh * gw + (k - gh)) * tn + q] = tile[qi * ld + nh + gw - 1 + qw - (k - gh)];
+    }
+  } else {
+    for (int i = threadIdx.x; i < nq * rp; i += blockDim.x) tile[(i / rp) * ld + (i % rp)] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (gh + gw) * kRtQ; i += blockDim.x) {
+      const int k = i / kRtQ, qi = i % kRtQ;
+      if (qi >= nq) continue;
+      const int q = q0 + qi, qh = q / gw, qw = q - qh * gw;
+      if (k < gh) tile[qi * ld + gh - 1 + qh - k] = rel_h[(bh * gh + k) * tn + q];
+      else tile[qi * ld + nh + gw - 1 + qw - (k - gh)] = rel_w[(bh * gw + (k - gh)) * tn + q];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq * rp; i += blockDim.x) {
+      const int qi = i / rp, c = i - qi * rp;
+      rel[(((long long)b * tn + q0 + qi) * heads + h) * rp + c] = tile[qi * ld + c];
+    }
+  }
+}
+
 // da == NULL: out = max(x, 0); else out = da * (x > 0)   (the ReLU after the LayerNorm of ViTDet's 4-conv box head)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -202,9 +244,9 @@ constexpr int kKeyTile = 32;
 struct AttnArgs {
   const void* qkv; const void* out; const void* dout;
   void* out_w; void* dqkv;
-  const float* relpos; float* drelpos; float* lse; float* delta;
+  const float* rel_h; const float* rel_w; float* drel_h; float* drel_w; float* lse; float* delta;
   long long row_stride, batch_stride, out_stride, out_batch_stride;
-  int gh, gw, heads, rp_stride, dim;
+  int gh, gw, heads, dim;
   float scale;
 };
 
@@ -239,8 +281,10 @@ attn_fwd_simt(const AttnArgs a) {
   load_row64<T>(base + (long long)qc * a.row_stride + h * kHd, qv);
 #pragma unroll
   for (int d = 0; d < kHd; ++d) { qv[d] *= a.scale; o[d] = 0.f; }
-  const int qh = qc / a.gw, qw = qc % a.gw;
-  const float* trow = a.relpos ? a.relpos + (((long long)b * tn + qc) * a.heads + h) * a.rp_stride : nullptr;
+  // key-major relative-position products: rel_h[(b, h, kh), q], rel_w[(b, h, kw), q]
+  const long long bh = (long long)b * a.heads + h;
+  const float* rh = a.rel_h ? a.rel_h + bh * a.gh * tn + qc : nullptr;
+  const float* rw = a.rel_h ? a.rel_w + bh * a.gw * tn + qc : nullptr;
   float m = -INFINITY, l = 0.f;
   for (int k0 = 0; k0 < tn; k0 += kKeyTile) {
     __syncthreads();
@@ -256,9 +300,9 @@ attn_fwd_simt(const AttnArgs a) {
       for (int d = 0; d < kHd; ++d) acc += qv[d] * sK[j][d];
       const int kk = k0 + j;
       if (kk < tn) {
-        if (trow) {
+        if (rh) {
           const int kh = kk / a.gw, kw = kk - kh * a.gw;
-          acc += trow[a.gh - 1 + qh - kh] + trow[2 * a.gh - 1 + a.gw - 1 + qw - kw];
+          acc += rh[(long long)kh * tn] + rw[(long long)kw * tn];
         }
       } else {
         acc = -INFINITY;
@@ -316,12 +360,15 @@ attn_bwd_dq_simt(const AttnArgs a) {
   const long long stat = ((long long)b * a.heads + h) * tn + qc;
   const float lse = a.lse[stat];
   if (valid) a.delta[stat] = delta;
-  const int qh = qc / a.gw, qw = qc % a.gw;
-  const long long roff = (((long long)b * tn + qc) * a.heads + h) * a.rp_stride;
-  const float* trow = a.relpos ? a.relpos + roff : nullptr;
-  float* drow = (a.relpos && valid) ? a.drelpos + roff : nullptr;
-  if (drow)
-    for (int c = 0; c < a.rp_stride; ++c) drow[c] = 0.f;
+  const long long bh = (long long)b * a.heads + h;
+  const float* rh = a.rel_h ? a.rel_h + bh * a.gh * tn + qc : nullptr;
+  const float* rw = a.rel_h ? a.rel_w + bh * a.gw * tn + qc : nullptr;
+  float* dh = (a.rel_h && valid) ? a.drel_h + bh * a.gh * tn + qc : nullptr;
+  float* dw = (a.rel_h && valid) ? a.drel_w + bh * a.gw * tn + qc : nullptr;
+  if (dh) {       // this thread owns column q of both gradient arrays
+    for (int k = 0; k < a.gh; ++k) dh[(long long)k * tn] = 0.f;
+    for (int k = 0; k < a.gw; ++k) dw[(long long)k * tn] = 0.f;
+  }
   for (int k0 = 0; k0 < tn; k0 += kKeyTile) {
     __syncthreads();
     stage_tile<T>(base, a.row_stride, k0, tn, a.dim + h * kHd, sK, tid, 128, kKeyTile);
@@ -334,18 +381,18 @@ attn_bwd_dq_simt(const AttnArgs a) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int d = 0; d < kHd; ++d) { s += qv[d] * sK[j][d]; dp += dov[d] * sV[j][d]; }
-      int ch = 0, cw = 0;
-      if (trow) {
+      long long ch = 0, cw = 0;
+      if (rh) {
         const int kh = kk / a.gw, kw = kk - kh * a.gw;
-        ch = a.gh - 1 + qh - kh;
-        cw = 2 * a.gh - 1 + a.gw - 1 + qw - kw;
-        s += trow[ch] + trow[cw];
+        ch = (long long)kh * tn;
+        cw = (long long)kw * tn;
+        s += rh[ch] + rw[cw];
       }
       const float p = __expf(s - lse);
       const float ds = p * (dp - delta);
 #pragma unroll
       for (int d = 0; d < kHd; ++d) dq[d] += ds * sK[j][d];
-      if (drow) { drow[ch] += ds; drow[cw] += ds; }     // this thread owns the row: plain read-modify-write
+      if (dh) { dh[ch] += ds; dw[cw] += ds; }     // this thread owns the column: plain read-modify-write
     }
   }
   if (valid) {
@@ -398,10 +445,9 @@ attn_bwd_dkv_simt(const AttnArgs a) {
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       dp += __shfl_xor_sync(0xffffffffu, dp, 1);
       s *= a.scale;
-      if (a.relpos) {
-        const int qh = qq / a.gw, qw = qq - qh * a.gw;
-        const float* trow = a.relpos + (((long long)b * tn + qq) * a.heads + h) * a.rp_stride;
-        s += trow[a.gh - 1 + qh - kh] + trow[2 * a.gh - 1 + a.gw - 1 + qw - kw];
+      if (a.rel_h) {
+        const long long bh = (long long)b * a.heads + h;
+        s += a.rel_h[(bh * a.gh + kh) * tn + qq] + a.rel_w[(bh * a.gw + kw) * tn + qq];
       }
       const float p = __expf(s - sLse[i]);
       const float ds = p * (dp - sDelta[i]);
@@ -422,10 +468,10 @@ attn_bwd_dkv_simt(const AttnArgs a) {
 AttnArgs make_args(const aldi_attn_params* p) {
   AttnArgs a;
   a.qkv = p->qkv; a.out = p->out; a.out_w = p->out; a.dout = p->dout; a.dqkv = p->dqkv;
-  a.relpos = p->relpos; a.drelpos = p->drelpos; a.lse = p->lse; a.delta = p->delta;
+  a.rel_h = p->rel_h; a.rel_w = p->rel_w; a.drel_h = p->drel_h; a.drel_w = p->drel_w; a.lse = p->lse; a.delta = p->delta;
   a.row_stride = p->row_stride; a.batch_stride = p->batch_stride;
   a.out_stride = p->out_stride; a.out_batch_stride = p->out_batch_stride;
-  a.gh = p->gh; a.gw = p->gw; a.heads = p->heads; a.rp_stride = p->rp_stride; a.dim = p->heads * kHd;
+  a.gh = p->gh; a.gw = p->gw; a.heads = p->heads; a.dim = p->heads * kHd;
   a.scale = p->scale;
   return a;
 }
@@ -435,12 +481,10 @@ int check_attn(const aldi_attn_params* p, bool backward, const char* who) {
   ALDI_CHECK_ARG(p->batch > 0 && p->gh > 0 && p->gw > 0 && p->heads > 0, "%s: empty problem", who);
   ALDI_CHECK_ARG(p->row_stride >= 3LL * p->heads * 64 && p->out_stride >= (long long)p->heads * 64, "%s: row strides too small", who);
   ALDI_CHECK_ARG(p->dtype == ALDI_F32 || p->dtype == ALDI_BF16, "%s: dtype %d", who, p->dtype);
-  if (p->relpos)
-    ALDI_CHECK_ARG(p->rp_stride >= 2 * p->gh - 1 + 2 * p->gw - 1, "%s: rp_stride %d < %d table columns", who, p->rp_stride,
-                   2 * p->gh - 1 + 2 * p->gw - 1);
+  ALDI_CHECK_ARG((p->rel_h == nullptr) == (p->rel_w == nullptr), "%s: rel_h and rel_w come together", who);
   if (backward) {
     ALDI_CHECK_ARG(p->dout && p->dqkv && p->delta, "%s: null gradient pointer", who);
-    ALDI_CHECK_ARG(!p->relpos || p->drelpos, "%s: relpos without drelpos", who);
+    ALDI_CHECK_ARG(!p->rel_h || (p->drel_h && p->drel_w), "%s: rel_h / rel_w without drel_h / drel_w", who);
   }
   return ALDI_OK;
 }
@@ -546,6 +590,22 @@ extern "C" int aldi_relu(const void* x, const void* da, void* out, size_t n, int
                (relu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)da,
                                                                     (__nv_bfloat16*)out, n)),
                "aldi_relu");
+  return ALDI_OK;
+}
+
+extern "C" int aldi_relpos_transpose(float* rel, int rp_stride, float* rel_h, float* rel_w, int batch, int gh, int gw, int heads,
+                                     int backward, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALDI_CHECK_ARG(rel && rel_h && rel_w && batch > 0 && gh > 0 && gw > 0 && heads > 0, "aldi_relpos_transpose: bad args");
+  ALDI_CHECK_ARG(rp_stride >= 2 * gh - 1 + 2 * gw - 1, "aldi_relpos_transpose: rp_stride %d < %d table columns", rp_stride,
+                 2 * gh - 1 + 2 * gw - 1);
+  ALDI_CHECK_ARG(batch <= 65535 && heads <= 65535, "aldi_relpos_transpose: batch / heads exceed the grid limits");
+  const size_t smem = (size_t)kRtQ * (rp_stride + 1) * sizeof(float);
+  ALDI_CHECK_ARG(smem <= 48 * 1024, "aldi_relpos_transpose: rp_stride %d too wide", rp_stride);
+  const dim3 grid((gh * gw + kRtQ - 1) / kRtQ, heads, batch);
+  relpos_transpose_kernel<<<grid, 256, smem, stream>>>(rel, rp_stride, rel_h, rel_w, gh, gw, heads, backward);
+  ALDI_COUNT_LAUNCH();
+  ALDI_CUDA_LAUNCH_CHECK("aldi_relpos_transpose");
   return ALDI_OK;
 }
 

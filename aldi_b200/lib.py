@@ -101,9 +101,9 @@ class AttnParams(ctypes.Structure):
     _fields_ = [
         ("qkv", c_void_p), ("batch", c_int), ("gh", c_int), ("gw", c_int), ("heads", c_int),
         ("row_stride", c_ll), ("batch_stride", c_ll),
-        ("relpos", c_void_p), ("rp_stride", c_int), ("scale", c_float), ("dtype", c_int),
+        ("rel_h", c_void_p), ("rel_w", c_void_p), ("scale", c_float), ("dtype", c_int),
         ("out", c_void_p), ("out_stride", c_ll), ("out_batch_stride", c_ll), ("lse", c_void_p),
-        ("dout", c_void_p), ("dqkv", c_void_p), ("drelpos", c_void_p), ("delta", c_void_p), ("impl", c_int),
+        ("dout", c_void_p), ("dqkv", c_void_p), ("drel_h", c_void_p), ("drel_w", c_void_p), ("delta", c_void_p), ("impl", c_int),
     ]
 
 
@@ -205,6 +205,7 @@ SIGNATURES = {
     "aldi_maxpool2x2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_maxpool2x2_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_relu": (c_int, [P, P, P, c_size_t, c_int, P]),
+    "aldi_relpos_transpose": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "aldi_attention_forward": (c_int, [ctypes.POINTER(AttnParams), P]),
     "aldi_attention_backward": (c_int, [ctypes.POINTER(AttnParams), P]),
 }

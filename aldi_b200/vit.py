@@ -13,8 +13,9 @@ tcgen05 implicit-GEMM kernels (`aldi_conv_tc` / `aldi_wgrad_tc`; fp32 CUDA-core 
   * patch embedding = `aldi_patchify_image` (16 x 16 x 3 rows straight from the uint8 canvas) + one GEMM;
   * attention = `aldi_attention_forward / _backward` (csrc/attn_tc.cu: QK^T, PV and the four backward products as UMMA
     tiles over 16 x 8-token TMA patches of the qkv tensor as the qkv Linear wrote it; csrc/vit.cu in parity mode); the
-    decomposed relative-position term enters as ONE extra GEMM per block, q x [Rh; Rw]^T, whose output the attention kernel
-    indexes per (query, key row / key column) -- so the tables' gradients and the term's share of dq are plain GEMMs too;
+    decomposed relative-position term enters as ONE extra GEMM per block, q x [Rh; Rw]^T, re-laid out key-major
+    (`aldi_relpos_transpose`) so the attention kernels read it per (key row / key column, query) with the query index
+    fastest -- the tables' gradients and the term's share of dq are plain GEMMs too;
   * windowed blocks run on the partitioned tensor (`aldi_window_partition`, padding tokens written as zeros AFTER norm1 and
     never masked, as detectron2 does: they are keys of their window and carry qkv = bias);
   * ConvTranspose2d(k=2, s=2) = GEMM to (dy, dx, cout) columns + depth-to-space (`aldi_space_to_depth`, inverse);
@@ -416,12 +417,12 @@ class ViTDetBackbone:
                  self.view(key + ".weight", self.grad), self.view(key + ".bias", self.grad))
         return dx
 
-    def _attn_params(self, qkv, rel, out, lse):
+    def _attn_params(self, qkv, rel_hw, out, lse):
         b, gh, gw, _ = qkv.shape
         p = _l.AttnParams()
         p.qkv, p.batch, p.gh, p.gw, p.heads = qkv.data_ptr(), b, gh, gw, self.heads
         p.row_stride, p.batch_stride = qkv.stride(2), qkv.stride(0)
-        p.relpos, p.rp_stride = rel.data_ptr(), rel.shape[3]
+        p.rel_h, p.rel_w = rel_hw[0].data_ptr(), rel_hw[1].data_ptr()
         p.scale, p.dtype = self.scale, self.dtc
         p.out, p.out_stride, p.out_batch_stride, p.lse = out.data_ptr(), out.stride(2), out.stride(0), lse.data_ptr()
         p.impl = 0
@@ -431,42 +432,52 @@ class ViTDetBackbone:
         """qkv Linear -> relative-position products -> attention -> proj Linear on a (B, gh, gw, C) token tensor."""
         p = "net.blocks.%d." % i
         b, gh, gw, _ = xin.shape
+        t = gh * gw
         qkv = self.gemm[p + "qkv"].forward(xin)
         rg = self._rel_gemm(i, gh, gw)["gemm"]
-        q4 = qkv.as_strided((b, gh * gw, self.heads, 64), (qkv.stride(0), qkv.stride(2), 64, 1), qkv.storage_offset())
+        q4 = qkv.as_strided((b, t, self.heads, 64), (qkv.stride(0), qkv.stride(2), 64, 1), qkv.storage_offset())
         rel = rg.forward(q4, out_dtype=torch.float32)          # (b, tokens, heads, pad64(2gh-1 + 2gw-1)) fp32
+        # key-major copies the attention kernels read with the query index fastest (coalesced across a warp's 32 rows)
+        rel_h = torch.empty(b, self.heads, gh, t, device=xin.device)
+        rel_w = torch.empty(b, self.heads, gw, t, device=xin.device)
+        ops.call("aldi_relpos_transpose", rel, rel.shape[3], rel_h, rel_w, b, gh, gw, self.heads, 0)
+        del rel
         out = torch.empty(b, gh, gw, self.C, device=xin.device, dtype=xin.dtype)
-        lse = torch.empty(b, self.heads, gh * gw, device=xin.device)
-        ap = self._attn_params(qkv, rel, out, lse)
+        lse = torch.empty(b, self.heads, t, device=xin.device)
+        ap = self._attn_params(qkv, (rel_h, rel_w), out, lse)
         L = _l.load()
         _l.check(ops._launch("aldi_attention_forward", lambda: L.aldi_attention_forward(_l.ctypes.byref(ap), ops._stream()),
-                             4.0 * b * self.heads * (gh * gw) ** 2 * 64), "aldi_attention_forward")
+                             4.0 * b * self.heads * t ** 2 * 64), "aldi_attention_forward")
         y = self.gemm[p + "proj"].forward(out)
-        return y, ((xin, qkv, rel, out, lse) if save else None)
+        return y, ((xin, qkv, rel_h, rel_w, out, lse) if save else None)
 
     def _attention_bwd(self, i, saved, dy):
         p = "net.blocks.%d." % i
-        xin, qkv, rel, out, lse = saved
+        xin, qkv, rel_h, rel_w, out, lse = saved
         b, gh, gw, _ = xin.shape
+        t = gh * gw
         dout = self.gemm[p + "proj"].backward(out, dy)
         dqkv = torch.empty_like(qkv)
-        drel = torch.empty_like(rel)
+        drel_h, drel_w = torch.empty_like(rel_h), torch.empty_like(rel_w)
         delta = torch.empty_like(lse)
-        ap = self._attn_params(qkv, rel, out, lse)
-        ap.dout, ap.dqkv, ap.drelpos, ap.delta = dout.data_ptr(), dqkv.data_ptr(), drel.data_ptr(), delta.data_ptr()
+        ap = self._attn_params(qkv, (rel_h, rel_w), out, lse)
+        ap.dout, ap.dqkv, ap.drel_h, ap.drel_w, ap.delta = (dout.data_ptr(), dqkv.data_ptr(), drel_h.data_ptr(), drel_w.data_ptr(),
+                                                           delta.data_ptr())
         L = _l.load()
         _l.check(ops._launch("aldi_attention_backward", lambda: L.aldi_attention_backward(_l.ctypes.byref(ap), ops._stream()),
-                             10.0 * b * self.heads * (gh * gw) ** 2 * 64), "aldi_attention_backward")
+                             10.0 * b * self.heads * t ** 2 * 64), "aldi_attention_backward")
         # the relative-position products are a GEMM of the q view: table gradients = wgrad, their share of dq = dgrad
         r = self._rel_gemm(i, gh, gw)
         rg = r["gemm"]
+        drel = torch.empty(b, t, self.heads, rg.cout_p, device=xin.device)
+        ops.call("aldi_relpos_transpose", drel, rg.cout_p, drel_h, drel_w, b, gh, gw, self.heads, 1)
         if self.dtype == torch.bfloat16:
             drel_a = torch.empty(drel.shape, device=drel.device, dtype=self.dtype)
             ops.call("aldi_cast_f32", drel_a, self.dtc, drel, drel.numel())
         else:
             drel_a = drel
-        q4 = qkv.as_strided((b, gh * gw, self.heads, 64), (qkv.stride(0), qkv.stride(2), 64, 1), qkv.storage_offset())
-        dq4 = dqkv.as_strided((b, gh * gw, self.heads, 64), (dqkv.stride(0), dqkv.stride(2), 64, 1), dqkv.storage_offset())
+        q4 = qkv.as_strided((b, t, self.heads, 64), (qkv.stride(0), qkv.stride(2), 64, 1), qkv.storage_offset())
+        dq4 = dqkv.as_strided((b, t, self.heads, 64), (dqkv.stride(0), dqkv.stride(2), 64, 1), dqkv.storage_offset())
         rg.backward(q4, drel_a, dx=dq4, accumulate=True)
         if r["eff"] is not None:
             # resampled tables: fold their gradient back onto the parameters (transpose of the linear interpolation)

@@ -443,23 +443,26 @@ int aldi_relu(const void* x, const void* da, void* out, size_t n, int dtype, voi
 
 /* Multi-head attention with MViTv2's decomposed relative position term (detectron2 vit.Attention + add_decomposed_rel_pos),
  * head dim 64, flash-style (the (tokens x tokens) matrix is never materialised):
- *   S[q, k] = scale * q.k + relpos[q, gh-1 + qh-kh] + relpos[q, 2gh-1 + gw-1 + qw-kw],   out = softmax_k(S) v
+ *   S[q, k] = scale * q.k + rel_h[kh, q] + rel_w[kw, q],   out = softmax_k(S) v        (k = (kh, kw) on the gh x gw token grid)
  * qkv: (batch, gh*gw tokens, ...) rows of `row_stride` elements = [q | k | v], each dim = heads*64 wide (the output of the
- * qkv Linear as it stands); relpos (nullable): fp32 (batch, tokens, heads, rp_stride), the product of the UNSCALED q with
- * the concatenated tables [Rh (2gh-1 rows); Rw (2gw-1 rows)] -- one plain GEMM of the q view (aldi_conv_tc / aldi_conv_f32),
- * so the tables' gradients and the term's part of dq are again plain GEMMs on `drelpos`.
+ * qkv Linear as it stands).  rel_h / rel_w (nullable, both or neither): fp32 (batch, heads, gh, tokens) / (batch, heads, gw,
+ * tokens), KEY-major with the query index fastest -- a warp's 32 query rows read 128 contiguous bytes per key row / column:
+ *   rel_h[kh, q] = q_vec . Rh[gh-1 + qh-kh],   rel_w[kw, q] = q_vec . Rw[gw-1 + qw-kw]        (q_vec UNSCALED)
+ * They come from ONE plain GEMM of the q view with the concatenated tables [Rh (2gh-1 rows); Rw (2gw-1 rows)]
+ * (aldi_conv_tc / aldi_conv_f32: fp32 (batch, tokens, heads, rp_stride) rows) followed by aldi_relpos_transpose, so the
+ * tables' gradients and the term's part of dq are again plain GEMMs on the transposed-back gradient.
  * dtype BF16: tcgen05 kernels (QK^T, PV, and in the backward dO V^T, dS K, P^T dO, dS^T Q as 128 x N x 16 UMMA tiles with
  * TMEM accumulators, 16 x 8-token TMA patches as tiles); dtype F32 or impl = 1: CUDA-core fp32 kernels (parity mode / the
  * cross-check of the tensor-core path).
  * forward writes out (batch, tokens, heads*64) rows of out_stride and lse (batch, heads, tokens) fp32;
- * backward reads out / dout / lse and writes dqkv (same layout as qkv, all three thirds), drelpos (every column) and the
- * delta workspace (batch, heads, tokens).                                                                               */
+ * backward reads out / dout / lse and writes dqkv (same layout as qkv, all three thirds), drel_h / drel_w (every element)
+ * and the delta workspace (batch, heads, tokens).                                                                        */
 typedef struct {
   const void* qkv;
   int batch, gh, gw, heads;
   long long row_stride, batch_stride;     /* elements */
-  const float* relpos;
-  int rp_stride;
+  const float* rel_h;
+  const float* rel_w;
   float scale;
   int dtype;
   void* out;
@@ -467,10 +470,16 @@ typedef struct {
   float* lse;
   const void* dout;                       /* backward only from here */
   void* dqkv;
-  float* drelpos;
+  float* drel_h;
+  float* drel_w;
   float* delta;
   int impl;
 } aldi_attn_params;
+/* GEMM layout <-> key-major layout of the relative-position products.  backward = 0: rel (batch, tokens, heads, rp_stride)
+ * -> rel_h, rel_w; backward = 1: the gradients drel_h, drel_w -> drel in the GEMM layout, EVERY column written (zeros where
+ * a (query, table row) pair is not used and in the padding columns).                                                     */
+int aldi_relpos_transpose(float* rel, int rp_stride, float* rel_h, float* rel_w, int batch, int gh, int gw, int heads, int backward,
+                          void* stream);
 int aldi_attention_forward(const aldi_attn_params* p, void* stream);
 int aldi_attention_backward(const aldi_attn_params* p, void* stream);
 

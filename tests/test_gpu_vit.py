@@ -121,6 +121,8 @@ def _ref_attention(qkv, rel, gh, gw, heads, scale):
 
 
 def _run_attention(qkv, rel, gh, gw, heads, scale, dout, impl):
+    """rel / the returned drel are in the GEMM layout (b, tokens, heads, columns): the key-major arrays the kernels consume
+    are made by aldi_relpos_transpose and the gradients brought back by its inverse, as aldi_b200/vit.py does."""
     from aldi_b200 import lib as _l, ops
     L = _l.load()
     b, t, _ = qkv.shape
@@ -128,17 +130,22 @@ def _run_attention(qkv, rel, gh, gw, heads, scale, dout, impl):
     out = torch.zeros(b, t, heads * 64, device=dev, dtype=dt)
     lse = torch.zeros(b, heads, t, device=dev)
     dqkv = torch.full_like(qkv, 5.0)
-    drel = torch.full_like(rel, 5.0)
+    rel_h, rel_w = torch.full((b, heads, gh, t), 7.0, device=dev), torch.full((b, heads, gw, t), 7.0, device=dev)
+    ops.call("aldi_relpos_transpose", rel, rel.shape[3], rel_h, rel_w, b, gh, gw, heads, 0)
+    drel_h, drel_w = torch.full_like(rel_h, 5.0), torch.full_like(rel_w, 5.0)
     delta = torch.zeros_like(lse)
     p = _l.AttnParams()
     p.qkv, p.batch, p.gh, p.gw, p.heads = qkv.data_ptr(), b, gh, gw, heads
     p.row_stride, p.batch_stride = qkv.stride(1), qkv.stride(0)
-    p.relpos, p.rp_stride, p.scale = rel.data_ptr(), rel.shape[3], scale
+    p.rel_h, p.rel_w, p.scale = rel_h.data_ptr(), rel_w.data_ptr(), scale
     p.dtype = _l.BF16 if dt == torch.bfloat16 else _l.F32
     p.out, p.out_stride, p.out_batch_stride, p.lse = out.data_ptr(), out.stride(1), out.stride(0), lse.data_ptr()
-    p.dout, p.dqkv, p.drelpos, p.delta, p.impl = dout.data_ptr(), dqkv.data_ptr(), drel.data_ptr(), delta.data_ptr(), impl
+    p.dout, p.dqkv, p.drel_h, p.drel_w, p.delta, p.impl = (dout.data_ptr(), dqkv.data_ptr(), drel_h.data_ptr(), drel_w.data_ptr(),
+                                                         delta.data_ptr(), impl)
     _l.check(L.aldi_attention_forward(ctypes.byref(p), ops._stream()), "fwd")
     _l.check(L.aldi_attention_backward(ctypes.byref(p), ops._stream()), "bwd")
+    drel = torch.full_like(rel, 5.0)
+    ops.call("aldi_relpos_transpose", drel, rel.shape[3], drel_h, drel_w, b, gh, gw, heads, 1)
     torch.cuda.synchronize()
     return out, lse, dqkv, drel
 

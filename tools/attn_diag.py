@@ -51,13 +51,17 @@ def main():
         lse = torch.zeros(b, heads, t, device=dev)
         dqkv = torch.full_like(qkv_d, 5.0)
         drel = torch.full_like(rel_d, 5.0)
+        rel_h, rel_w = torch.zeros(b, heads, gh, t, device=dev), torch.zeros(b, heads, gw, t, device=dev)
+        ops.call("aldi_relpos_transpose", rel_d, nrp, rel_h, rel_w, b, gh, gw, heads, 0)
+        drel_h, drel_w = torch.full_like(rel_h, 5.0), torch.full_like(rel_w, 5.0)
         delta = torch.zeros_like(lse)
         p = _l.AttnParams()
         p.qkv, p.batch, p.gh, p.gw, p.heads = qkv_d.data_ptr(), b, gh, gw, heads
         p.row_stride, p.batch_stride = qkv_d.stride(1), qkv_d.stride(0)
-        p.relpos, p.rp_stride, p.scale, p.dtype = rel_d.data_ptr(), nrp, scale, _l.BF16
+        p.rel_h, p.rel_w, p.scale, p.dtype = rel_h.data_ptr(), rel_w.data_ptr(), scale, _l.BF16
         p.out, p.out_stride, p.out_batch_stride, p.lse = out.data_ptr(), out.stride(1), out.stride(0), lse.data_ptr()
-        p.dout, p.dqkv, p.drelpos, p.delta, p.impl = dout_d.data_ptr(), dqkv.data_ptr(), drel.data_ptr(), delta.data_ptr(), impl
+        p.dout, p.dqkv, p.drel_h, p.drel_w, p.delta, p.impl = (dout_d.data_ptr(), dqkv.data_ptr(), drel_h.data_ptr(),
+                                                             drel_w.data_ptr(), delta.data_ptr(), impl)
         print("case b=%d grid=%dx%d heads=%d impl=%d" % (b, gh, gw, heads, impl), flush=True)
         _l.check(L.aldi_attention_forward(ctypes.byref(p), ops._stream()), "fwd")
         torch.cuda.synchronize()
@@ -73,6 +77,7 @@ def main():
         out.copy_(out_r.detach().to(dev))
         lse.copy_(lse_r.detach().to(dev))
         _l.check(L.aldi_attention_backward(ctypes.byref(p), ops._stream()), "bwd")
+        ops.call("aldi_relpos_transpose", drel, nrp, drel_h, drel_w, b, gh, gw, heads, 1)
         torch.cuda.synchronize()
         dim = heads * 64
         g, gr = dqkv.cpu().float(), qd.grad
