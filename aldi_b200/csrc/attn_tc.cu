@@ -56,6 +56,8 @@ __device__ __forceinline__ float ex2(float x) {      // 2^x, one MUFU (x <= 0 he
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Scheduling fence for a register value: a prefetched global load must not be consumed (and so waited for) before this point
+__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
@@ -160,19 +162,29 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
 #pragma unroll
   for (int d = 0; d < 32; ++d) o[d] = 0.f;
   float m = -INFINITY, l = 0.f;
+  float th[4], tw[kPW];
+  // relative-position terms of this row for key tile kt (x log2 e): 4 key rows + 16 key columns, coalesced over the warp's rows.
+  // Loaded one tile AHEAD (right after the previous tile's exponentials) so the L2 latency hides behind the MMA waits.
+  auto load_bias = [&](int kt) {
+    const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = (kt % a.tiles_w) * kPW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) th[i] = (rh && kh0 + i < a.gh) ? __ldg(rh + (long long)(kh0 + i) * tn) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) : 0.f;
+  };
+  load_bias(0);
   for (int kt = 0; kt < nkt; ++kt) {
     const int buf = kt & 1;
     const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = (kt % a.tiles_w) * kPW;     // this thread's 4 x 16 keys
-    float th[4], tw[kPW];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) th[i] = (rh && kh0 + i < a.gh) ? __ldg(rh + (long long)(kh0 + i) * tn) * kLog2e : 0.f;
-#pragma unroll
-    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) * kLog2e : 0.f;
     const bool interior = (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
     mbar_wait(&s_bar, kt & 1);
     __syncwarp();
     tc_fence_after();
-    float mt = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pin(th[i]); th[i] *= kLog2e; }        // first use of the prefetched terms: after the wait
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) { pin(tw[i]); tw[i] *= kLog2e; }
+    float mt4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // independent chains: two warps per scheduler hide little
 #pragma unroll
     for (int cl = 0; cl < 2; ++cl) {
       uint32_t raw[32];
@@ -182,16 +194,17 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
       for (int i = 0; i < 32; ++i) {
         const int ph = 2 * cl + (i >> 4), pw = i & 15;
         const float s2 = fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw];
-        mt = fmaxf(mt, (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? s2 : -INFINITY);
+        mt4[i & 3] = fmaxf(mt4[i & 3], (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? s2 : -INFINITY);
       }
     }
+    const float mt = fmaxf(fmaxf(mt4[0], mt4[1]), fmaxf(mt4[2], mt4[3]));
     sX[half * kTile + r] = mt;
     __syncthreads();
     const float mn = fmaxf(m, fmaxf(mt, sX[(half ^ 1) * kTile + r]));     // >= one valid key per tile: finite
     const float alpha = ex2(m - mn);
 #pragma unroll
     for (int i = 0; i < 4; ++i) th[i] -= mn;        // the exponent's offset rides in the row term
-    float lp = 0.f;
+    float lp4[4] = {0.f, 0.f, 0.f, 0.f};
     uint8_t* dst = half ? sP1 : sK + buf * kTileBytes;
 #pragma unroll
     for (int cl = 0; cl < 2; ++cl) {
@@ -204,7 +217,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
         const int ph = 2 * cl + (i >> 4), pw = i & 15;
         const float e = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw]);
         p[i] = (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? e : 0.f;
-        lp += p[i];
+        lp4[i & 3] += p[i];
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -216,6 +229,8 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
         *reinterpret_cast<uint4*>(dst + swz128(r, cl * 4 + g)) = v;
       }
     }
+    const float lp = (lp4[0] + lp4[1]) + (lp4[2] + lp4[3]);
+    if (kt + 1 < nkt) load_bias(kt + 1);
     m = mn;
     l = l * alpha + lp;
     fence_proxy_async();
@@ -384,49 +399,64 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   float dth[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) dth[i] = 0.f;
+  float th[4], tw[kPW];
+  // this row's relative-position terms for key tile kt (x log2 e, minus the row's log-sum-exp), loaded one tile ahead
+  auto load_bias = [&](int kt) {
+    const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = (kt % a.tiles_w) * kPW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) th[i] = (rh && kh0 + i < a.gh) ? __ldg(rh + (long long)(kh0 + i) * tn) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) : 0.f;
+  };
+  load_bias(0);
   for (int kt = 0; kt < nkt; ++kt) {
     const int buf = kt & 1;
     const int ktw = kt % a.tiles_w;
     const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = ktw * kPW;     // this thread's 4 x 16 keys
-    float th[4], tw[kPW], dtw[kPW];
+    float dtw[kPW];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) th[i] = (rh && kh0 + i < a.gh) ? __ldg(rh + (long long)(kh0 + i) * tn) * kLog2e - lse2 : -lse2;
-#pragma unroll
-    for (int i = 0; i < kPW; ++i) {
-      tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) * kLog2e : 0.f;
-      dtw[i] = 0.f;
-    }
+    for (int i = 0; i < kPW; ++i) dtw[i] = 0.f;
     const bool interior = valid_q && (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
     mbar_wait(&s_bar, kt & 1);
     __syncwarp();
     tc_fence_after();
 #pragma unroll
-    for (int cl = 0; cl < 2; ++cl) {
-      const int c = 2 * half + cl;           // 32-column chunk of the tile
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
-      tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
-      tmem_ld_wait();
-      float ds[32];
+    for (int i = 0; i < 4; ++i) { pin(th[i]); th[i] = fmaf(th[i], kLog2e, -lse2); }      // first use of the prefetched terms
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ph = 2 * cl + (i >> 4), pw = i & 15;
-        float p = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
-        if (!interior) p = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p : 0.f;
-        ds[i] = p * (__uint_as_float(rp[i]) - delta);
-        dth[ph] += ds[i];
-        dtw[pw] += ds[i];
+    for (int i = 0; i < kPW; ++i) { pin(tw[i]); tw[i] *= kLog2e; }
+    {
+      // both 32-column chunks of S and dP in flight before the one wait
+      uint32_t rs[2][32], rp[2][32];
+#pragma unroll
+      for (int cl = 0; cl < 2; ++cl) {
+        tmem_ld_32x32(tmem_s + lane_off + (2 * half + cl) * 32, rs[cl]);
+        tmem_ld_32x32(tmem_dp + lane_off + (2 * half + cl) * 32, rp[cl]);
       }
+      tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack2(ds[8 * g], ds[8 * g + 1]);
-        v.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
-        v.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
-        v.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-        *reinterpret_cast<uint4*>(sDS + half * kTileBytes + swz128(r, cl * 4 + g)) = v;
+      for (int cl = 0; cl < 2; ++cl) {
+        float ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ph = 2 * cl + (i >> 4), pw = i & 15;
+          float p = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[ph]) + tw[pw]);
+          if (!interior) p = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p : 0.f;
+          ds[i] = p * (__uint_as_float(rp[cl][i]) - delta);
+          dth[ph] += ds[i];
+          dtw[pw] += ds[i];
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack2(ds[8 * g], ds[8 * g + 1]);
+          v.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
+          v.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
+          v.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
+          *reinterpret_cast<uint4*>(sDS + half * kTileBytes + swz128(r, cl * 4 + g)) = v;
+        }
       }
     }
+    if (kt + 1 < nkt) load_bias(kt + 1);
     if (dh) {
 #pragma unroll
       for (int i = 0; i < kPW; ++i) atomicAdd(&sDtw[(kw0 + i) * kTile + r], dtw[i]);    // shared with the row's other thread
@@ -565,58 +595,78 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int tn = a.gh * a.gw;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const int khh = kh0 + 4 * half;            // this thread's 4 x 16 keys of the CTA's key tile
-  for (int qt = 0; qt < nqt; ++qt) {
-    const int buf = qt & 1;
+  float th[4], tw[kPW], delta, lse2;
+  bool valid_q;
+  // per query tile: this row's validity, delta and relative-position terms (x log2 e, minus the row's log-sum-exp) for the
+  // CTA's keys -- loaded one tile ahead
+  auto load_row = [&](int qt) {
     const int qh = (qt / a.tiles_w) * kPH + r / kPW, qw = (qt % a.tiles_w) * kPW + r % kPW;
-    const bool valid_q = qh < a.gh && qw < a.gw;
+    valid_q = qh < a.gh && qw < a.gw;
     const int qtok = valid_q ? qh * a.gw + qw : 0;
     const long long bh = (long long)b * a.heads + h;
     const float* rh = (a.rel_h && valid_q) ? a.rel_h + bh * a.gh * tn + qtok : nullptr;
     const float* rw = (a.rel_h && valid_q) ? a.rel_w + bh * a.gw * tn + qtok : nullptr;
-    const long long stat = bh * tn + qtok;
-    const float lse2 = __ldg(a.lse + stat) * kLog2e;
-    const float delta = __ldg(a.delta + stat);
-    float th[4], tw[kPW];
+    lse2 = __ldg(a.lse + bh * tn + qtok);
+    delta = __ldg(a.delta + bh * tn + qtok);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) th[i] = (rh && khh + i < a.gh) ? __ldg(rh + (long long)(khh + i) * tn) * kLog2e - lse2 : -lse2;
+    for (int i = 0; i < 4; ++i) th[i] = (rh && khh + i < a.gh) ? __ldg(rh + (long long)(khh + i) * tn) : 0.f;
 #pragma unroll
-    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) * kLog2e : 0.f;
+    for (int i = 0; i < kPW; ++i) tw[i] = (rh && kw0 + i < a.gw) ? __ldg(rw + (long long)(kw0 + i) * tn) : 0.f;
+  };
+  load_row(0);
+  for (int qt = 0; qt < nqt; ++qt) {
+    const int buf = qt & 1;
     const bool interior = valid_q && (khh + 4 <= a.gh) && (kw0 + kPW <= a.gw);
+    const bool vq = valid_q;
     mbar_wait(&s_bar, qt & 1);
     __syncwarp();
     tc_fence_after();
+    pin(lse2);
+    pin(delta);
+    {
+      const float l2 = lse2 * kLog2e;
 #pragma unroll
-    for (int cl = 0; cl < 2; ++cl) {
-      const int c = 2 * half + cl;
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem_s + lane_off + c * 32, rs);
-      tmem_ld_32x32(tmem_dp + lane_off + c * 32, rp);
-      tmem_ld_wait();
-      float p[32], ds[32];
+      for (int i = 0; i < 4; ++i) { pin(th[i]); th[i] = fmaf(th[i], kLog2e, -l2); }      // first use of the prefetched terms
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ph = 2 * cl + (i >> 4), pw = i & 15;
-        float pv = ex2(fmaf(__uint_as_float(rs[i]), a.scale_log2, th[ph]) + tw[pw]);
-        if (!interior) pv = (valid_q && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
-        p[i] = pv;
-        ds[i] = pv * (__uint_as_float(rp[i]) - delta);
+      for (int i = 0; i < kPW; ++i) { pin(tw[i]); tw[i] *= kLog2e; }
+    }
+    {
+      uint32_t rs[2][32], rp[2][32];
+#pragma unroll
+      for (int cl = 0; cl < 2; ++cl) {
+        tmem_ld_32x32(tmem_s + lane_off + (2 * half + cl) * 32, rs[cl]);
+        tmem_ld_32x32(tmem_dp + lane_off + (2 * half + cl) * 32, rp[cl]);
       }
+      tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v, w;
-        v.x = pack2(p[8 * g], p[8 * g + 1]);
-        v.y = pack2(p[8 * g + 2], p[8 * g + 3]);
-        v.z = pack2(p[8 * g + 4], p[8 * g + 5]);
-        v.w = pack2(p[8 * g + 6], p[8 * g + 7]);
-        w.x = pack2(ds[8 * g], ds[8 * g + 1]);
-        w.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
-        w.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
-        w.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-        const uint32_t off = half * kTileBytes + swz128(r, cl * 4 + g);
-        *reinterpret_cast<uint4*>(sP + off) = v;
-        *reinterpret_cast<uint4*>(sDS + off) = w;
+      for (int cl = 0; cl < 2; ++cl) {
+        float p[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ph = 2 * cl + (i >> 4), pw = i & 15;
+          float pv = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[ph]) + tw[pw]);
+          if (!interior) pv = (vq && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
+          p[i] = pv;
+          ds[i] = pv * (__uint_as_float(rp[cl][i]) - delta);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v, w;
+          v.x = pack2(p[8 * g], p[8 * g + 1]);
+          v.y = pack2(p[8 * g + 2], p[8 * g + 3]);
+          v.z = pack2(p[8 * g + 4], p[8 * g + 5]);
+          v.w = pack2(p[8 * g + 6], p[8 * g + 7]);
+          w.x = pack2(ds[8 * g], ds[8 * g + 1]);
+          w.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
+          w.z = pack2(ds[8 * g + 4], ds[8 * g + 5]);
+          w.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
+          const uint32_t off = half * kTileBytes + swz128(r, cl * 4 + g);
+          *reinterpret_cast<uint4*>(sP + off) = v;
+          *reinterpret_cast<uint4*>(sDS + off) = w;
+        }
       }
     }
+    if (qt + 1 < nqt) load_row(qt + 1);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();     // P and dS of this tile are in shared memory; every thread has finished with S and dP
