@@ -56,6 +56,26 @@ __device__ __forceinline__ float ex2(float x) {      // 2^x, one MUFU (x <= 0 he
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// CTA-wide wait on an mbarrier: ONE warp polls (with a short sleep between polls), the other seven park on the hardware
+// barrier.  Every polling warp costs issue slots whether one lane or 32 spin -- ncu on the first version of these kernels: 70 %
+// of the issue slots busy at 8 % tensor-pipe activity, most of it 256 threads spinning on `try_wait` next to the co-resident
+// CTA's exponentials.
+__device__ __forceinline__ void cta_wait(uint64_t* bar, uint32_t parity, int warp) {
+  if (warp == 0) {
+    const uint32_t addr = smem_u32(bar);
+    if (!mbar_try_wait(addr, parity)) {
+      long long t0 = clock64();
+      while (!mbar_try_wait(addr, parity)) {
+        __nanosleep(40);
+        if (clock64() - t0 > 40000000000LL) {
+          printf("aldi_b200: attention mbarrier wait timeout (block %d,%d,%d)\n", (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
 // Scheduling fence for a register value: a prefetched global load must not be consumed (and so waited for) before this point
 __device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -177,8 +197,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
     const int buf = kt & 1;
     const int kh0 = (kt / a.tiles_w) * kPH + 4 * half, kw0 = (kt % a.tiles_w) * kPW;     // this thread's 4 x 16 keys
     const bool interior = (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
-    mbar_wait(&s_bar, kt & 1);
-    __syncwarp();
+    cta_wait(&s_bar, kt & 1, warp);
     tc_fence_after();
 #pragma unroll
     for (int i = 0; i < 4; ++i) { pin(th[i]); th[i] *= kLog2e; }        // first use of the prefetched terms: after the wait
@@ -190,11 +209,17 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
       uint32_t raw[32];
       tmem_ld_32x32(tmem_s + lane_off + (2 * half + cl) * 32, raw);
       tmem_ld_wait();
+      if (interior) {        // uniform branch: interior tiles (all but the last row / column of patches) skip the masks
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ph = 2 * cl + (i >> 4), pw = i & 15;
-        const float s2 = fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw];
-        mt4[i & 3] = fmaxf(mt4[i & 3], (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? s2 : -INFINITY);
+        for (int i = 0; i < 32; ++i)
+          mt4[i & 3] = fmaxf(mt4[i & 3], fmaf(__uint_as_float(raw[i]), a.scale_log2, th[2 * cl + (i >> 4)]) + tw[i & 15]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ph = 2 * cl + (i >> 4), pw = i & 15;
+          const float s2 = fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw];
+          mt4[i & 3] = fmaxf(mt4[i & 3], ((kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? s2 : -INFINITY);
+        }
       }
     }
     const float mt = fmaxf(fmaxf(mt4[0], mt4[1]), fmaxf(mt4[2], mt4[3]));
@@ -212,12 +237,20 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
       tmem_ld_32x32(tmem_s + lane_off + (2 * half + cl) * 32, raw);
       tmem_ld_wait();
       float p[32];
+      if (interior) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ph = 2 * cl + (i >> 4), pw = i & 15;
-        const float e = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw]);
-        p[i] = (interior || ((kh0 + ph < a.gh) && (kw0 + pw < a.gw))) ? e : 0.f;
-        lp4[i & 3] += p[i];
+        for (int i = 0; i < 32; ++i) {
+          p[i] = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[2 * cl + (i >> 4)]) + tw[i & 15]);
+          lp4[i & 3] += p[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ph = 2 * cl + (i >> 4), pw = i & 15;
+          const float e = ex2(fmaf(__uint_as_float(raw[i]), a.scale_log2, th[ph]) + tw[pw]);
+          p[i] = ((kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? e : 0.f;
+          lp4[i & 3] += p[i];
+        }
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -249,8 +282,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
       if (kt + 1 < nkt) issue_s(kt + 1);      // runs behind P V while the rows below read O back
     }
     __syncwarp();
-    mbar_wait(&o_bar, kt & 1);
-    __syncwarp();
+    cta_wait(&o_bar, kt & 1, warp);
     tc_fence_after();
     if (tid == 0 && kt + 2 < nkt) load_kv(kt + 2);     // P V has finished with this buffer (V and the P chunk in the K slot)
     __syncwarp();
@@ -417,8 +449,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < kPW; ++i) dtw[i] = 0.f;
     const bool interior = valid_q && (kh0 + 4 <= a.gh) && (kw0 + kPW <= a.gw);
-    mbar_wait(&s_bar, kt & 1);
-    __syncwarp();
+    cta_wait(&s_bar, kt & 1, warp);
     tc_fence_after();
 #pragma unroll
     for (int i = 0; i < 4; ++i) { pin(th[i]); th[i] = fmaf(th[i], kLog2e, -lse2); }      // first use of the prefetched terms
@@ -436,14 +467,24 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 #pragma unroll
       for (int cl = 0; cl < 2; ++cl) {
         float ds[32];
+        if (interior) {        // uniform branch: no per-key masks away from the grid's last row / column of patches
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[2 * cl + (i >> 4)]) + tw[i & 15]);
+            ds[i] = p * (__uint_as_float(rp[cl][i]) - delta);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ph = 2 * cl + (i >> 4), pw = i & 15;
+            const float p = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[ph]) + tw[pw]);
+            ds[i] = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p * (__uint_as_float(rp[cl][i]) - delta) : 0.f;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * cl + (i >> 4), pw = i & 15;
-          float p = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[ph]) + tw[pw]);
-          if (!interior) p = (valid_q && (kh0 + ph < a.gh) && (kw0 + pw < a.gw)) ? p : 0.f;
-          ds[i] = p * (__uint_as_float(rp[cl][i]) - delta);
-          dth[ph] += ds[i];
-          dtw[pw] += ds[i];
+          dth[2 * cl + (i >> 4)] += ds[i];
+          dtw[i & 15] += ds[i];
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -484,8 +525,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       if (kt + 1 < nkt) issue_s(kt + 1);
     }
     __syncwarp();
-    mbar_wait(&o_bar, kt & 1);    // dS buffer and this tile's K / V buffers are free again
-    __syncwarp();
+    cta_wait(&o_bar, kt & 1, warp);    // dS buffer and this tile's K / V buffers are free again
     if (tid == 0 && kt + 2 < nkt) load_kv(kt + 2);
     __syncwarp();
   }
@@ -618,8 +658,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int buf = qt & 1;
     const bool interior = valid_q && (khh + 4 <= a.gh) && (kw0 + kPW <= a.gw);
     const bool vq = valid_q;
-    mbar_wait(&s_bar, qt & 1);
-    __syncwarp();
+    cta_wait(&s_bar, qt & 1, warp);
     tc_fence_after();
     pin(lse2);
     pin(delta);
@@ -641,13 +680,20 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
       for (int cl = 0; cl < 2; ++cl) {
         float p[32], ds[32];
+        if (interior) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ph = 2 * cl + (i >> 4), pw = i & 15;
-          float pv = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[ph]) + tw[pw]);
-          if (!interior) pv = (vq && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
-          p[i] = pv;
-          ds[i] = pv * (__uint_as_float(rp[cl][i]) - delta);
+          for (int i = 0; i < 32; ++i) {
+            p[i] = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[2 * cl + (i >> 4)]) + tw[i & 15]);
+            ds[i] = p[i] * (__uint_as_float(rp[cl][i]) - delta);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ph = 2 * cl + (i >> 4), pw = i & 15;
+            const float pv = ex2(fmaf(__uint_as_float(rs[cl][i]), a.scale_log2, th[ph]) + tw[pw]);
+            p[i] = (vq && (khh + ph < a.gh) && (kw0 + pw < a.gw)) ? pv : 0.f;
+            ds[i] = p[i] * (__uint_as_float(rp[cl][i]) - delta);
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -683,8 +729,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (qt + 1 < nqt) issue_s(qt + 1);
     }
     __syncwarp();
-    mbar_wait(&o_bar, qt & 1);
-    __syncwarp();
+    cta_wait(&o_bar, qt & 1, warp);
     if (tid == 0 && qt + 2 < nqt) load_q(qt + 2);
     __syncwarp();
   }
