@@ -325,7 +325,9 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQKV, const TcArgs a) {
 // ---------------------------------------------------------------------------------------------------------------------
 // backward, query side: dq, drelpos, delta.  One CTA per SM (TMEM: S 128 + dP 128 + dQ 64 columns).
 // ---------------------------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int dq_smem_bytes(int tiles_w) { return 8 * kTileBytes + tiles_w * kPW * kTile * 4 + 1024; }
+__host__ __device__ constexpr int dq_smem_bytes(int tiles_w) {
+  return 8 * kTileBytes + tiles_w * kPW * kTile * 4 + kPW * kTile * 4 + 1024;      // tiles, column-sum table, exchange buffer
+}
 
 __global__ void __launch_bounds__(kCompute, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const TcArgs a) {
@@ -344,6 +346,8 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int qh0 = (qt / a.tiles_w) * kPH, qw0 = (qt % a.tiles_w) * kPW;
   const int nkt = a.tiles_h * a.tiles_w;
+  // the upper half's per-tile column sums cross to the row's lower-half thread here (shared-memory float atomics are CAS loops)
+  float* sXw = sDtw + a.tiles_w * kPW * kTile;                   // [16][row]
   constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 128, 0, 0);
   constexpr uint32_t idesc_dq = make_idesc_bf16(kTile, 64, 0, 1);
 
@@ -499,8 +503,10 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     }
     if (kt + 1 < nkt) load_bias(kt + 1);
     if (dh) {
+      if (half) {
 #pragma unroll
-      for (int i = 0; i < kPW; ++i) atomicAdd(&sDtw[(kw0 + i) * kTile + r], dtw[i]);    // shared with the row's other thread
+        for (int i = 0; i < kPW; ++i) sXw[i * kTile + r] = dtw[i];
+      }
       if (ktw == a.tiles_w - 1) {      // this band of key rows is complete
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -525,6 +531,10 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       if (kt + 1 < nkt) issue_s(kt + 1);
     }
     __syncwarp();
+    if (dh && !half) {      // one owner per (key column, row): plain read-modify-write; the barrier inside the wait below
+#pragma unroll                // separates these reads from the next tile's writes of the exchange buffer
+      for (int i = 0; i < kPW; ++i) sDtw[(kw0 + i) * kTile + r] += dtw[i] + sXw[i * kTile + r];
+    }
     cta_wait(&o_bar, kt & 1, warp);    // dS buffer and this tile's K / V buffers are free again
     if (tid == 0 && kt + 2 < nkt) load_kv(kt + 2);
     __syncwarp();
