@@ -295,3 +295,62 @@ def test_vitdet_backbone_bf16_tracks_fp32():
     cos = float((a * b).sum() / (a.norm() * b.norm()))
     assert cos > 0.995, cos
     assert abs(float(a.norm() / b.norm()) - 1) < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] shape
+# ---------------------------------------------------------------------------------------------------------------------
+FULL = dict(embed_dim=768, depth=2, num_heads=12, drop_path_rate=0.0, window_block_indexes=(0,), lr_decay_rate=1.0)
+
+
+def test_vitdet_b_blocks_at_the_baseline_shape_match_oracle():
+    """ViT-B widths (768 channels, 12 heads, hidden 3072) on a 1024 x 1024 image = the 64 x 64 token grid of BASELINE
+    configs[2]: one windowed block (25 windows of 14 x 14 with zero-padded edges) and one global block (4096 tokens, the
+    127-row relative-position tables at their native length), then the SimpleFeaturePyramid -- the tile variants, TMA patch
+    geometry and launch sizes the benchmark runs.  fp32 parity mode against the float64 oracle (pyramid + every parameter
+    gradient), and the benchmarked bf16 tcgen05 path against the fp32 mode."""
+    from aldi_b200 import vit
+    dev = _dev()
+    layout = vit.ViTLayout(img_size=1024, **FULL)
+    sd = vit.synthetic_state_dict(layout, seed=5, rel_pos_std=0.2)
+    g = torch.Generator().manual_seed(6)
+    for k in sd:
+        if sd[k].dim() == 1:
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+    img = torch.randint(0, 256, (1, 3, 1024, 1024), generator=g, dtype=torch.uint8)
+    sizes = torch.tensor([[1024, 1024]], dtype=torch.int32, device=dev)
+    from oracle import vit_ref
+    net = vit_ref.ViT(img_size=1024, embed_dim=768, depth=2, num_heads=12, drop_path_rate=0.0, window_block_indexes=(0,))
+    ora = vit_ref.SimpleFeaturePyramid(net)
+    ora.load_state_dict(sd, strict=True)
+    ora = ora.double().train()
+    x = (img.double() - torch.tensor(MEAN).view(1, 3, 1, 1)) / torch.tensor(STD).view(1, 3, 1, 1)
+    ref = ora(x)
+    gs, loss = {}, 0.0
+    for name in ("p2", "p3", "p4", "p5"):
+        r = ref[name].permute(0, 2, 3, 1)
+        gs[name] = torch.randn(r.shape, generator=g)
+        loss = loss + (r * gs[name].double()).sum()
+    loss.backward()
+    res = {}
+    for mode in ("fp32", "bf16"):
+        net_d = vit.ViTDetBackbone(sd, size=None, dtype=mode, device=dev, img_size=1024, pixel_mean=MEAN, pixel_std=STD, **FULL)
+        outs = net_d.forward(img.to(dev), sizes, keep_masks=None, save=True)
+        net_d.backward({k: v.to(dev, outs[k].dtype) for k, v in gs.items()})
+        res[mode] = ({k: v.float().cpu() for k, v in outs.items()}, layout.unpack(net_d.grad))
+        del net_d, outs
+        torch.cuda.empty_cache()
+    for name in ("p2", "p3", "p4", "p5"):
+        r = ref[name].permute(0, 2, 3, 1).detach()
+        assert _rel(res["fp32"][0][name], r) < 2e-4, name
+        assert _rel(res["bf16"][0][name], r) < 6e-2, name
+    bad = {}
+    cos_num = cos_a = cos_b = 0.0
+    for k, p in ora.named_parameters():
+        e = _rel(res["fp32"][1][k], p.grad)
+        if e > 1e-3:
+            bad[k] = e
+        a, b = res["bf16"][1][k].double().flatten(), p.grad.flatten()
+        cos_num += float(a @ b); cos_a += float(a @ a); cos_b += float(b @ b)
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    assert cos_num / (cos_a * cos_b) ** 0.5 > 0.995, cos_num / (cos_a * cos_b) ** 0.5
