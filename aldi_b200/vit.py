@@ -503,15 +503,13 @@ class ViTDetBackbone:
         ops.call("aldi_layerscale_backward", dy, dy, None, keep, n * h * w, h * w, self.C, cp, self.dtc, du, None)
         return du
 
-    def _convt(self, name, x, cout, save_list):
+    def _convt(self, name, x, cout):
         """ConvTranspose2d(kernel 2, stride 2): GEMM to (dy, dx, cout) columns, then depth-to-space."""
         n, h, w, _ = x.shape
         rows = self.gemm[name].forward(x)
         cp = _pad64(cout)
         fine = (torch.zeros if cp != cout else torch.empty)(n, 2 * h, 2 * w, cp, device=x.device, dtype=x.dtype)
         ops.call("aldi_space_to_depth", rows, fine, n, h, w, 2, cout, cp, rows.shape[3], self.dtc, 1)
-        if save_list is not None:
-            save_list.append((name, x, cout))
         return fine
 
     def _convt_bwd(self, name, x, cout, dfine, dx=None, accumulate=False):
@@ -582,16 +580,16 @@ class ViTDetBackbone:
         outs = {}
         P = {} if save else None
         # p2: ConvT -> LN -> GELU -> ConvT -> 1x1 + LN -> 3x3 + LN
-        t0 = self._convt("simfp_2.0", x, C // 2, None)
+        t0 = self._convt("simfp_2.0", x, C // 2)
         l0, st0 = self._ln(t0, "simfp_2.1", C // 2)
         g0 = torch.empty_like(l0)
         ops.call("aldi_gelu", l0, None, g0, l0.numel(), self.dtc)
-        t1 = self._convt("simfp_2.3", g0, C // 4, None)
+        t1 = self._convt("simfp_2.3", g0, C // 4)
         c1, s1 = self._conv_norm("simfp_2.4", t1)
         outs["p2"], s2 = self._conv_norm("simfp_2.5", c1)
         if save:
             P[2] = (t0, st0, l0, g0, s1, s2)
-        t0 = self._convt("simfp_3.0", x, C // 2, None)
+        t0 = self._convt("simfp_3.0", x, C // 2)
         c1, s1 = self._conv_norm("simfp_3.1", t0)
         outs["p3"], s2 = self._conv_norm("simfp_3.2", c1)
         if save:

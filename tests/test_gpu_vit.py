@@ -3,7 +3,6 @@ vit.py + aldi/backbone.py:21-64 and is parity-unpinned, see its header): the sma
 arithmetic modes (CUDA-core fp32 = parity mode, tcgen05 bf16 = the benchmarked mode) and the whole backbone forward +
 backward (pyramid outputs and every parameter gradient)."""
 import ctypes
-import math
 
 import pytest
 import torch
