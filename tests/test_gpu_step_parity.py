@@ -174,6 +174,31 @@ def test_empty_pseudo_labels(dtype):
     check_grads(step, student)
 
 
+@pytest.mark.parametrize("loss_type,cls_tmp,obj_tmp", [("KL", 2.0, 1.5), ("CE", 0.5, 2.0)])
+def test_distillation_kl_and_temperatures_match_oracle(loss_type, cls_tmp, obj_tmp):
+    """DOMAIN_ADAPT.CLS_LOSS_TYPE "KL" (F.kl_div, batchmean) and DISTILL.CLS_TMP / OBJ_TMP != 1 (aldi/distill.py:199-204,
+    245-262: teacher logits sharpened / softened before the sigmoid / softmax): the fused loss kernels' other branches,
+    losses and every gradient of a distillation-only step against the oracle."""
+    sd_s, sd_t, ls, uw, us = pu.make_inputs(53, 0, 2, 96, 128)
+    pu.install_device_sampler(pu.predict_seed_log(1234, 0, 1))
+    student, teacher = pu.oracle_models(sd_s, sd_t)
+    dist = aldi_ref.ALDIDistiller(teacher, student, cls_temperature=cls_tmp, obj_temperature=obj_tmp, cls_loss_type=loss_type,
+                                  **pu.SOFT)
+    prop_log = pu.log_student_proposals(student)
+    uw_o = pu.to_d2(uw, False)
+    with d2.EventStorage():
+        ora = aldi_ref.run_model_labeled_unlabeled(student, dist, (None, None, uw_o, pu.to_d2(us, False)), 2, False,
+                                                   lambda l: l.backward())
+    d2.set_sample_chooser(None)
+    override = [pu.pseudo_to_device([d["instances"] for d in uw_o], "cuda")]
+    step, dev_losses = run_device(sd_s, sd_t, (None, None, uw, us), pseudo_override=override, ims_per_gpu=2,
+                                  cls_loss_type=loss_type, cls_temperature=cls_tmp, obj_temperature=obj_tmp,
+                                  proposal_override=pu.proposal_override(prop_log, 0, 1))
+    check_losses(dev_losses, ora)
+    worst = check_grads(step, student)
+    print("distillation %s T=(%g, %g): losses" % (loss_type, cls_tmp, obj_tmp), dev_losses, "worst grad rel err", worst)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16x6"])
 def test_ragged_batch_and_empty_gt_match_oracle(dtype):
     """Edge cases of the batch format: images of different sizes share a zero-padded canvas (detectron2 ImageList),
