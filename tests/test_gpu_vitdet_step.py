@@ -240,3 +240,31 @@ def test_vitdet_trainer_runs_on_the_reference_cfg_keys(monkeypatch):
         DetectionCheckpointerWithEMA(other.step_impl, tmp).resume_or_load("", resume=True)
         for a, b in ((other.step_impl.student, trainer.step_impl.student), (other.step_impl.teacher, trainer.step_impl.teacher)):
             assert torch.equal(a.flat, b.flat) and torch.equal(a.bottom_up.flat, b.bottom_up.flat)
+
+
+def test_vitdet_l_configuration_steps():
+    """`build_vitdet_l_backbone` (aldi/backbone.py:45-64) at its real size -- embed_dim 1024, depth 24, 16 heads, DropPath
+    0.4, global attention in blocks 5 / 11 / 17 / 23, no layer-wise lr decay -- through two whole ALDI++ iterations in bf16 on
+    a small image (16 x 16 tokens: four zero-padded 14 x 14 windows, the 127-row global tables resampled to 31 rows)."""
+    _need_gpu()
+    from aldi_b200 import synth_data
+    from aldi_b200.train_step import B200TrainStep, StepConfig, synthetic_state_dict_for
+    cfg = StepConfig(dtype="bf16", ims_per_gpu=1, backbone="vitdet_l", pixel_mean=MEAN, pixel_std=STD, optimizer="ADAMW",
+                     base_lr=1e-4, weight_decay=0.1, ema_start_iter=0)
+    sd = synthetic_state_dict_for(cfg, 2)
+    assert sd["backbone.net.blocks.23.attn.qkv.weight"].shape == (3072, 1024) and "backbone.net.blocks.24.norm1.weight" not in sd
+    assert sd["backbone.net.blocks.5.attn.rel_pos_h"].shape == (127, 64) and sd["backbone.net.blocks.4.attn.rel_pos_h"].shape == (27, 64)
+    step = B200TrainStep(cfg, sd)
+    bu = step.student.bottom_up
+    assert bu.heads == 16 and bu.depth == 24 and len(bu.drop_rates) == 48 and abs(bu.drop_rates[-1] - 0.4) < 1e-6
+    assert all(f == 1.0 for _, _, f, _ in bu.opt_segments())
+    before = bu.flat.clone()
+    ls, uw, us = synth_data.synthetic_batch(3, 1, 1, 256, 256)
+    random.seed(9)
+    hist = [dict(step.step((None, ls, uw, us)).items()) for _ in range(2)]
+    torch.cuda.synchronize()
+    assert all(v == v and abs(v) != float("inf") for h in hist for v in h.values()), hist
+    moved = (bu.flat - before).abs()
+    off, n, _ = bu.layout.entries["net.blocks.23.mlp.fc2.weight"]
+    assert float(moved[off:off + n].max()) > 0 and float(moved.max()) < 1e-2          # AdamW steps of ~lr per element
+    assert not torch.equal(step.teacher.bottom_up.flat, bu.flat)                       # the EMA teacher trails
