@@ -171,13 +171,34 @@ def cpu_model_name():
 
 
 def cpu_reference_step_factory(threads):
-    """The reference path restated on CPU (oracle port): one (source + target) image pair per step."""
+    """The reference path restated on CPU (oracle port) for the SELECTED config: one (source + target) image pair per step,
+    IMS_PER_GPU 1.  rcnn_r50: R50-FPN; vitdet_b: ViTDet-B (oracle/vit_ref.py under the ViTDet heads); convnext_l: ConvNeXt-L
+    FPN (oracle/convnext_ref.py).  The optimizer of the CPU arm is SGD at a tiny learning rate for all three (its cost is
+    noise next to the forward / backward passes); DropPath is drawn as all-keep for the two stochastic-depth backbones (a
+    per-sample scale: no arithmetic to speak of)."""
     import torch
-    from aldi_b200 import arch, synth_data
+    from aldi_b200 import synth_data
+    from aldi_b200.train_step import StepConfig, synthetic_state_dict_for
     from oracle import aldi_ref, d2_rcnn as d2
     torch.set_num_threads(threads)
-    sd = arch.synthetic_state_dict(0)
-    student = aldi_ref.ALDI(num_classes=8)
+    kw, refill = {}, lambda: None
+    if CONFIG == "vitdet_b":
+        from oracle import vit_ref
+        scfg = StepConfig(backbone="vitdet_b", optimizer="ADAMW")
+        net = vit_ref.ViT(drop_path_rate=0.0)
+        kw = dict(pixel_mean=(123.675, 116.28, 103.53), pixel_std=(58.395, 57.12, 57.375), backbone=vit_ref.SimpleFeaturePyramid(net),
+                  rpn_conv_dims=(-1, -1), box_fc_dims=(1024,), box_conv_dims=(256,) * 4, box_conv_norm="LN")
+    elif CONFIG == "convnext_l":
+        from oracle import convnext_ref
+        depths, dims = CONVNEXT_L
+        scfg = StepConfig(backbone="convnext", convnext_depths=depths, convnext_dims=dims, optimizer="ADAMW")
+        bu = convnext_ref.ConvNeXt(depths=depths, dims=dims, drop_path_rate=0.0, layer_scale_init_value=1e-6)
+        kw = dict(bottom_up=bu, fpn_in_features=(0, 1, 2, 3), pixel_std=(57.375, 57.12, 58.395),
+                  anchor_sizes=((64,), (128,), (256,), (512,), (1024,)))
+    else:
+        scfg = StepConfig()
+    sd = synthetic_state_dict_for(scfg, 0)
+    student = aldi_ref.ALDI(num_classes=8, **kw)
     student.load_state_dict(sd)
     trainer = aldi_ref.OracleTrainer(student, distill_kwargs=dict(do_cls_dst=True, do_obj_dst=True, do_rpn_reg_dst=True,
                                                                   do_roih_reg_dst=True), ims_per_gpu=1,
@@ -220,8 +241,8 @@ def run_reference(args):
         imgs += step()
     dt = time.perf_counter() - t0
     value = imgs / dt
-    sample = ("oracle port (oracle/aldi_ref.py on torch CPU fp32), %d step(s) of ONE (source+target) 1024x2048 image pair "
-              "with IMS_PER_GPU 1 (requested %d steps; bounded to ~%.0f s)" % (steps, args.steps, budget_s))
+    sample = ("oracle port (oracle/aldi_ref.py on torch CPU fp32), %d step(s) of ONE (source+target) %dx%d image pair "
+              "with IMS_PER_GPU 1 (requested %d steps; bounded to ~%.0f s)" % (steps, H, W, args.steps, budget_s))
     line = {"metric": METRIC, "value": value, "unit": "images/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm + 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -568,7 +589,7 @@ def run_ours(args):
     host_floor_ms = (time.perf_counter() - t0) / 3 * 1e3
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and CONFIG == "rcnn_r50":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cstep = cpu_reference_step_factory(threads)
         t0 = time.perf_counter()
@@ -581,8 +602,8 @@ def run_ours(args):
         cpu_baseline = {"value": n / dt, "unit": "images/s", "cores": threads, "kind": "port",
                         "cpu_model": cpu_model_name(), "os_cpu_count": os.cpu_count(),
                         "sample": "oracle port of the reference step (oracle/aldi_ref.py, torch CPU fp32, %d threads), ONE "
-                                  "(source+target) 1024x2048 pair per step: 1 warm-up step (%.1f s) + %d timed step(s) (%.1f s)"
-                                  % (threads, t_warm, k, dt)}
+                                  "(source+target) %dx%d pair per step: 1 warm-up step (%.1f s) + %d timed step(s) (%.1f s)"
+                                  % (threads, H, W, t_warm, k, dt)}
     graph_replays, peak_mem_gb = step.graph_replays, round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)
     deviation = None
     if rank == 0 and world == 1 and not args.no_deviation and CONFIG == "rcnn_r50":
