@@ -1,17 +1,22 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement of the ViTDet backbone the reference builds in aldi/backbone.py:21-64.
 
-Only tests/ may import this.  **PARITY UNPINNED**: `build_vitdet_b_backbone` / `build_vitdet_l_backbone` instantiate
-Detectron2's `SimpleFeaturePyramid(net=ViT(...))` from the LazyConfig `common/models/mask_rcnn_vitdet.py`; that code
-lives in the third-party `detectron2` package (`pyproject.toml:18`, a git dependency with no pinned commit) which is
-absent from /root/reference and cannot be installed here, and the reference holds no golden vectors for it.  What is
-restated below is detectron2 v0.6's `modeling/backbone/vit.py` + `modeling/backbone/utils.py` as published, with the
-reference's own changes applied on top:
+Only tests/ may import this.  **Parity: the ViT trunk is PINNED to an independent published port, the pyramid is UNPINNED.**
+`build_vitdet_b_backbone` / `build_vitdet_l_backbone` instantiate Detectron2's `SimpleFeaturePyramid(net=ViT(...))` from the
+LazyConfig `common/models/mask_rcnn_vitdet.py`; that code lives in the third-party `detectron2` package (`pyproject.toml:18`, a
+git dependency with no pinned commit) which is absent from /root/reference and cannot be installed here, and the reference holds
+no golden vectors for it.  What is restated below is detectron2 v0.6's `modeling/backbone/vit.py` + `modeling/backbone/utils.py`
+as published, with the reference's own changes applied on top:
   * `square_pad = 0` (aldi/backbone.py:40,48) -- images are padded to the size divisibility only, not to a square;
   * `checkpointed_vit_forward` (aldi/backbone.py:21-35): patch_embed -> + get_abs_pos(pos_embed) -> blocks -> NCHW,
     with per-block activation checkpointing (`VIT.USE_ACT_CHECKPOINT`), which changes memory, not values;
   * ViT-L: embed_dim 1024, depth 24, 16 heads, drop_path 0.4, global attention in blocks 5, 11, 17, 23 (:50-58).
-tests/test_vit_oracle.py checks the pieces against independent formulations (dense relative-position bias, torch's
-scaled_dot_product_attention, partition round trips) since nothing of the reference's can be executed for this path.
+The pin: `ViT` (patch embedding, bicubic pos_embed, windowed / global blocks, decomposed relative position with resampled
+tables, zero-padded windows) reproduces HuggingFace transformers' `VitDetModel` -- a port of the same detectron2 file made by
+other hands -- to 1e-12 in float64 on outputs and every parameter gradient (tests/golden/make_vit_golden.py executes it,
+tests/test_vit_golden.py replays the committed vectors and, when transformers is importable, the live model).
+`SimpleFeaturePyramid`, `get_vit_lr_decay_rate` and the ViTDet heads in d2_rcnn.py have no such counterpart: restated only;
+tests/test_vit_oracle.py checks them against independent formulations (dense relative-position bias, torch's
+scaled_dot_product_attention, partition round trips).
 
 Module tree and parameter names are Detectron2's (`net.pos_embed`, `net.patch_embed.proj`, `net.blocks.{i}.attn.qkv`,
 `...attn.rel_pos_h`, `simfp_{2..5}.{k}`, `...norm.weight`), so released ViTDet checkpoints would load with strict=True.
